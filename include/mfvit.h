@@ -1,0 +1,238 @@
+/* mfvit.h - C ABI of libmfvit.so: hand-written sm_100a kernels for the MF-ViT CA training hot path.
+ *
+ * The reference (endiqq/Multi-Feature-ViT) has no FFI of its own: its hot path is PyTorch library calls made from
+ * Python nn.Modules.  This header is the boundary a maintainer binds *below* that module surface; each entry point
+ * names the reference call-site(s) it replaces (paths relative to the reference tree; MAIN_CA / MAIN_PRE / FUS / MOD /
+ * BLD are the aliases defined in SURVEY.md).  See INTEGRATION.md for the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MFV_ERR_* for rejected arguments (shape / alignment / arch), or a
+ *     positive cudaError_t.  There is no CPU fallback and no alternate backend: on a non-sm_100 device mfv_init fails.
+ *   - all pointers are device pointers owned by the caller (PyTorch tensors); the library allocates nothing
+ *     persistent, never synchronises the stream and is safe under CUDA-graph capture.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - bf16 = __nv_bfloat16 storage, f32 = float.  "G" is the group count: the two MF-ViT branches (CXR, enhanced) are
+ *     processed by one launch with per-group weights (G = 2), a single ViT uses G = 1.
+ */
+#ifndef MFVIT_H_
+#define MFVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFV_ABI_VERSION 1
+
+/* ---- runtime ------------------------------------------------------------------------------------------------- */
+int mfv_abi_version(void);
+/* Binds the library to `device`; checks compute capability 10.x, resolves cuTensorMapEncodeTiled. */
+int mfv_init(int device);
+const char* mfv_strerror(int code);
+int mfv_num_sms(void);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) ----------------------------------------------------------------------------------
+ * C[g][m][n] = epilogue( sum_k A[g][m][k] * B[g][n][k] ), bf16 operands, fp32 accumulation in TMEM.
+ * Replaces: timm Block qkv/proj/fc1/fc2 nn.Linear forward + autograd backward (absent vits.py; same math restated at
+ * MOD:45-63 and MOD:23-34), the cuBLASLt calls behind them, and the bias/GELU/residual ATen kernels (SURVEY K3,K5,K6).
+ * Operand (m,k) of A lives at A + g*a_gstride + (a_mn_major ? k*lda + m : m*lda + k); likewise B with (n,k).        */
+enum {
+  MFV_EPI_BF16 = 0,       /* C(bf16)  = acc + bias                                           (qkv, dgrad)        */
+  MFV_EPI_GELU = 1,       /* C(bf16)  = u = acc + bias ; C2(bf16) = gelu_erf(u)             (fc1)                */
+  MFV_EPI_RESID_F32 = 2,  /* C(f32)   = acc + bias + aux(f32)                               (proj, fc2)          */
+  MFV_EPI_DGELU = 3,      /* C(bf16)  = acc * gelu_erf'(aux(bf16) = u)                      (fc2 dgrad)          */
+  MFV_EPI_F32 = 4,        /* C(f32)   = acc + bias                                                               */
+  MFV_EPI_ATOMIC_F32 = 5  /* C(f32)  += acc  (red.global.add; split-K weight gradients)                          */
+};
+typedef struct {
+  const void* A;
+  const void* B;
+  void* C;
+  void* C2;
+  const void* bias; /* f32 [G][N] or NULL */
+  const void* aux;
+  int64_t M, N, K, G;
+  int64_t lda, ldb, ldc;                 /* elements */
+  int64_t a_gstride, b_gstride, c_gstride; /* elements between groups */
+  int64_t aux_ld, aux_gstride, bias_gstride;
+  int32_t a_mn_major, b_mn_major; /* 0: reduction dim contiguous (K-major), 1: M/N dim contiguous */
+  int32_t epilogue;
+  int32_t splits;  /* split-K factor (only with MFV_EPI_ATOMIC_F32) */
+  int32_t block_n; /* 0 = auto, else 64/128/256 */
+  int32_t reserved;
+} mfv_gemm_args;
+int mfv_gemm(const mfv_gemm_args* args, void* stream);
+
+/* ---- LayerNorm ------------------------------------------------------------------------------------------------------
+ * Replaces nn.LayerNorm(384, eps=1e-6) x25 per branch in the absent timm ViT, PreNorm's LayerNorm (MOD:15-21).
+ * x f32 [G][rows][C] -> y bf16 (GEMM operand) and/or y32 f32; mean/rstd f32 [G][rows] saved for backward.
+ * gamma/beta f32 [G][C] (group stride gb_gstride elements).                                                          */
+int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                      float* rstd, int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, float eps, void* stream);
+/* dx = dres (optional residual-path gradient, f32) + LN'(dy); dy is bf16 (dy_bf16) or f32 (dy_f32).
+ * Writes dx as f32 and (optionally) a bf16 copy that feeds the next dgrad/wgrad GEMMs.
+ * dgamma/dbeta f32 [G][C] are ACCUMULATED (+=) with red.global.add.                                                   */
+int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x, const float* mean,
+                      const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                      int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, void* stream);
+
+/* ---- fused softmax self-attention -----------------------------------------------------------------------------------
+ * Replaces timm Attention: q@k^T*scale -> softmax -> @v and the transpose copies around it (same math
+ * MOD:52-64).  qkv bf16 [NB][S][3][H][D] (the qkv GEMM's natural output), o bf16 [NB][S][H][D], lse f32 [NB][H][S].
+ * D in {32, 64}; any S >= 1 (197 @224^2, 577 @384^2).                                                                 */
+int mfv_attn_fwd(const void* qkv, void* o, float* lse, int64_t NB, int64_t S, int64_t H, int64_t D, float scale,
+                 void* stream);
+/* dqkv bf16 [NB][S][3][H][D]; delta f32 [NB][H][S] is scratch (rowsum(dO*O)).                                          */
+int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, void* dqkv,
+                 int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream);
+
+/* ---- patch embedding -----------------------------------------------------------------------------------------------
+ * Replaces timm PatchEmbed Conv2d(3,C,k=16,s=16)+flatten+transpose, cls-token concat and pos-embed add
+ * (commented restatement FUS:197-221, crossvit.py:130-146).
+ * mfv_patchify: img f32 [G][B][3][HW][HW] -> patches bf16 [G][B*np][768] (k = c*256 + i*16 + j), np = (HW/16)^2.
+ * The GEMM itself is mfv_gemm; mfv_embed_finish writes tokens x f32 [G][B][np+1][C]:
+ *   row 0 = cls + pos[0], row 1+p = acc[p] + bias + pos[1+p].                                                         */
+int mfv_patchify(const float* img, void* patches, int64_t GB, int64_t HW, void* stream);
+int mfv_embed_finish(const float* acc, const float* bias, const float* cls, const float* pos, float* x, int64_t G,
+                     int64_t B, int64_t np, int64_t C, int64_t p_gstride, void* stream);
+/* backward of the above: dacc bf16 [G][B*np][C] (for the conv weight gradient GEMM), dbias/dcls accumulated.
+ * (pos_embed is a fixed sin-cos table, requires_grad=False.)                                                          */
+int mfv_embed_finish_bwd(const float* dx, void* dacc_bf16, float* dbias, float* dcls, int64_t G, int64_t B, int64_t np,
+                         int64_t C, int64_t p_gstride, void* stream);
+
+/* ---- column sums (bias gradients) ----------------------------------------------------------------------------------
+ * out f32 [G][C] += sum over rows of x bf16 [G][rows][C]                                                              */
+int mfv_colsum_bf16(const void* x, float* out, int64_t G, int64_t rows, int64_t C, int64_t out_gstride, void* stream);
+
+/* ---- CLS-query cross-attention fusion (single kernel forward, single kernel backward) ---------------------------------
+ * Replaces Fus_CrossViT.forward after the backbones (FUS:137-157), MultiScaleTransformerEncoder.forward (FUS:35-65),
+ * PreNorm (MOD:15-21), CrossAttention (MOD:123-137), both mlp heads and both backbone heads.
+ * tok f32 [2][B][S][C] final-normed tokens of (cxr, enh).  Parameter block layout: see mfv_fusion_params.           */
+typedef struct {
+  /* index d = 0: the CXR-CLS query (cross_attn_layers.0.0 + LayerNorm .3, mlp_head_cxr, vit_cxr.head)
+   * index d = 1: the ENH-CLS query (cross_attn_layers.0.2 + LayerNorm .1, mlp_head_enh, vit_enh.head)              */
+  const float* ln1_w[2]; const float* ln1_b[2];     /* PreNorm LayerNorm, eps 1e-5 */
+  const float* wq[2]; const float* wk[2]; const float* wv[2]; /* [C][C], no bias */
+  const float* proj_w[2]; const float* proj_b[2];
+  const float* ln2_w[2]; const float* ln2_b[2];     /* post LayerNorm, eps 1e-6 */
+  const float* head_w[2]; const float* head_b[2];   /* mlp_head_{cxr,enh}: [NC][C] */
+  const float* vhead_w[2]; const float* vhead_b[2]; /* backbone heads: [NC][C] (may be NULL -> x_* not computed) */
+} mfv_fusion_params;
+typedef struct {
+  float* ln1_w[2]; float* ln1_b[2];
+  float* wq[2]; float* wk[2]; float* wv[2];
+  float* proj_w[2]; float* proj_b[2];
+  float* ln2_w[2]; float* ln2_b[2];
+  float* head_w[2]; float* head_b[2];
+  float* vhead_w[2]; float* vhead_b[2];
+} mfv_fusion_grads;
+/* out_fused / out_x f32: fused [B][NC], x [2][B][NC]; `saved` f32 scratch of mfv_fusion_saved_floats(B,S,C,heads). */
+size_t mfv_fusion_saved_floats(int64_t B, int64_t S, int64_t C, int64_t heads);
+int mfv_fusion_fwd(const float* tok, const mfv_fusion_params* p, float* out_fused, float* out_x, float* saved,
+                   int64_t B, int64_t S, int64_t C, int64_t heads, int64_t NC, void* stream);
+/* dtok f32 [2][B][S][C] is OVERWRITTEN (all rows); parameter gradients are accumulated (+=).                          */
+int mfv_fusion_bwd(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
+                   const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
+                   int64_t heads, int64_t NC, void* stream);
+
+/* ---- small-N linear (classification heads, N <= 32) ------------------------------------------------------------------
+ * Replaces `head = nn.Linear(384, 3)` (MAIN_CA:309-310, MAIN_LPFT:288) applied to the CLS row.
+ * x f32 rows with stride ldx; y f32 [rows][N].                                                                        */
+int mfv_linear_small_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t rows,
+                         int64_t C, int64_t N, void* stream);
+int mfv_linear_small_bwd(const float* x, int64_t ldx, const float* w, const float* dy, float* dx, int64_t lddx,
+                         float* dw, float* db, int64_t rows, int64_t C, int64_t N, void* stream);
+
+/* ---- softmax cross-entropy on small class counts -------------------------------------------------------------------
+ * Replaces nn.CrossEntropyLoss on `output_fus+output_cxr+output_enh` (MAIN_CA:868-873).  logits = a + b + c (b, c
+ * optional), mean reduction.  loss f32 [1]; dlogits f32 [rows][NC] = (softmax - onehot)/rows.                         */
+int mfv_ce_small(const float* a, const float* b, const float* c, const int64_t* target, float* loss, float* dlogits,
+                 int64_t rows, int64_t NC, void* stream);
+
+/* ---- MoCo: momentum (EMA) update -----------------------------------------------------------------------------------
+ * Replaces MoCo._momentum_update_key_encoder (BLD:83-89): k = k*m + q*(1.-m), bit-exact with the 3-op eager sequence
+ * (two roundings of the products, one of the sum: no FMA contraction).  m and one_minus_m are the separately
+ * rounded fp32 values of the Python doubles m and (1.-m).  Chunk table: n_chunks x {k ptr, q ptr, count}.             */
+typedef struct {
+  float* k;
+  const float* q;
+  int64_t n;
+} mfv_ema_chunk;
+int mfv_ema_update(const mfv_ema_chunk* chunks_dev, int64_t n_chunks, int64_t max_chunk_elems, float m,
+                   float one_minus_m, void* stream);
+
+/* ---- MoCo: InfoNCE logits (v2 loss) ---------------------------------------------------------------------------------
+ * Replaces BLD:165,175 (F.normalize), BLD:183-191 (l_pos, l_neg = q @ queue, cat, /T) and MAIN_PRE:535 (CE, label 0).
+ * q_raw, k_raw f32 [N][D] un-normalised; queue f32 [D][K] (column j = key j).  Outputs: qn, kn f32 [N][D] normalised,
+ * logits f32 [N][1+K], lse f32 [N*(1+2*K/64)] (first N: log-sum-exp of each logits row, for the fused CE; the rest is
+ * per-tile scratch), loss f32 [1] (mean CE).                                                                          */
+int mfv_infonce_fwd(const float* q_raw, const float* k_raw, const float* queue, float* qn, float* kn, float* logits,
+                    float* lse, float* loss, int64_t N, int64_t D, int64_t K, float T, void* stream);
+/* d(q_raw) f32 [N][D] from the mean-CE loss (scaled by gscale), through /T, the logits and F.normalize.
+ * dlogits_ext (optional, f32 [N][1+K]) lets autograd pass an arbitrary upstream gradient instead of the fused CE.   */
+int mfv_infonce_bwd(const float* q_raw, const float* qn, const float* kn, const float* queue, const float* logits,
+                    const float* lse, const float* dlogits_ext, float gscale, float* dq_raw, int64_t N, int64_t D,
+                    int64_t K, float T, void* stream);
+/* queue[:, ptr:ptr+n] = keys^T  (BLD:102); keys f32 [n][D] (already all-gathered, rank-major).                        */
+int mfv_enqueue_keys(const float* keys, float* queue, int64_t n, int64_t D, int64_t K, int64_t ptr, void* stream);
+
+/* ---- whole-encoder orchestration (native runtime) ------------------------------------------------------------------
+ * Enqueues every kernel of the ViT-S/16 encoder forward / backward for G branches in one call (no per-kernel Python
+ * round trips; capture-safe).  Replaces VisionTransformer.forward_features of the absent vits.py (timm): patch embed ->
+ * +cls -> +pos -> depth x Block -> norm, and its autograd backward.  All buffers are caller-owned.
+ * Parameter addressing: tensor t of group g lives at master + g*P + off_t (f32) and shadow + g*P + off_t (bf16 copy).  */
+typedef struct {
+  int64_t G, B, S, C, H, depth, hidden, img, np;
+  int64_t P;
+  const float* master;
+  const void* shadow;
+  float* grad; /* f32 [G][P], accumulated into (caller zeroes) */
+  int64_t off_cls, off_pos, off_pe_w, off_pe_b, off_norm_w, off_norm_b, off_block0, block_stride;
+  int64_t r_ln1_w, r_ln1_b, r_qkv_w, r_qkv_b, r_proj_w, r_proj_b, r_ln2_w, r_ln2_b, r_fc1_w, r_fc1_b, r_fc2_w, r_fc2_b;
+  const float* images[2]; /* per group: f32 [B][3][img][img] */
+  void* patches;          /* bf16 [G][B*np][768] */
+  float* acc;             /* f32  [G][B*np][C] */
+  float* x;               /* f32  [nslot_x][G][M][C]  residual stream: slot 0 = embed out, 2l+1 = mid of block l, 2l+2 = out */
+  void* xn;               /* bf16 [nslot][G][M][C]    LayerNorm outputs: slot 2l = norm1, 2l+1 = norm2 */
+  float* stats;           /* f32  [nslot_x][2][G][M]  mean, rstd of the LN applied to x slot i */
+  void* qkv;              /* bf16 [nblk][G][M][3C] */
+  void* attn_o;           /* bf16 [nblk][G][M][C] */
+  float* lse;             /* f32  [nblk][G*B][H][S] */
+  void* u;                /* bf16 [nblk][G][M][hidden] pre-GELU */
+  void* gact;             /* bf16 [nblk][G][M][hidden] GELU out */
+  float* tokens;          /* f32  [G][M][C] final-normed tokens (features3D) */
+  int32_t save_for_backward; /* 1: one slot per block (training); 0: slots are reused (inference / momentum encoder) */
+  int32_t stop_grad_conv1;
+  /* backward only */
+  const float* dtokens;   /* f32 [G][M][C] */
+  float* dx[2];           /* f32 [G][M][C] ping-pong */
+  void* dx16[2];          /* bf16 copies */
+  void* dhid;             /* bf16 [G][M][hidden] */
+  void* dxn;              /* bf16 [G][M][C] */
+  void* d_o;              /* bf16 [G][M][C] */
+  void* dqkv;             /* bf16 [G][M][3C] */
+  float* delta;           /* f32 [G*B][H][S] */
+  void* dacc;             /* bf16 [G][B*np][C] */
+} mfv_vit_plan;
+int mfv_vit_forward(const mfv_vit_plan* plan, void* stream);
+int mfv_vit_backward(const mfv_vit_plan* plan, void* stream);
+
+/* ---- elementwise / optimiser ------------------------------------------------------------------------------------------
+ * f32 -> bf16 shadow weights for the GEMM operands.                                                                   */
+int mfv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int mfv_fill_f32(float* dst, float value, int64_t n, void* stream);
+/* torch.optim.SGD semantics (MAIN_CA:449): g += wd*p ; buf = mom*buf + g (buf = g on first step) ; p -= lr*buf.
+ * Optionally refreshes the bf16 shadow in the same pass.                                                              */
+int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, int64_t n, float lr, float momentum,
+                 float weight_decay, int first_step, void* stream);
+/* torch.optim.Adam / AdamW semantics (MAIN_CA:457, MAIN_PRE:339); step is 1-based.                                    */
+int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int decoupled_wd, int64_t step,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFVIT_H_ */

@@ -1,0 +1,445 @@
+// Fused softmax self-attention, forward and backward, for the ViT-S/16 block: S = 197 (224^2) or 577
+// (384^2) tokens, head_dim 64 (or 32).  The whole K/V (forward, dQ pass) or Q/dO (dK/dV pass) of one head stays
+// resident in shared memory; each warp owns 16 rows and keeps its softmax statistics in registers (warp-level online
+// softmax, quad shuffles only).  Scores never touch HBM; the backward recomputes them from the saved log-sum-exp.
+// Tensor-core path: mma.sync.m16n8k16 bf16 with ldmatrix from XOR-swizzled smem (the attention FLOPs are <8 % of the
+// step; the dense contractions live in gemm.cu on tcgen05).
+#include "common.cuh"
+#include "mfvit_internal.h"
+
+namespace mfv {
+
+constexpr int ATT_WARPS = 4;
+constexpr int ATT_ROWS = ATT_WARPS * 16;  // 64 rows per CTA
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Shared-memory tile [rows][D] bf16, 16-byte chunks XOR-swizzled so ldmatrix rows hit distinct banks.
+template <int D>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  if constexpr (D == 64) {
+    return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+  } else {  // D == 32: two rows per 128-byte line
+    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+  }
+}
+
+// Load `nrows` rows (starting at token s0) of one [S][.] slice into a swizzled tile; rows >= S are zero-filled.
+template <int D>
+__device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* base, long long row_stride, int s0,
+                                          int nrows, int S) {
+  constexpr int CH = D / 8;
+  for (int i = threadIdx.x; i < nrows * CH; i += ATT_WARPS * 32) {
+    const int r = i / CH, c = i % CH;
+    const int s = s0 + r;
+    const bool ok = s < S;
+    cp_async16(tile + tile_off<D>(r, c), base + (long long)(ok ? s : 0) * row_stride + c * 8, ok);
+  }
+}
+
+// acc[j] (16 x 8 per n-tile j) += A(16 x D, register fragments) * Bt, with Bt rows = "n" index taken from a
+// [n][D] row-major tile (ldmatrix, no transpose).  Used for Q K^T, dO V^T, K Q^T, V dO^T.
+template <int D>
+__device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&afrag)[D / 16][4], const uint8_t* tile,
+                                         int n_row0, int lane) {
+  const uint32_t tbase = smem_u32(tile);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      const int row = n_row0 + jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+      const int chunk = 2 * kk + ((lane >> 3) & 1);
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(tbase + tile_off<D>(row, chunk), b0, b1, b2, b3);
+      mma16816(acc[2 * jp], afrag[kk], b0, b1);
+      mma16816(acc[2 * jp + 1], afrag[kk], b2, b3);
+    }
+  }
+}
+
+// out[j] (16 x 8 per d-tile j, D/8 tiles) += P(16 x 64, from accumulator registers, rounded to bf16) * B, with B rows =
+// reduction index taken from a [k][D] row-major tile (ldmatrix.trans).  Used for P V, dS K, P^T dO, dS^T Q.
+template <int D>
+__device__ __forceinline__ void mma_p_b(float (&out)[D / 8][4], const float (&p)[8][4], const uint8_t* tile,
+                                        int k_row0, int lane) {
+  const uint32_t tbase = smem_u32(tile);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+    a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+    a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int jp = 0; jp < D / 16; ++jp) {
+      const int row = k_row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int chunk = 2 * jp + ((lane >> 4) & 1);
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(tbase + tile_off<D>(row, chunk), b0, b1, b2, b3);
+      mma16816(out[2 * jp], a, b0, b1);
+      mma16816(out[2 * jp + 1], a, b2, b3);
+    }
+  }
+}
+
+// A fragments (16 rows x D) of this warp's rows from a swizzled tile.
+template <int D>
+__device__ __forceinline__ void load_afrag(uint32_t (&afrag)[D / 16][4], const uint8_t* tile, int row0, int lane) {
+  const uint32_t tbase = smem_u32(tile);
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const int row = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int chunk = 2 * kk + (lane >> 4);
+    ldsm_x4(tbase + tile_off<D>(row, chunk), afrag[kk][0], afrag[kk][1], afrag[kk][2], afrag[kk][3]);
+  }
+}
+
+// Write this warp's 16 x D fp32 fragments as bf16 rows (row stride in elements); rows >= S are skipped.
+template <int D>
+__device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], __nv_bfloat16* base, long long row_stride,
+                                           int s_row0, int S, int lane, float mul0, float mul1) {
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = s_row0 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) {
+    if (r0 < S)
+      *reinterpret_cast<uint32_t*>(base + (long long)r0 * row_stride + j * 8 + 2 * t) =
+          pack_bf16(acc[j][0] * mul0, acc[j][1] * mul0);
+    if (r1 < S)
+      *reinterpret_cast<uint32_t*>(base + (long long)r1 * row_stride + j * 8 + 2 * t) =
+          pack_bf16(acc[j][2] * mul1, acc[j][3] * mul1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// grid = (ceil(S/64), NB*H).  smem: K[Spad][D], V[Spad][D], Q[64][D].
+template <int D>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int S,
+                int H, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Spad = (S + 63) & ~63;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Spad * D * 2;
+  uint8_t* sQ = sV + Spad * D * 2;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * ATT_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rs = 3LL * H * D;
+  const __nv_bfloat16* qb = qkv + (long long)b * S * rs + h * D;
+  load_tile<D>(sQ, qb, rs, q0, ATT_ROWS, S);
+  load_tile<D>(sK, qb + H * D, rs, 0, Spad, S);
+  load_tile<D>(sV, qb + 2 * H * D, rs, 0, Spad, S);
+  cp_async_wait_all();
+  __syncthreads();
+
+  uint32_t qf[D / 16][4];
+  load_afrag<D>(qf, sQ, warp * 16, lane);
+  float oacc[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int t = lane & 3;
+
+  for (int kb = 0; kb < Spad; kb += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    mma_a_bt<D>(s, qf, sK, kb, lane);
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kb + j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = (key + (e & 1) < S) ? s[j][e] * scale_log2 : -INFINITY;
+        s[j][e] = v;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);  // first block: exp2(-inf) = 0
+    m0 = mx0; m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - m0); s[j][1] = exp2f(s[j][1] - m0);
+      s[j][2] = exp2f(s[j][2] - m1); s[j][3] = exp2f(s[j][3] - m1);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      oacc[j][0] *= a0; oacc[j][1] *= a0; oacc[j][2] *= a1; oacc[j][3] *= a1;
+    }
+    mma_p_b<D>(oacc, s, sV, kb, lane);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const int row0 = q0 + warp * 16;
+  __nv_bfloat16* ob = o + (long long)b * S * H * D + h * D;
+  store_rows<D>(oacc, ob, (long long)H * D, row0, S, lane, 1.f / l0, 1.f / l1);
+  if (t == 0) {
+    const int g = lane >> 2;
+    float* lb = lse + (long long)bh * S;
+    if (row0 + g < S) lb[row0 + g] = (m0 + log2f(l0)) * LN2;
+    if (row0 + g + 8 < S) lb[row0 + g + 8] = (m1 + log2f(l1)) * LN2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ
+// grid = (ceil(S/64), NB*H).  smem: K[Spad][D], V[Spad][D], Q[64][D], dO[64][D].  Also emits delta = rowsum(dO*O).
+template <int D>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+                   const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse, float* __restrict__ delta,
+                   __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Spad = (S + 63) & ~63;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Spad * D * 2;
+  uint8_t* sQ = sV + Spad * D * 2;
+  uint8_t* sdO = sQ + ATT_ROWS * D * 2;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * ATT_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rs = 3LL * H * D, ors = (long long)H * D;
+  const __nv_bfloat16* qb = qkv + (long long)b * S * rs + h * D;
+  const __nv_bfloat16* dob = d_o + (long long)b * S * ors + h * D;
+  const __nv_bfloat16* ob = o + (long long)b * S * ors + h * D;
+  load_tile<D>(sQ, qb, rs, q0, ATT_ROWS, S);
+  load_tile<D>(sdO, dob, ors, q0, ATT_ROWS, S);
+  load_tile<D>(sK, qb + H * D, rs, 0, Spad, S);
+  load_tile<D>(sV, qb + 2 * H * D, rs, 0, Spad, S);
+
+  // delta for this warp's 16 rows: 2 lanes per row, D/2 elements each (straight from global)
+  const int row0 = q0 + warp * 16;
+  float dl;
+  {
+    const int r = row0 + (lane >> 1);
+    float acc = 0.f;
+    if (r < S) {
+      const uint4* po = reinterpret_cast<const uint4*>(ob + (long long)r * ors + (lane & 1) * (D / 2));
+      const uint4* pd = reinterpret_cast<const uint4*>(dob + (long long)r * ors + (lane & 1) * (D / 2));
+#pragma unroll
+      for (int i = 0; i < D / 16; ++i) {
+        const uint4 a = __ldg(po + i), c = __ldg(pd + i);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(cw[j]);
+          acc += x.x * y.x + x.y * y.y;
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    dl = acc;  // lanes 2r, 2r+1 hold delta of row r
+    if ((lane & 1) == 0 && r < S) delta[(long long)bh * S + r] = acc;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const float dl0 = __shfl_sync(0xffffffffu, dl, 2 * g), dl1 = __shfl_sync(0xffffffffu, dl, 2 * (g + 8));
+  const float* lb = lse + (long long)bh * S;
+  const float lse0 = (row0 + g < S) ? lb[row0 + g] * LOG2E : INFINITY;
+  const float lse1 = (row0 + g + 8 < S) ? lb[row0 + g + 8] * LOG2E : INFINITY;
+  const float scale_log2 = scale * LOG2E;
+
+  cp_async_wait_all();
+  __syncthreads();
+  uint32_t qf[D / 16][4], dof[D / 16][4];
+  load_afrag<D>(qf, sQ, warp * 16, lane);
+  load_afrag<D>(dof, sdO, warp * 16, lane);
+  float dq[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+
+  for (int kb = 0; kb < Spad; kb += 64) {
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+    mma_a_bt<D>(s, qf, sK, kb, lane);
+    mma_a_bt<D>(dp, dof, sV, kb, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kb + j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = key + (e & 1) < S;
+        const float p = ok ? exp2f(s[j][e] * scale_log2 - (e < 2 ? lse0 : lse1)) : 0.f;
+        s[j][e] = p * (dp[j][e] - (e < 2 ? dl0 : dl1)) * scale;  // dS
+      }
+    }
+    mma_p_b<D>(dq, s, sK, kb, lane);
+  }
+  __nv_bfloat16* dqb = dqkv + (long long)b * S * rs + h * D;
+  store_rows<D>(dq, dqb, rs, row0, S, lane, 1.f, 1.f);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+// grid = (ceil(S/64), NB*H) over key tiles.  smem: Q[Spad][D], dO[Spad][D], K[64][D], V[64][D], lse2[Spad], delta[Spad].
+template <int D>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
+                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                    int S, int H, float scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Spad = (S + 63) & ~63;
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + Spad * D * 2;
+  uint8_t* sK = sdO + Spad * D * 2;
+  uint8_t* sV = sK + ATT_ROWS * D * 2;
+  float* sLse = reinterpret_cast<float*>(sV + ATT_ROWS * D * 2);
+  float* sDel = sLse + Spad;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.x * ATT_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rs = 3LL * H * D, ors = (long long)H * D;
+  const __nv_bfloat16* qb = qkv + (long long)b * S * rs + h * D;
+  const __nv_bfloat16* dob = d_o + (long long)b * S * ors + h * D;
+  load_tile<D>(sK, qb + H * D, rs, k0, ATT_ROWS, S);
+  load_tile<D>(sV, qb + 2 * H * D, rs, k0, ATT_ROWS, S);
+  load_tile<D>(sQ, qb, rs, 0, Spad, S);
+  load_tile<D>(sdO, dob, ors, 0, Spad, S);
+  for (int i = threadIdx.x; i < Spad; i += ATT_WARPS * 32) {
+    sLse[i] = i < S ? lse[(long long)bh * S + i] * LOG2E : INFINITY;  // +inf -> p = 0 for padded queries
+    sDel[i] = i < S ? delta[(long long)bh * S + i] : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  uint32_t kf[D / 16][4], vf[D / 16][4];
+  load_afrag<D>(kf, sK, warp * 16, lane);
+  load_afrag<D>(vf, sV, warp * 16, lane);
+  float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) {
+    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+  }
+  const int t = lane & 3;
+  const float scale_log2 = scale * LOG2E;
+
+  for (int qb0 = 0; qb0 < Spad; qb0 += 64) {
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+      dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+    }
+    mma_a_bt<D>(st, kf, sQ, qb0, lane);     // S^T  = K Q^T   (rows: keys, cols: queries)
+    mma_a_bt<D>(dpt, vf, sdO, qb0, lane);   // dP^T = V dO^T
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int qi = qb0 + j * 8 + 2 * t;
+      const float ls0 = sLse[qi], ls1 = sLse[qi + 1], de0 = sDel[qi], de1 = sDel[qi + 1];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = exp2f(st[j][e] * scale_log2 - ((e & 1) ? ls1 : ls0));
+        st[j][e] = p;                                                   // P^T
+        dpt[j][e] = p * (dpt[j][e] - ((e & 1) ? de1 : de0)) * scale;     // dS^T
+      }
+    }
+    mma_p_b<D>(dv, st, sdO, qb0, lane);   // dV += P^T dO
+    mma_p_b<D>(dk, dpt, sQ, qb0, lane);   // dK += dS^T Q
+  }
+  __nv_bfloat16* dkb = dqkv + (long long)b * S * rs + H * D + h * D;
+  __nv_bfloat16* dvb = dqkv + (long long)b * S * rs + 2 * H * D + h * D;
+  store_rows<D>(dk, dkb, rs, k0 + warp * 16, S, lane, 1.f, 1.f);
+  store_rows<D>(dv, dvb, rs, k0 + warp * 16, S, lane, 1.f, 1.f);
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t bytes) {
+  if (bytes > 227 * 1024) return MFV_ERR_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e == cudaSuccess ? MFV_OK : (int)e;
+}
+
+}  // namespace mfv
+
+extern "C" int mfv_attn_fwd(const void* qkv, void* o, float* lse, int64_t NB, int64_t S, int64_t H, int64_t D,
+                            float scale, void* stream) {
+  using namespace mfv;
+  if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
+  if (NB * H > 65535) return MFV_ERR_SHAPE;
+  const int Spad = ((int)S + 63) & ~63;
+  const size_t smem = (size_t)(2 * Spad + ATT_ROWS) * D * 2;
+  dim3 grid((unsigned)((S + ATT_ROWS - 1) / ATT_ROWS), (unsigned)(NB * H));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(o);
+  int rc;
+  if (D == 64) {
+    if ((rc = set_smem(attn_fwd_kernel<64>, smem))) return rc;
+    attn_fwd_kernel<64><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, lse, (int)S, (int)H, scale * LOG2E);
+  } else {
+    if ((rc = set_smem(attn_fwd_kernel<32>, smem))) return rc;
+    attn_fwd_kernel<32><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, lse, (int)S, (int)H, scale * LOG2E);
+  }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+extern "C" int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, void* dqkv,
+                            int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream) {
+  using namespace mfv;
+  if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
+  if (NB * H > 65535) return MFV_ERR_SHAPE;
+  const int Spad = ((int)S + 63) & ~63;
+  const size_t smem_dq = (size_t)(2 * Spad + 2 * ATT_ROWS) * D * 2;
+  const size_t smem_dkv = smem_dq + (size_t)Spad * 8;
+  dim3 grid((unsigned)((S + ATT_ROWS - 1) / ATT_ROWS), (unsigned)(NB * H));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* op = reinterpret_cast<const __nv_bfloat16*>(o);
+  const __nv_bfloat16* dop = reinterpret_cast<const __nv_bfloat16*>(d_o);
+  __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  int rc;
+  if (D == 64) {
+    if ((rc = set_smem(attn_bwd_dq_kernel<64>, smem_dq))) return rc;
+    if ((rc = set_smem(attn_bwd_dkv_kernel<64>, smem_dkv))) return rc;
+    attn_bwd_dq_kernel<64><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale);
+    MFV_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<64><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale);
+  } else {
+    if ((rc = set_smem(attn_bwd_dq_kernel<32>, smem_dq))) return rc;
+    if ((rc = set_smem(attn_bwd_dkv_kernel<32>, smem_dkv))) return rc;
+    attn_bwd_dq_kernel<32><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale);
+    MFV_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<32><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale);
+  }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}

@@ -1,0 +1,200 @@
+// Native runtime for the ViT-S/16 encoder: one call enqueues the whole forward (or backward) of G branches on a
+// stream.  No kernels here - this file is the host-side executor that sequences gemm.cu / ln.cu / attn.cu /
+// elementwise.cu launches over caller-owned buffers (see mfv_vit_plan in include/mfvit.h).
+//
+// Forward per block l (residual stream x kept in fp32, GEMM operands bf16):
+//   xn1 = LN(x_in)            -> qkv = xn1 Wqkv^T + b        -> o = softmax(q k^T / sqrt(d)) v
+//   x_mid = x_in + o Wp^T + b -> xn2 = LN(x_mid)             -> u = xn2 W1^T + b, g = gelu(u)
+//   x_out = x_mid + g W2^T + b
+// Backward mirrors it: for every Linear a split-K wgrad (A,B MN-major), a dgrad (B MN-major), a bias column-sum; the
+// LN backward kernels carry the fp32 residual-stream gradient and emit the bf16 copy the next GEMMs consume.
+#include "common.cuh"
+#include "mfvit_internal.h"
+
+namespace mfv {
+
+struct PlanView {
+  const mfv_vit_plan* p;
+  long long M, MC, Mh, M3;
+  explicit PlanView(const mfv_vit_plan* pl) : p(pl) {
+    M = pl->B * pl->S;
+    MC = pl->G * M * pl->C;
+    Mh = pl->G * M * pl->hidden;
+    M3 = pl->G * M * 3 * pl->C;
+  }
+  int slot(int i) const { return p->save_for_backward ? i : 0; }
+  float* x(int i) const { return p->x + (long long)(p->save_for_backward ? i : (i & 1)) * MC; }
+  float* mean(int i) const { return p->stats + (long long)slot(i) * 2 * p->G * M; }
+  float* rstd(int i) const { return mean(i) + p->G * M; }
+  __nv_bfloat16* xn(int i) const { return reinterpret_cast<__nv_bfloat16*>(p->xn) + (long long)slot(i) * MC; }
+  __nv_bfloat16* qkv(int l) const { return reinterpret_cast<__nv_bfloat16*>(p->qkv) + (long long)slot(l) * M3; }
+  __nv_bfloat16* ao(int l) const { return reinterpret_cast<__nv_bfloat16*>(p->attn_o) + (long long)slot(l) * MC; }
+  float* lse(int l) const { return p->lse + (long long)slot(l) * p->G * p->B * p->H * p->S; }
+  __nv_bfloat16* u(int l) const { return reinterpret_cast<__nv_bfloat16*>(p->u) + (long long)slot(l) * Mh; }
+  __nv_bfloat16* g(int l) const { return reinterpret_cast<__nv_bfloat16*>(p->gact) + (long long)slot(l) * Mh; }
+  long long boff(int l, long long rel) const { return p->off_block0 + (long long)l * p->block_stride + rel; }
+  const float* w32(long long off) const { return p->master + off; }
+  const __nv_bfloat16* w16(long long off) const { return reinterpret_cast<const __nv_bfloat16*>(p->shadow) + off; }
+  float* gr(long long off) const { return p->grad + off; }
+};
+
+// y = x W^T (+bias): A = activations [G][M][K] bf16 K-major, B = weight [N][K] bf16 K-major
+static int linear_fwd(const PlanView& v, const void* A, long long K, long long w_off, long long b_off, long long N,
+                      int epi, void* C, void* C2, const void* aux, long long aux_ld, cudaStream_t st) {
+  mfv_gemm_args a = {};
+  a.A = A; a.B = v.w16(w_off); a.C = C; a.C2 = C2;
+  a.bias = b_off >= 0 ? v.w32(b_off) : nullptr;
+  a.aux = aux;
+  a.M = v.M; a.N = N; a.K = K; a.G = v.p->G;
+  a.lda = K; a.ldb = K; a.ldc = N;
+  a.a_gstride = v.M * K; a.b_gstride = v.p->P; a.c_gstride = v.M * N;
+  a.aux_ld = aux_ld; a.aux_gstride = v.M * aux_ld; a.bias_gstride = v.p->P;
+  a.epilogue = epi;
+  return mfv_gemm(&a, st);
+}
+// dx = dy W: A = dy [G][M][N] K-major (reduction over N), B = W [N][K] read MN-major
+static int linear_dgrad(const PlanView& v, const void* dY, long long N, long long w_off, long long K, int epi, void* C,
+                        const void* aux, long long aux_ld, cudaStream_t st) {
+  mfv_gemm_args a = {};
+  a.A = dY; a.B = v.w16(w_off); a.C = C; a.aux = aux;
+  a.M = v.M; a.N = K; a.K = N; a.G = v.p->G;
+  a.lda = N; a.ldb = K; a.ldc = K;
+  a.a_gstride = v.M * N; a.b_gstride = v.p->P; a.c_gstride = v.M * K;
+  a.aux_ld = aux_ld; a.aux_gstride = v.M * aux_ld;
+  a.b_mn_major = 1;
+  a.epilogue = epi;
+  return mfv_gemm(&a, st);
+}
+// dW[N][K] += dy^T x (reduction over `rows` tokens), db[N] += colsum(dy)
+static int linear_wgrad(const PlanView& v, const void* dY, long long N, const void* X, long long K, long long rows,
+                        long long w_off, long long b_off, cudaStream_t st) {
+  mfv_gemm_args a = {};
+  a.A = dY; a.B = X; a.C = v.gr(w_off);
+  a.M = N; a.N = K; a.K = rows; a.G = v.p->G;
+  a.lda = N; a.ldb = K; a.ldc = K;
+  a.a_gstride = rows * N; a.b_gstride = rows * K; a.c_gstride = v.p->P;
+  a.a_mn_major = 1; a.b_mn_major = 1;
+  a.epilogue = MFV_EPI_ATOMIC_F32;
+  a.block_n = 128;
+  const long long tiles = ((N + 127) / 128) * ((K + 127) / 128) * v.p->G;
+  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
+  const long long kb = (rows + 63) / 64;
+  if (splits > kb) splits = kb;
+  if (splits < 1) splits = 1;
+  a.splits = (int)splits;
+  int rc = mfv_gemm(&a, st);
+  if (rc) return rc;
+  if (b_off >= 0) rc = mfv_colsum_bf16(dY, v.gr(b_off), v.p->G, rows, N, v.p->P, st);
+  return rc;
+}
+
+#define RC(expr)            \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+static int check_plan(const mfv_vit_plan* p) {
+  if (!p) return MFV_ERR_ARG;
+  if (p->G < 1 || p->G > 2 || p->B < 1 || p->depth < 1) return MFV_ERR_SHAPE;
+  if (p->C % 128 || p->hidden % 32 || p->C % p->H) return MFV_ERR_SHAPE;
+  if (p->S != p->np + 1 || p->np != (p->img / 16) * (p->img / 16)) return MFV_ERR_SHAPE;
+  const long long d = p->C / p->H;
+  if (d != 64 && d != 32) return MFV_ERR_SHAPE;
+  if (p->P % 8) return MFV_ERR_ALIGN;
+  return MFV_OK;
+}
+
+}  // namespace mfv
+
+extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
+  using namespace mfv;
+  RC(check_plan(p));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const PlanView v(p);
+  const long long G = p->G, C = p->C, Hd = p->hidden, M = v.M;
+  const long long D = C / p->H;
+  const float scale = 1.0f / sqrtf((float)D);
+  const long long rows_pe = p->B * p->np;
+  // patch embedding: patchify (per group: images are separate caller tensors) -> GEMM(+bias) -> +cls, +pos
+  for (int g = 0; g < G; ++g)
+    RC(mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768, p->B,
+                    p->img, st));
+  {
+    mfv_gemm_args a = {};
+    a.A = p->patches; a.B = v.w16(p->off_pe_w); a.C = p->acc; a.bias = v.w32(p->off_pe_b);
+    a.M = rows_pe; a.N = C; a.K = 768; a.G = G;
+    a.lda = 768; a.ldb = 768; a.ldc = C;
+    a.a_gstride = rows_pe * 768; a.b_gstride = p->P; a.c_gstride = rows_pe * C; a.bias_gstride = p->P;
+    a.epilogue = MFV_EPI_F32;
+    RC(mfv_gemm(&a, st));
+  }
+  RC(mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
+
+  for (int l = 0; l < p->depth; ++l) {
+    float* x_in = v.x(2 * l);
+    float* x_mid = v.x(2 * l + 1);
+    float* x_out = v.x(2 * l + 2);
+    RC(mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), nullptr,
+                         v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f, st));
+    RC(linear_fwd(v, v.xn(2 * l), C, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), 3 * C, MFV_EPI_BF16, v.qkv(l),
+                  nullptr, nullptr, 0, st));
+    RC(mfv_attn_fwd(v.qkv(l), v.ao(l), v.lse(l), G * p->B, p->S, p->H, D, scale, st));
+    RC(linear_fwd(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), C, MFV_EPI_RESID_F32, x_mid, nullptr,
+                  x_in, C, st));
+    RC(mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), nullptr,
+                         v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C, p->P, 1e-6f, st));
+    RC(linear_fwd(v, v.xn(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), Hd, MFV_EPI_GELU, v.u(l),
+                  v.g(l), nullptr, 0, st));
+    RC(linear_fwd(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), C, MFV_EPI_RESID_F32, x_out, nullptr,
+                  x_mid, C, st));
+  }
+  const int last = 2 * (int)p->depth;
+  RC(mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, p->tokens, v.mean(last),
+                       v.rstd(last), G, M, C, p->P, 1e-6f, st));
+  return MFV_OK;
+}
+
+extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
+  using namespace mfv;
+  RC(check_plan(p));
+  if (!p->save_for_backward || !p->grad || !p->dtokens) return MFV_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const PlanView v(p);
+  const long long G = p->G, C = p->C, Hd = p->hidden, M = v.M;
+  const long long D = C / p->H;
+  const float scale = 1.0f / sqrtf((float)D);
+  const int last = 2 * (int)p->depth;
+  int cur = 0;  // dx[cur] holds the gradient of the residual stream
+  // final norm
+  RC(mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
+                       p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b), G, M, C, p->P, st));
+  for (int l = (int)p->depth - 1; l >= 0; --l) {
+    // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+    RC(linear_wgrad(v, p->dx16[cur], C, v.g(l), Hd, M, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), st));
+    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid, v.u(l), Hd, st));
+    RC(linear_wgrad(v, p->dhid, Hd, v.xn(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
+    RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
+    RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
+                         v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
+                         v.gr(v.boff(l, p->r_ln2_b)), G, M, C, p->P, st));
+    cur ^= 1;
+    // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
+    RC(linear_wgrad(v, p->dx16[cur], C, v.ao(l), C, M, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), st));
+    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, 0, st));
+    RC(mfv_attn_bwd(v.qkv(l), v.ao(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
+    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
+    RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
+    RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
+                         v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
+                         v.gr(v.boff(l, p->r_ln1_b)), G, M, C, p->P, st));
+    cur ^= 1;
+  }
+  // ---- embedding: cls gradient, conv bias / weight gradient (pos_embed is a fixed table)
+  const long long rows_pe = p->B * p->np;
+  RC(mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
+                          p->B, p->np, C, p->P, st));
+  if (!p->stop_grad_conv1)
+    RC(linear_wgrad(v, p->dacc, C, p->patches, 768, rows_pe, p->off_pe_w, -1, st));
+  return MFV_OK;
+}

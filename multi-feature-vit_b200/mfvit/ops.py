@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (one function per mfv_* entry point).  PyTorch is used for device memory and
+streams only; every computation below runs in libmfvit.so.  Inputs must be CUDA tensors - there is no CPU path."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESID_F32, EmaChunk, FusionGrads,
+                   FusionParams, GemmArgs, MfvError, check)
+
+
+def _lib_for(t):
+    if not t.is_cuda:
+        raise MfvError("mfvit ops need CUDA tensors (sm_100a); got a %s tensor - there is no CPU fallback" % t.device)
+    return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c_gstride=0, bias=None,
+         bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
+         splits=1, block_n=0):
+    lib = _lib_for(A)
+    a = GemmArgs()
+    a.A, a.B, a.C, a.C2, a.bias, a.aux = (A.data_ptr(), B.data_ptr(), Cout.data_ptr(),
+                                           C2.data_ptr() if C2 is not None else None,
+                                           bias.data_ptr() if bias is not None else None,
+                                           aux.data_ptr() if aux is not None else None)
+    a.M, a.N, a.K, a.G = M, N, K, G
+    a.lda, a.ldb, a.ldc = lda, ldb, ldc
+    a.a_gstride, a.b_gstride, a.c_gstride = a_gstride, b_gstride, c_gstride
+    a.aux_ld, a.aux_gstride, a.bias_gstride = aux_ld, aux_gstride, bias_gstride
+    a.a_mn_major, a.b_mn_major, a.epilogue, a.splits, a.block_n = int(a_mn), int(b_mn), epilogue, splits, block_n
+    check(lib.mfv_gemm(C.byref(a), _stream()), "mfv_gemm")
+    return Cout
+
+
+def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=None, block_n=0):
+    """x16 [G,M,K] bf16, w16 [G,N,K] bf16, bias [G,N] f32."""
+    G, M, K = x16.shape
+    N = w16.shape[1]
+    if out is None:
+        out = torch.empty(G, M, N, device=x16.device,
+                          dtype=torch.float32 if epilogue in (EPI_RESID_F32, EPI_F32) else torch.bfloat16)
+    return gemm(x16, w16, out, M=M, N=N, K=K, G=G, lda=K, ldb=K, ldc=N, a_gstride=M * K, b_gstride=N * K,
+                c_gstride=M * N, bias=bias, bias_gstride=N, aux=aux, aux_ld=N, aux_gstride=M * N, C2=out2,
+                epilogue=epilogue, block_n=block_n)
+
+
+def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0):
+    """dy16 [G,M,N] bf16, w16 [G,N,K] bf16 -> dx [G,M,K]."""
+    G, M, N = dy16.shape
+    K = w16.shape[2]
+    if out is None:
+        out = torch.empty(G, M, K, device=dy16.device, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16)
+    return gemm(dy16, w16, out, M=M, N=K, K=N, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=N * K,
+                c_gstride=M * K, aux=aux, aux_ld=K, aux_gstride=M * K, b_mn=True, epilogue=epilogue, block_n=block_n)
+
+
+def linear_wgrad(dy16, x16, dw, splits=8, block_n=128):
+    """dw [G,N,K] f32 += dy16[G,M,N]^T x16[G,M,K]."""
+    G, M, N = dy16.shape
+    K = x16.shape[2]
+    return gemm(dy16, x16, dw, M=N, N=K, K=M, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=M * K,
+                c_gstride=N * K, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, splits=splits, block_n=block_n)
+
+
+def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False):
+    G, rows, Cd = x.shape
+    lib = _lib_for(x)
+    y16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
+    y32 = torch.empty_like(x) if want_f32 else None
+    mean = torch.empty(G, rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    check(lib.mfv_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd), G, rows, Cd,
+                                gamma.stride(0) if gamma.dim() > 1 else 0, eps, _stream()), "mfv_layernorm_fwd")
+    return y16, y32, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, want_bf16=True):
+    G, rows, Cd = x.shape
+    lib = _lib_for(x)
+    dx = torch.empty_like(x)
+    dx16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
+    dy16 = dy if dy.dtype == torch.bfloat16 else None
+    dy32 = dy if dy.dtype == torch.float32 else None
+    check(lib.mfv_layernorm_bwd(_p(dy16), _p(dy32), _p(dres), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx16),
+                                _p(dgamma), _p(dbeta), G, rows, Cd, gamma.stride(0) if gamma.dim() > 1 else 0,
+                                _stream()), "mfv_layernorm_bwd")
+    return dx, dx16
+
+
+def attn_fwd(qkv, H):
+    """qkv bf16 [NB,S,3,H,D] -> o bf16 [NB,S,H,D], lse f32 [NB,H,S]."""
+    NB, S, three, Hh, D = qkv.shape
+    assert three == 3 and Hh == H
+    lib = _lib_for(qkv)
+    o = torch.empty(NB, S, H, D, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(NB, H, S, device=qkv.device, dtype=torch.float32)
+    check(lib.mfv_attn_fwd(_p(qkv), _p(o), _p(lse), NB, S, H, D, float(D) ** -0.5, _stream()), "mfv_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(qkv, o, d_o, lse):
+    NB, S, _, H, D = qkv.shape
+    lib = _lib_for(qkv)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    check(lib.mfv_attn_bwd(_p(qkv), _p(o), _p(d_o), _p(lse), _p(delta), _p(dqkv), NB, S, H, D, float(D) ** -0.5,
+                           _stream()), "mfv_attn_bwd")
+    return dqkv
+
+
+def colsum_bf16(x, out):
+    G, rows, Cd = x.shape
+    check(_lib_for(x).mfv_colsum_bf16(_p(x), _p(out), G, rows, Cd, out.stride(0) if out.dim() > 1 else 0, _stream()),
+          "mfv_colsum_bf16")
+    return out
+
+
+def cast_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty_like(src, dtype=torch.bfloat16)
+    check(_lib_for(src).mfv_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "mfv_cast_f32_bf16")
+    return dst
+
+
+def fill_(t, value=0.0):
+    check(_lib_for(t).mfv_fill_f32(_p(t), float(value), t.numel(), _stream()), "mfv_fill_f32")
+    return t
+
+
+def ema_update_(chunks_dev, n_chunks, max_elems, m):
+    """chunks_dev: uint8 CUDA tensor holding n_chunks mfv_ema_chunk records.  k = k*m + q*(1.-m), bit-exact with the
+    eager reference: m and (1.-m) are rounded to fp32 separately, exactly as torch does for Python-scalar operands."""
+    check(_lib_for(chunks_dev).mfv_ema_update(_p(chunks_dev), n_chunks, max_elems, float(m), float(1.0 - m),
+                                              _stream()), "mfv_ema_update")
+
+
+def make_ema_chunks(pairs, device):
+    """pairs: list of (k_tensor, q_tensor) fp32 contiguous.  Adjacent-in-memory tensors are merged into one chunk."""
+    merged = []
+    for k, q in pairs:
+        n = k.numel()
+        if merged:
+            pk, pq, pn = merged[-1]
+            if pk + 4 * pn == k.data_ptr() and pq + 4 * pn == q.data_ptr():
+                merged[-1] = (pk, pq, pn + n)
+                continue
+        merged.append((k.data_ptr(), q.data_ptr(), n))
+    arr = (EmaChunk * len(merged))()
+    for i, (pk, pq, n) in enumerate(merged):
+        arr[i].k, arr[i].q, arr[i].n = pk, pq, n
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(merged), max(n for _, _, n in merged)
+
+
+def fusion_param_struct(tensors, cls=FusionParams):
+    """tensors: dict name -> (t_dir0, t_dir1) with None allowed."""
+    s = cls()
+    for name, pair in tensors.items():
+        arr = getattr(s, name)
+        for d in range(2):
+            arr[d] = pair[d].data_ptr() if pair[d] is not None else None
+    return s
+
+
+def fusion_fwd(tok, params, B, S, Cd, heads, NC):
+    lib = _lib_for(tok)
+    fused = torch.empty(B, NC, device=tok.device, dtype=torch.float32)
+    x = torch.empty(2, B, NC, device=tok.device, dtype=torch.float32)
+    check(lib.mfv_fusion_fwd(_p(tok), C.byref(params), _p(fused), _p(x), None, B, S, Cd, heads, NC, _stream()),
+          "mfv_fusion_fwd")
+    return fused, x
+
+
+def fusion_bwd(tok, params, grads, d_fused, d_x, B, S, Cd, heads, NC, dtok=None):
+    lib = _lib_for(tok)
+    n = lib.mfv_fusion_saved_floats(B, S, Cd, heads)
+    scratch = torch.empty(n, device=tok.device, dtype=torch.float32)
+    if dtok is None:
+        dtok = torch.empty_like(tok)
+    check(lib.mfv_fusion_bwd(_p(tok), C.byref(params), _p(scratch), _p(d_fused), _p(d_x), _p(dtok), C.byref(grads), B,
+                             S, Cd, heads, NC, _stream()), "mfv_fusion_bwd")
+    return dtok
+
+
+def linear_small_fwd(x, ldx, w, b, rows):
+    N, Cd = w.shape
+    y = torch.empty(rows, N, device=x.device, dtype=torch.float32)
+    check(_lib_for(x).mfv_linear_small_fwd(_p(x), ldx, _p(w), _p(b), _p(y), rows, Cd, N, _stream()),
+          "mfv_linear_small_fwd")
+    return y
+
+
+def linear_small_bwd(x, ldx, w, dy, dx, lddx, dw, db, rows):
+    N, Cd = w.shape
+    check(_lib_for(x).mfv_linear_small_bwd(_p(x), ldx, _p(w), _p(dy), _p(dx), lddx, _p(dw), _p(db), rows, Cd, N,
+                                           _stream()), "mfv_linear_small_bwd")
+
+
+def ce_small(a, b, c, target, want_grad=True):
+    rows, NC = a.shape
+    loss = torch.empty(1, device=a.device, dtype=torch.float32)
+    dl = torch.empty_like(a) if want_grad else None
+    check(_lib_for(a).mfv_ce_small(_p(a), _p(b), _p(c), _p(target), _p(loss), _p(dl), rows, NC, _stream()),
+          "mfv_ce_small")
+    return loss, dl
+
+
+def infonce_fwd(q_raw, k_raw, queue, T):
+    N, D = q_raw.shape
+    K = queue.shape[1]
+    dev = q_raw.device
+    qn = torch.empty_like(q_raw)
+    kn = torch.empty_like(k_raw)
+    logits = torch.empty(N, K + 1, device=dev, dtype=torch.float32)
+    lse = torch.empty(N * (1 + 2 * (K // 64)), device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    check(_lib_for(q_raw).mfv_infonce_fwd(_p(q_raw), _p(k_raw), _p(queue), _p(qn), _p(kn), _p(logits), _p(lse),
+                                          _p(loss), N, D, K, float(T), _stream()), "mfv_infonce_fwd")
+    return qn, kn, logits, lse, loss
+
+
+def infonce_bwd(q_raw, qn, kn, queue, logits, lse, T, dlogits=None, gscale=1.0):
+    N, D = q_raw.shape
+    K = queue.shape[1]
+    dq = torch.empty_like(q_raw)
+    check(_lib_for(q_raw).mfv_infonce_bwd(_p(q_raw), _p(qn), _p(kn), _p(queue), _p(logits), _p(lse), _p(dlogits),
+                                          float(gscale), _p(dq), N, D, K, float(T), _stream()), "mfv_infonce_bwd")
+    return dq
+
+
+def enqueue_keys_(keys, queue, ptr):
+    n, D = keys.shape
+    K = queue.shape[1]
+    check(_lib_for(keys).mfv_enqueue_keys(_p(keys), _p(queue), n, D, K, int(ptr), _stream()), "mfv_enqueue_keys")
+
+
+def sgd_step_(p, g, buf, shadow, lr, momentum, weight_decay, first_step):
+    check(_lib_for(p).mfv_sgd_step(_p(p), _p(g), _p(buf), _p(shadow), p.numel(), float(lr), float(momentum),
+                                   float(weight_decay), int(bool(first_step)), _stream()), "mfv_sgd_step")
+
+
+def adam_step_(p, g, m1, m2, shadow, lr, betas, eps, weight_decay, decoupled, step):
+    check(_lib_for(p).mfv_adam_step(_p(p), _p(g), _p(m1), _p(m2), _p(shadow), p.numel(), float(lr), float(betas[0]),
+                                    float(betas[1]), float(eps), float(weight_decay), int(bool(decoupled)), int(step),
+                                    _stream()), "mfv_adam_step")

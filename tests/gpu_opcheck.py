@@ -1,0 +1,346 @@
+"""Op-by-op parity report of the CUDA kernels against PyTorch fp32 references (run on a B200 via gpurun).
+
+    python tests/gpu_opcheck.py [filter-substring] > gpurun_out/opcheck.log
+
+Unlike the pytest suite it keeps going after a failure and prints error statistics for every op, which is what is
+needed when bringing kernels up without an interactive GPU."""
+import os
+import sys
+import traceback
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multi-feature-vit_b200"))
+sys.path.insert(0, ROOT)
+
+from mfvit import ops  # noqa: E402
+from mfvit._lib import EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESID_F32, FusionGrads  # noqa: E402
+
+dev = torch.device("cuda:0")
+RESULTS = []
+
+
+def report(name, got, ref, tol, rel=False):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    maxerr = err.max().item()
+    val = maxerr / denom if rel else maxerr
+    cos = F.cosine_similarity(got.flatten().double(), ref.flatten().double(), dim=0).item()
+    ok = bool(val <= tol) and not bool(torch.isnan(got).any())
+    RESULTS.append((name, ok))
+    print("%-52s %s maxerr=%.3e (ref max %.3e) %s=%.3e tol=%.1e cos=%.6f" % (
+        name, "OK  " if ok else "FAIL", maxerr, denom, "rel" if rel else "abs", val, tol, cos), flush=True)
+    return ok
+
+
+def run(name, fn, flt):
+    if flt and flt not in name:
+        return
+    try:
+        fn()
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        RESULTS.append((name, False))
+        print("%-52s EXCEPTION\n%s" % (name, traceback.format_exc()), flush=True)
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------------------ GEMM
+def t_gemm_fwd(G, M, N, K, block_n=0):
+    def f():
+        torch.manual_seed(0)
+        x = bf(torch.randn(G, M, K, device=dev))
+        w = bf(torch.randn(G, N, K, device=dev) * 0.05)
+        b = torch.randn(G, N, device=dev)
+        ref = torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :]
+        out = ops.linear_fwd(x, w, b, EPI_BF16, block_n=block_n)
+        report("gemm_fwd bf16 G%d M%d N%d K%d bn%d" % (G, M, N, K, block_n), out, ref, 2e-2, rel=True)
+        out32 = ops.linear_fwd(x, w, b, EPI_F32, block_n=block_n)
+        report("gemm_fwd f32  G%d M%d N%d K%d bn%d" % (G, M, N, K, block_n), out32, ref, 1e-4, rel=True)
+    return f
+
+
+def t_gemm_epilogues():
+    torch.manual_seed(1)
+    G, M, N, K = 2, 1000, 384, 256
+    x = bf(torch.randn(G, M, K, device=dev))
+    w = bf(torch.randn(G, N, K, device=dev) * 0.05)
+    b = torch.randn(G, N, device=dev)
+    res = torch.randn(G, M, N, device=dev)
+    acc = torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :]
+    out = ops.linear_fwd(x, w, b, EPI_RESID_F32, aux=res)
+    report("gemm epilogue resid_f32", out, acc + res, 1e-4, rel=True)
+    u = torch.empty(G, M, N, device=dev, dtype=torch.bfloat16)
+    g = torch.empty_like(u)
+    ops.linear_fwd(x, w, b, EPI_GELU, out=u, out2=g)
+    report("gemm epilogue gelu: u", u, acc, 2e-2, rel=True)
+    report("gemm epilogue gelu: g", g, F.gelu(acc), 2e-2, rel=True)
+    # dgelu: C = (dy @ W) * gelu'(u)
+    dy = bf(torch.randn(G, M, N, device=dev))
+    w2 = bf(torch.randn(G, N, K, device=dev) * 0.05)  # [N,K] -> dx [M,K]
+    upre = bf(torch.randn(G, M, K, device=dev))
+    dxr = torch.einsum("gmn,gnk->gmk", dy.float(), w2.float())
+    uu = upre.float().requires_grad_(True)
+    F.gelu(uu).backward(torch.ones_like(uu))
+    out = ops.linear_dgrad(dy, w2, EPI_DGELU, aux=upre)
+    report("gemm dgrad + dgelu", out, dxr * uu.grad, 2e-2, rel=True)
+    out = ops.linear_dgrad(dy, w2, EPI_BF16)
+    report("gemm dgrad (B mn-major)", out, dxr, 2e-2, rel=True)
+
+
+def t_gemm_wgrad(G, M, N, K, splits):
+    def f():
+        torch.manual_seed(2)
+        dy = bf(torch.randn(G, M, N, device=dev))
+        x = bf(torch.randn(G, M, K, device=dev))
+        ref = torch.einsum("gmn,gmk->gnk", dy.float(), x.float())
+        dw = torch.zeros(G, N, K, device=dev)
+        ops.linear_wgrad(dy, x, dw, splits=splits)
+        report("gemm wgrad G%d M%d N%d K%d s%d" % (G, M, N, K, splits), dw, ref, 1e-4, rel=True)
+    return f
+
+
+# ------------------------------------------------------------------------------------------------------------ LN
+def t_ln():
+    torch.manual_seed(3)
+    G, rows, C = 2, 1234, 384
+    x = torch.randn(G, rows, C, device=dev) * 2 + 0.5
+    gam = torch.randn(G, C, device=dev)
+    bet = torch.randn(G, C, device=dev)
+    y16, y32, mean, rstd = ops.layernorm_fwd(x, gam, bet, 1e-6, want_bf16=True, want_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr = gam.clone().requires_grad_(True)
+    br = bet.clone().requires_grad_(True)
+    ref = torch.stack([F.layer_norm(xr[g], (C,), gr[g], br[g], 1e-6) for g in range(G)])
+    report("layernorm fwd f32", y32, ref, 1e-5)
+    report("layernorm fwd bf16", y16, ref, 2e-2, rel=True)
+    dy = torch.randn_like(x)
+    dres = torch.randn_like(x)
+    ref.backward(dy)
+    dgam = torch.zeros_like(gam)
+    dbet = torch.zeros_like(bet)
+    dx, dx16 = ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dgam, dbeta=dbet)
+    report("layernorm bwd dx (f32 dy, +dres)", dx, xr.grad + dres, 1e-4)
+    report("layernorm bwd dx bf16 copy", dx16, xr.grad + dres, 2e-2, rel=True)
+    report("layernorm bwd dgamma", dgam, gr.grad, 1e-3, rel=True)
+    report("layernorm bwd dbeta", dbet, br.grad, 1e-3, rel=True)
+    dx2, _ = ops.layernorm_bwd(bf(dy), x, mean, rstd, gam)
+    report("layernorm bwd dx (bf16 dy)", dx2, xr.grad, 3e-2, rel=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ attention
+def t_attn(NB, S, H, D):
+    def f():
+        torch.manual_seed(4)
+        qkv = bf(torch.randn(NB, S, 3, H, D, device=dev))
+        o, lse = ops.attn_fwd(qkv, H)
+        q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3)]
+        s = (q @ k.transpose(-1, -2)) * D ** -0.5
+        ref = (s.softmax(-1) @ v)
+        tag = "NB%d S%d H%d D%d" % (NB, S, H, D)
+        report("attn fwd o " + tag, o.permute(0, 2, 1, 3), ref, 2e-2, rel=True)
+        report("attn fwd lse " + tag, lse, torch.logsumexp(s, -1), 1e-3)
+        do = bf(torch.randn(NB, S, H, D, device=dev))
+        ref.backward(do.float().permute(0, 2, 1, 3))
+        dqkv = ops.attn_bwd(qkv, o, do, lse)
+        for i, (nm, t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
+            report("attn bwd %s %s" % (nm, tag), dqkv[:, :, i].permute(0, 2, 1, 3), t.grad, 3e-2, rel=True)
+    return f
+
+
+# ------------------------------------------------------------------------------------------------------------ fusion
+def t_fusion():
+    from oracle.fusion_ref import Fus_CrossViT
+    torch.manual_seed(5)
+    B, S, C, heads, NC = 6, 197, 384, 3, 3
+
+    class Stub:
+        def features3D(self, x):
+            return x
+    fus = Fus_CrossViT(Stub(), Stub()).to(dev)
+    with torch.no_grad():
+        for p in fus.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    vh = [torch.nn.Linear(C, NC).to(dev) for _ in range(2)]
+    tok = (torch.randn(2, B, S, C, device=dev) * 1.5).requires_grad_(True)
+    fused_ref = fus.fuse(tok[0], tok[1])
+    cf = fus.closed_form(tok[0], tok[1])
+    report("fusion oracle closed-form == as-written", cf, fused_ref, 1e-5)
+    x_ref = torch.stack([vh[0](tok[0][:, 0]), vh[1](tok[1][:, 0])])
+    L = fus.multi_scale_transformers[0].cross_attn_layers[0]
+    # direction 0: CXR cls queries ENH patches: PreNorm L[0], post-LN L[3], mlp_head_cxr, vit_cxr.head
+    # direction 1: ENH cls queries CXR patches: PreNorm L[2], post-LN L[1], mlp_head_enh, vit_enh.head
+    pre = (L[0], L[2]); post = (L[3], L[1]); heads_m = (fus.mlp_head_cxr[0], fus.mlp_head_enh[0])
+    names = {
+        "ln1_w": [m.norm.weight for m in pre], "ln1_b": [m.norm.bias for m in pre],
+        "wq": [m.fn.wq.weight for m in pre], "wk": [m.fn.wk.weight for m in pre], "wv": [m.fn.wv.weight for m in pre],
+        "proj_w": [m.fn.proj.weight for m in pre], "proj_b": [m.fn.proj.bias for m in pre],
+        "ln2_w": [m.weight for m in post], "ln2_b": [m.bias for m in post],
+        "head_w": [m.weight for m in heads_m], "head_b": [m.bias for m in heads_m],
+        "vhead_w": [m.weight for m in vh], "vhead_b": [m.bias for m in vh],
+    }
+    prm = ops.fusion_param_struct({k: tuple(t.detach() for t in v) for k, v in names.items()})
+    fused, x = ops.fusion_fwd(tok.detach(), prm, B, S, C, heads, NC)
+    report("fusion fwd fused", fused, fused_ref, 1e-4)
+    report("fusion fwd x (backbone heads)", x, x_ref, 1e-4)
+    d_fused = torch.randn(B, NC, device=dev)
+    d_x = torch.randn(2, B, NC, device=dev)
+    (fused_ref * d_fused).sum().add((x_ref * d_x).sum()).backward()
+    gt = {k: tuple(torch.zeros_like(t) for t in v) for k, v in names.items()}
+    grads = ops.fusion_param_struct(gt, cls=FusionGrads)
+    dtok = ops.fusion_bwd(tok.detach(), prm, grads, d_fused, d_x, B, S, C, heads, NC)
+    report("fusion bwd dtok", dtok, tok.grad, 1e-3, rel=True)
+    for k, v in names.items():
+        for d in range(2):
+            report("fusion bwd d%s[%d]" % (k, d), gt[k][d], v[d].grad, 2e-3, rel=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ misc
+def t_ema():
+    torch.manual_seed(6)
+    sizes = [384, 1152 * 384, 7, 1536 * 384 + 3, 100000]
+    ks = [torch.randn(n, device=dev) for n in sizes]
+    qs = [torch.randn(n, device=dev) for n in sizes]
+    m = 0.99
+    ref = [k * m + q * (1. - m) for k, q in zip(ks, qs)]
+    chunks, n, mx = ops.make_ema_chunks(list(zip(ks, qs)), dev)
+    ops.ema_update_(chunks, n, mx, m)
+    bad = sum(int((a != b).sum().item()) for a, b in zip(ks, ref))
+    RESULTS.append(("ema bit-exact", bad == 0))
+    print("%-52s %s mismatching elements=%d (chunks=%d)" % ("ema bit-exact vs eager k*m+q*(1.-m)", "OK  " if bad == 0 else "FAIL", bad, n))
+    flat_k = torch.randn(5_000_000, device=dev)
+    flat_q = torch.randn(5_000_000, device=dev)
+    r = flat_k * 0.996 + flat_q * (1. - 0.996)
+    chunks, n, mx = ops.make_ema_chunks([(flat_k[:3_000_000], flat_q[:3_000_000]), (flat_k[3_000_000:], flat_q[3_000_000:])], dev)
+    ops.ema_update_(chunks, n, mx, 0.996)
+    bad = int((flat_k != r).sum().item())
+    RESULTS.append(("ema bit-exact flat", bad == 0))
+    print("%-52s %s mismatching elements=%d (merged chunks=%d)" % ("ema bit-exact flat", "OK  " if bad == 0 else "FAIL", bad, n))
+
+
+def t_infonce():
+    from oracle.moco_ref import infonce_logits
+    torch.manual_seed(7)
+    N, D, K, T = 128, 256, 65536, 0.2
+    q = torch.randn(N, D, device=dev, requires_grad=True)
+    k = torch.randn(N, D, device=dev)
+    queue = F.normalize(torch.randn(D, K, device=dev), dim=0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    logits_ref, labels, qn_ref, kn_ref = infonce_logits(q, k, queue, T)
+    loss_ref = F.cross_entropy(logits_ref, labels)
+    loss_ref.backward()
+    qn, kn, logits, lse, loss = ops.infonce_fwd(q.detach(), k, queue, T)
+    report("infonce qn", qn, qn_ref, 1e-6)
+    report("infonce logits", logits, logits_ref, 1e-4)
+    report("infonce lse", lse[:N], torch.logsumexp(logits_ref, 1), 1e-4)
+    report("infonce loss", loss, loss_ref.reshape(1), 1e-4)
+    dq = ops.infonce_bwd(q.detach(), qn, kn, queue, logits, lse, T)
+    report("infonce dq (fused CE)", dq, q.grad, 2e-3, rel=True)
+    dl = torch.randn_like(logits_ref) * 1e-3
+    q2 = q.detach().clone().requires_grad_(True)
+    l2, _, _, _ = infonce_logits(q2, k, queue, T)
+    (l2 * dl).sum().backward()
+    dq2 = ops.infonce_bwd(q.detach(), qn, kn, queue, logits, lse, T, dlogits=dl)
+    report("infonce dq (external dlogits)", dq2, q2.grad, 2e-3, rel=True)
+    keys = torch.randn(256, D, device=dev)
+    qq = queue.clone()
+    ops.enqueue_keys_(keys, qq, 1024)
+    ref = queue.clone()
+    ref[:, 1024:1024 + 256] = keys.t()
+    report("enqueue keys", qq, ref, 0.0)
+
+
+def t_small():
+    torch.manual_seed(8)
+    B, C, NC = 37, 384, 3
+    a, b, c = [torch.randn(B, NC, device=dev, requires_grad=True) for _ in range(3)]
+    tgt = torch.randint(0, NC, (B,), device=dev)
+    lr = F.cross_entropy(a + b + c, tgt)
+    lr.backward()
+    loss, dl = ops.ce_small(a.detach(), b.detach(), c.detach(), tgt)
+    report("ce_small loss", loss, lr.reshape(1), 1e-5)
+    report("ce_small dlogits", dl, a.grad, 1e-6)
+    x = torch.randn(B, 197, C, device=dev, requires_grad=True)
+    lin = torch.nn.Linear(C, NC).to(dev)
+    y_ref = lin(x[:, 0])
+    y = ops.linear_small_fwd(x.detach(), 197 * C, lin.weight.detach(), lin.bias.detach(), B)
+    report("linear_small fwd", y, y_ref, 1e-4)
+    dy = torch.randn(B, NC, device=dev)
+    y_ref.backward(dy)
+    dx = torch.zeros_like(x)
+    dw = torch.zeros_like(lin.weight)
+    db = torch.zeros_like(lin.bias)
+    ops.linear_small_bwd(x.detach(), 197 * C, lin.weight.detach(), dy, dx, 197 * C, dw, db, B)
+    report("linear_small bwd dx", dx, x.grad, 1e-5)
+    report("linear_small bwd dw", dw, lin.weight.grad, 1e-4)
+    report("linear_small bwd db", db, lin.bias.grad, 1e-4)
+    # column sums
+    xb = bf(torch.randn(2, 3001, 1536, device=dev))
+    out = torch.zeros(2, 1536, device=dev)
+    ops.colsum_bf16(xb, out)
+    report("colsum bf16", out, xb.float().sum(1), 1e-3, rel=True)
+    # cast / optimisers
+    p = torch.randn(100003, device=dev)
+    report("cast bf16", ops.cast_bf16(p[:100000]), p[:100000], 1e-2, rel=True)
+    p0 = torch.randn(70001, device=dev)
+    g0 = torch.randn(70001, device=dev)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pt], lr=0.1, momentum=0.9, weight_decay=1e-4)
+    pm = p0.clone()
+    buf = torch.zeros_like(pm)
+    sh = torch.empty_like(pm, dtype=torch.bfloat16)
+    for it in range(3):
+        pt.grad = g0 * (it + 1)
+        opt.step()
+        ops.sgd_step_(pm, g0 * (it + 1), buf, sh, 0.1, 0.9, 1e-4, it == 0)
+    report("sgd 3 steps", pm, pt.detach(), 1e-5)
+    report("sgd shadow", sh, pm, 1e-2, rel=True)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=1e-3, weight_decay=0.1)
+    pm = p0.clone()
+    m1 = torch.zeros_like(pm)
+    m2 = torch.zeros_like(pm)
+    for it in range(3):
+        pt.grad = g0 * (it + 1)
+        opt.step()
+        ops.adam_step_(pm, g0 * (it + 1), m1, m2, None, 1e-3, (0.9, 0.999), 1e-8, 0.1, True, it + 1)
+    report("adamw 3 steps", pm, pt.detach(), 1e-5)
+
+
+def main():
+    flt = sys.argv[1] if len(sys.argv) > 1 else ""
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+    run("gemm_fwd small", t_gemm_fwd(1, 128, 64, 64, 64), flt)
+    run("gemm_fwd small128", t_gemm_fwd(1, 256, 128, 128, 128), flt)
+    run("gemm_fwd qkv", t_gemm_fwd(2, 6304, 1152, 384), flt)
+    run("gemm_fwd qkv bn256", t_gemm_fwd(2, 6304, 1536, 384, 256), flt)
+    run("gemm_fwd ragged", t_gemm_fwd(2, 197 * 3, 384, 1536, 128), flt)
+    run("gemm epilogues", t_gemm_epilogues, flt)
+    run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
+    run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
+    run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)
+    run("layernorm", t_ln, flt)
+    run("attn 197/64", t_attn(4, 197, 6, 64), flt)
+    run("attn 577/64", t_attn(2, 577, 6, 64), flt)
+    run("attn 197/32", t_attn(2, 197, 12, 32), flt)
+    run("attn 50/64", t_attn(3, 50, 2, 64), flt)
+    run("fusion", t_fusion, flt)
+    run("ema", t_ema, flt)
+    run("infonce", t_infonce, flt)
+    run("small ops", t_small, flt)
+    bad = [n for n, ok in RESULTS if not ok]
+    print("\n%d checks, %d failed" % (len(RESULTS), len(bad)))
+    for n in bad:
+        print("  FAILED:", n)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
