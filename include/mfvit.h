@@ -51,6 +51,7 @@ typedef struct {
   const void* B;
   void* C;
   void* C2;
+  void* C3;         /* MFV_EPI_GELU only: optional bf16 copy of C2 (kept for the backward GEMMs when C2 is fp16) */
   const void* bias; /* f32 [G][N] or NULL */
   const void* aux;
   int64_t M, N, K, G;
@@ -61,16 +62,18 @@ typedef struct {
   int32_t epilogue;
   int32_t splits;  /* split-K factor (only with MFV_EPI_ATOMIC_F32) */
   int32_t block_n; /* 0 = auto, else 64/128/256 */
-  int32_t reserved;
+  int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere) */
 } mfv_gemm_args;
 int mfv_gemm(const mfv_gemm_args* args, void* stream);
 
 /* ---- LayerNorm ------------------------------------------------------------------------------------------------------
  * Replaces nn.LayerNorm(384, eps=1e-6) x25 per branch in the absent timm ViT, PreNorm's LayerNorm (MOD:15-21).
- * x f32 [G][rows][C] -> y bf16 (GEMM operand) and/or y32 f32; mean/rstd f32 [G][rows] saved for backward.
+ * x f32 [G][rows][C] -> y16 (16-bit GEMM operand: bf16, or fp16 when y16_is_f16; optional extra bf16 copy for the
+ * backward GEMMs) and/or y32 f32; mean/rstd f32 [G][rows] saved for backward.
  * gamma/beta f32 [G][C] (group stride gb_gstride elements).                                                          */
-int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
-                      float* rstd, int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, float eps, void* stream);
+int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16, int y16_is_f16,
+                      void* y_bf16_copy, float* y_f32, float* mean, float* rstd, int64_t G, int64_t rows, int64_t C,
+                      int64_t gb_gstride, float eps, void* stream);
 /* dx = dres (optional residual-path gradient, f32) + LN'(dy); dy is bf16 (dy_bf16) or f32 (dy_f32).
  * Writes dx as f32 and (optionally) a bf16 copy that feeds the next dgrad/wgrad GEMMs.
  * dgamma/dbeta f32 [G][C] are ACCUMULATED (+=) with red.global.add.                                                   */
@@ -81,12 +84,14 @@ int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dre
 /* ---- fused softmax self-attention -----------------------------------------------------------------------------------
  * Replaces timm Attention: q@k^T*scale -> softmax -> @v and the transpose copies around it (same math
  * MOD:52-64).  qkv bf16 [NB][S][3][H][D] (the qkv GEMM's natural output), o bf16 [NB][S][H][D], lse f32 [NB][H][S].
+ * o may be written as fp16 (o_is_f16; proj GEMM operand of the fp16-forward mode) with an optional bf16 copy.
  * D in {32, 64}; any S >= 1 (197 @224^2, 577 @384^2).                                                                 */
-int mfv_attn_fwd(const void* qkv, void* o, float* lse, int64_t NB, int64_t S, int64_t H, int64_t D, float scale,
-                 void* stream);
-/* dqkv bf16 [NB][S][3][H][D]; delta f32 [NB][H][S] is scratch (rowsum(dO*O)).                                          */
-int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, void* dqkv,
-                 int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream);
+int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, int64_t NB,
+                 int64_t S, int64_t H, int64_t D, float scale, void* stream);
+/* dqkv bf16 [NB][S][3][H][D]; delta f32 [NB][H][S] is scratch (rowsum(dO*O)); o and d_o are bf16.  When the forward
+ * kept qkv in fp16 (qkv_is_f16) the tiles are converted to bf16 in shared memory: the backward always runs in bf16.                                        */
+int mfv_attn_bwd(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, float* delta,
+                 void* dqkv, int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream);
 
 /* ---- patch embedding -----------------------------------------------------------------------------------------------
  * Replaces timm PatchEmbed Conv2d(3,C,k=16,s=16)+flatten+transpose, cls-token concat and pos-embed add
@@ -94,7 +99,8 @@ int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* l
  * mfv_patchify: img f32 [G][B][3][HW][HW] -> patches bf16 [G][B*np][768] (k = c*256 + i*16 + j), np = (HW/16)^2.
  * The GEMM itself is mfv_gemm; mfv_embed_finish writes tokens x f32 [G][B][np+1][C]:
  *   row 0 = cls + pos[0], row 1+p = acc[p] + bias + pos[1+p].                                                         */
-int mfv_patchify(const float* img, void* patches, int64_t GB, int64_t HW, void* stream);
+int mfv_patchify(const float* img, void* patches, int patches_is_f16, void* patches_bf16_copy, int64_t GB, int64_t HW,
+                 void* stream);
 int mfv_embed_finish(const float* acc, const float* bias, const float* cls, const float* pos, float* x, int64_t G,
                      int64_t B, int64_t np, int64_t C, int64_t p_gstride, void* stream);
 /* backward of the above: dacc bf16 [G][B*np][C] (for the conv weight gradient GEMM), dbias/dcls accumulated.
@@ -171,10 +177,12 @@ int mfv_ema_update(const mfv_ema_chunk* chunks_dev, int64_t n_chunks, int64_t ma
 int mfv_infonce_fwd(const float* q_raw, const float* k_raw, const float* queue, float* qn, float* kn, float* logits,
                     float* lse, float* loss, int64_t N, int64_t D, int64_t K, float T, void* stream);
 /* d(q_raw) f32 [N][D] from the mean-CE loss (scaled by gscale), through /T, the logits and F.normalize.
- * dlogits_ext (optional, f32 [N][1+K]) lets autograd pass an arbitrary upstream gradient instead of the fused CE.   */
+ * dlogits_ext (optional, f32 [N][1+K]) lets autograd pass an arbitrary upstream gradient instead of the fused CE.
+ * queue_override (optional, f32 [D][ov_n]): the pre-enqueue contents of queue columns [ov_start, ov_start+ov_n), so the
+ * backward sees the queue the forward saw without the reference's 64 MiB queue.clone() (BLD:185).                     */
 int mfv_infonce_bwd(const float* q_raw, const float* qn, const float* kn, const float* queue, const float* logits,
-                    const float* lse, const float* dlogits_ext, float gscale, float* dq_raw, int64_t N, int64_t D,
-                    int64_t K, float T, void* stream);
+                    const float* lse, const float* dlogits_ext, const float* queue_override, int64_t ov_start,
+                    int64_t ov_n, float gscale, float* dq_raw, int64_t N, int64_t D, int64_t K, float T, void* stream);
 /* queue[:, ptr:ptr+n] = keys^T  (BLD:102); keys f32 [n][D] (already all-gathered, rank-major).                        */
 int mfv_enqueue_keys(const float* keys, float* queue, int64_t n, int64_t D, int64_t K, int64_t ptr, void* stream);
 
@@ -182,12 +190,14 @@ int mfv_enqueue_keys(const float* keys, float* queue, int64_t n, int64_t D, int6
  * Enqueues every kernel of the ViT-S/16 encoder forward / backward for G branches in one call (no per-kernel Python
  * round trips; capture-safe).  Replaces VisionTransformer.forward_features of the absent vits.py (timm): patch embed ->
  * +cls -> +pos -> depth x Block -> norm, and its autograd backward.  All buffers are caller-owned.
- * Parameter addressing: tensor t of group g lives at master + g*P + off_t (f32) and shadow + g*P + off_t (bf16 copy).  */
+ * Parameter addressing: tensor t of group g lives at master + g*P + off_t (f32), shadow + g*P + off_t (bf16 copy) and
+ * shadow16 + g*P + off_t (fp16 copy).                                                                                   */
 typedef struct {
   int64_t G, B, S, C, H, depth, hidden, img, np;
   int64_t P;
   const float* master;
-  const void* shadow;
+  const void* shadow;   /* bf16 [G][P] */
+  const void* shadow16; /* fp16 [G][P] (fwd_f16 mode) */
   float* grad; /* f32 [G][P], accumulated into (caller zeroes) */
   int64_t off_cls, off_pos, off_pe_w, off_pe_b, off_norm_w, off_norm_b, off_block0, block_stride;
   int64_t r_ln1_w, r_ln1_b, r_qkv_w, r_qkv_b, r_proj_w, r_proj_b, r_ln2_w, r_ln2_b, r_fc1_w, r_fc1_b, r_fc2_w, r_fc2_b;
@@ -205,6 +215,12 @@ typedef struct {
   float* tokens;          /* f32  [G][M][C] final-normed tokens (features3D) */
   int32_t save_for_backward; /* 1: one slot per block (training); 0: slots are reused (inference / momentum encoder) */
   int32_t stop_grad_conv1;
+  /* fwd_f16 = 1: forward GEMM operands (patches, xn, attn_o, gact, weights) are IEEE fp16 (8x finer than bf16; keeps the
+   * logits within 2e-3 of the fp32 reference); the backward stays bf16 and reads the *_bf copies written alongside
+   * (only when save_for_backward).  fwd_f16 = 0: everything bf16, the *_bf pointers are unused.                        */
+  int32_t fwd_f16;
+  int32_t reserved;
+  void* patches_bf; void* xn_bf; void* attn_o_bf; void* gact_bf;
   /* backward only */
   const float* dtokens;   /* f32 [G][M][C] */
   float* dx[2];           /* f32 [G][M][C] ping-pong */
@@ -220,17 +236,17 @@ int mfv_vit_forward(const mfv_vit_plan* plan, void* stream);
 int mfv_vit_backward(const mfv_vit_plan* plan, void* stream);
 
 /* ---- elementwise / optimiser ------------------------------------------------------------------------------------------
- * f32 -> bf16 shadow weights for the GEMM operands.                                                                   */
-int mfv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+ * f32 master -> 16-bit shadow weights for the GEMM operands: bf16 (backward) and/or fp16 (forward); either may be NULL. */
+int mfv_cast_shadow(const float* src, void* dst_bf16, void* dst_f16, int64_t n, void* stream);
 int mfv_fill_f32(float* dst, float value, int64_t n, void* stream);
 /* torch.optim.SGD semantics (MAIN_CA:449): g += wd*p ; buf = mom*buf + g (buf = g on first step) ; p -= lr*buf.
  * Optionally refreshes the bf16 shadow in the same pass.                                                              */
-int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, int64_t n, float lr, float momentum,
-                 float weight_decay, int first_step, void* stream);
+int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, void* shadow_f16, int64_t n, float lr,
+                 float momentum, float weight_decay, int first_step, void* stream);
 /* torch.optim.Adam / AdamW semantics (MAIN_CA:457, MAIN_PRE:339); step is 1-based.                                    */
-int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int decoupled_wd, int64_t step,
-                  void* stream);
+int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, void* shadow_f16,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
+                  int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma16816_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ void mma_any(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16) mma16816_f16(c, a, b0, b1); else mma16816(c, a, b0, b1);
+}
+
 // Shared-memory tile [rows][D] bf16, 16-byte chunks XOR-swizzled so ldmatrix rows hit distinct banks.
 template <int D>
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
@@ -63,7 +74,7 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* ba
 
 // acc[j] (16 x 8 per n-tile j) += A(16 x D, register fragments) * Bt, with Bt rows = "n" index taken from a
 // [n][D] row-major tile (ldmatrix, no transpose).  Used for Q K^T, dO V^T, K Q^T, V dO^T.
-template <int D>
+template <int D, bool F16 = false>
 __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&afrag)[D / 16][4], const uint8_t* tile,
                                          int n_row0, int lane) {
   const uint32_t tbase = smem_u32(tile);
@@ -75,34 +86,56 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&af
       const int chunk = 2 * kk + ((lane >> 3) & 1);
       uint32_t b0, b1, b2, b3;
       ldsm_x4(tbase + tile_off<D>(row, chunk), b0, b1, b2, b3);
-      mma16816(acc[2 * jp], afrag[kk], b0, b1);
-      mma16816(acc[2 * jp + 1], afrag[kk], b2, b3);
+      mma_any<F16>(acc[2 * jp], afrag[kk], b0, b1);
+      mma_any<F16>(acc[2 * jp + 1], afrag[kk], b2, b3);
     }
   }
 }
 
 // out[j] (16 x 8 per d-tile j, D/8 tiles) += P(16 x 64, from accumulator registers, rounded to bf16) * B, with B rows =
 // reduction index taken from a [k][D] row-major tile (ldmatrix.trans).  Used for P V, dS K, P^T dO, dS^T Q.
-template <int D>
+template <int D, bool F16 = false>
 __device__ __forceinline__ void mma_p_b(float (&out)[D / 8][4], const float (&p)[8][4], const uint8_t* tile,
                                         int k_row0, int lane) {
   const uint32_t tbase = smem_u32(tile);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     uint32_t a[4];
-    a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
-    a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
-    a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
-    a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    if constexpr (F16) {
+      a[0] = pack_f16(p[2 * kk][0], p[2 * kk][1]);
+      a[1] = pack_f16(p[2 * kk][2], p[2 * kk][3]);
+      a[2] = pack_f16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+      a[3] = pack_f16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    } else {
+      a[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+      a[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+      a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+      a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    }
 #pragma unroll
     for (int jp = 0; jp < D / 16; ++jp) {
       const int row = k_row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
       const int chunk = 2 * jp + ((lane >> 4) & 1);
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(tbase + tile_off<D>(row, chunk), b0, b1, b2, b3);
-      mma16816(out[2 * jp], a, b0, b1);
-      mma16816(out[2 * jp + 1], a, b2, b3);
+      mma_any<F16>(out[2 * jp], a, b0, b1);
+      mma_any<F16>(out[2 * jp + 1], a, b2, b3);
     }
+  }
+}
+
+// In-place fp16 -> bf16 conversion of a shared-memory tile (elementwise, so the swizzle is irrelevant).  The forward
+// keeps q,k,v in fp16 (finer mantissa); the backward runs in bf16 (gradient range) and converts after the load.
+__device__ __forceinline__ void tile_f16_to_bf16(uint8_t* tile, int bytes) {
+  for (int i = threadIdx.x * 16; i < bytes; i += ATT_WARPS * 32 * 16) {
+    uint4 v = *reinterpret_cast<uint4*>(tile + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_f16(w[j]);
+      w[j] = pack_bf16(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(tile + i) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -119,7 +152,7 @@ __device__ __forceinline__ void load_afrag(uint32_t (&afrag)[D / 16][4], const u
 }
 
 // Write this warp's 16 x D fp32 fragments as bf16 rows (row stride in elements); rows >= S are skipped.
-template <int D>
+template <int D, bool F16 = false>
 __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], __nv_bfloat16* base, long long row_stride,
                                            int s_row0, int S, int lane, float mul0, float mul1) {
   const int g = lane >> 2, t = lane & 3;
@@ -128,19 +161,19 @@ __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], __nv_bf
   for (int j = 0; j < D / 8; ++j) {
     if (r0 < S)
       *reinterpret_cast<uint32_t*>(base + (long long)r0 * row_stride + j * 8 + 2 * t) =
-          pack_bf16(acc[j][0] * mul0, acc[j][1] * mul0);
+          F16 ? pack_f16(acc[j][0] * mul0, acc[j][1] * mul0) : pack_bf16(acc[j][0] * mul0, acc[j][1] * mul0);
     if (r1 < S)
       *reinterpret_cast<uint32_t*>(base + (long long)r1 * row_stride + j * 8 + 2 * t) =
-          pack_bf16(acc[j][2] * mul1, acc[j][3] * mul1);
+          F16 ? pack_f16(acc[j][2] * mul1, acc[j][3] * mul1) : pack_bf16(acc[j][2] * mul1, acc[j][3] * mul1);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
 // grid = (ceil(S/64), NB*H).  smem: K[Spad][D], V[Spad][D], Q[64][D].
-template <int D>
+template <int D, bool F16>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int S,
-                int H, float scale_log2) {
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o, int o_is_f16,
+                __nv_bfloat16* __restrict__ o_bf, float* __restrict__ lse, int S, int H, float scale_log2) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Spad = (S + 63) & ~63;
   uint8_t* sK = smem;
@@ -169,7 +202,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mma_a_bt<D>(s, qf, sK, kb, lane);
+    mma_a_bt<D, F16>(s, qf, sK, kb, lane);
     float mx0 = m0, mx1 = m1;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -202,13 +235,15 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     for (int j = 0; j < D / 8; ++j) {
       oacc[j][0] *= a0; oacc[j][1] *= a0; oacc[j][2] *= a1; oacc[j][3] *= a1;
     }
-    mma_p_b<D>(oacc, s, sV, kb, lane);
+    mma_p_b<D, F16>(oacc, s, sV, kb, lane);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const int row0 = q0 + warp * 16;
   __nv_bfloat16* ob = o + (long long)b * S * H * D + h * D;
-  store_rows<D>(oacc, ob, (long long)H * D, row0, S, lane, 1.f / l0, 1.f / l1);
+  if (o_is_f16) store_rows<D, true>(oacc, ob, (long long)H * D, row0, S, lane, 1.f / l0, 1.f / l1);
+  else store_rows<D, false>(oacc, ob, (long long)H * D, row0, S, lane, 1.f / l0, 1.f / l1);
+  if (o_bf) store_rows<D, false>(oacc, o_bf + (long long)b * S * H * D + h * D, (long long)H * D, row0, S, lane, 1.f / l0, 1.f / l1);
   if (t == 0) {
     const int g = lane >> 2;
     float* lb = lse + (long long)bh * S;
@@ -223,7 +258,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                    const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse, float* __restrict__ delta,
-                   __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, int S, int H, float scale, int qkv_is_f16) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Spad = (S + 63) & ~63;
   uint8_t* sK = smem;
@@ -275,6 +310,10 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 
   cp_async_wait_all();
   __syncthreads();
+  if (qkv_is_f16) {
+    tile_f16_to_bf16(sK, (2 * Spad + ATT_ROWS) * D * 2);  // sK, sV, sQ are contiguous
+    __syncthreads();
+  }
   uint32_t qf[D / 16][4], dof[D / 16][4];
   load_afrag<D>(qf, sQ, warp * 16, lane);
   load_afrag<D>(dof, sdO, warp * 16, lane);
@@ -313,7 +352,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                    int S, int H, float scale) {
+                    int S, int H, float scale, int qkv_is_f16) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Spad = (S + 63) & ~63;
   uint8_t* sQ = smem;
@@ -338,6 +377,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   }
   cp_async_wait_all();
   __syncthreads();
+  if (qkv_is_f16) {
+    tile_f16_to_bf16(sQ, Spad * D * 2);
+    tile_f16_to_bf16(sK, 2 * ATT_ROWS * D * 2);  // sK, sV contiguous
+    __syncthreads();
+  }
 
   uint32_t kf[D / 16][4], vf[D / 16][4];
   load_afrag<D>(kf, sK, warp * 16, lane);
@@ -389,8 +433,8 @@ static int set_smem(Kern kern, size_t bytes) {
 
 }  // namespace mfv
 
-extern "C" int mfv_attn_fwd(const void* qkv, void* o, float* lse, int64_t NB, int64_t S, int64_t H, int64_t D,
-                            float scale, void* stream) {
+extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse,
+                            int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream) {
   using namespace mfv;
   if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
   if (NB * H > 65535) return MFV_ERR_SHAPE;
@@ -400,20 +444,24 @@ extern "C" int mfv_attn_fwd(const void* qkv, void* o, float* lse, int64_t NB, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(o);
+  __nv_bfloat16* obf = reinterpret_cast<__nv_bfloat16*>(o_bf16_copy);
   int rc;
-  if (D == 64) {
-    if ((rc = set_smem(attn_fwd_kernel<64>, smem))) return rc;
-    attn_fwd_kernel<64><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, lse, (int)S, (int)H, scale * LOG2E);
-  } else {
-    if ((rc = set_smem(attn_fwd_kernel<32>, smem))) return rc;
-    attn_fwd_kernel<32><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, lse, (int)S, (int)H, scale * LOG2E);
-  }
+#define MFV_ATT_FWD(DD, FF)                                                                                          \
+  do {                                                                                                               \
+    if ((rc = set_smem(attn_fwd_kernel<DD, FF>, smem))) return rc;                                                   \
+    attn_fwd_kernel<DD, FF><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, o_is_f16, obf, lse, (int)S, (int)H,           \
+                                                                 scale * LOG2E);                                      \
+  } while (0)
+  if (D == 64) { if (qkv_is_f16) MFV_ATT_FWD(64, true); else MFV_ATT_FWD(64, false); }
+  else { if (qkv_is_f16) MFV_ATT_FWD(32, true); else MFV_ATT_FWD(32, false); }
+#undef MFV_ATT_FWD
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
 
-extern "C" int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, void* dqkv,
-                            int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream) {
+extern "C" int mfv_attn_bwd(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse,
+                            float* delta, void* dqkv, int64_t NB, int64_t S, int64_t H, int64_t D, float scale,
+                            void* stream) {
   using namespace mfv;
   if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
   if (NB * H > 65535) return MFV_ERR_SHAPE;
@@ -430,15 +478,15 @@ extern "C" int mfv_attn_bwd(const void* qkv, const void* o, const void* d_o, con
   if (D == 64) {
     if ((rc = set_smem(attn_bwd_dq_kernel<64>, smem_dq))) return rc;
     if ((rc = set_smem(attn_bwd_dkv_kernel<64>, smem_dkv))) return rc;
-    attn_bwd_dq_kernel<64><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale);
+    attn_bwd_dq_kernel<64><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale, qkv_is_f16);
     MFV_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<64><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale);
+    attn_bwd_dkv_kernel<64><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale, qkv_is_f16);
   } else {
     if ((rc = set_smem(attn_bwd_dq_kernel<32>, smem_dq))) return rc;
     if ((rc = set_smem(attn_bwd_dkv_kernel<32>, smem_dkv))) return rc;
-    attn_bwd_dq_kernel<32><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale);
+    attn_bwd_dq_kernel<32><<<grid, ATT_WARPS * 32, smem_dq, st>>>(q, op, dop, lse, delta, dq, (int)S, (int)H, scale, qkv_is_f16);
     MFV_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<32><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale);
+    attn_bwd_dkv_kernel<32><<<grid, ATT_WARPS * 32, smem_dkv, st>>>(q, dop, lse, delta, dq, (int)S, (int)H, scale, qkv_is_f16);
   }
   MFV_LAUNCH_CHECK();
   return MFV_OK;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -181,6 +182,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t v) {
+  __half2 t = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(t);
+}
 __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);
@@ -191,6 +200,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+// same, with independent A / B element formats (0 = fp16, 1 = bf16): kind::f16 accepts mixed 16-bit operands
+__host__ __device__ constexpr uint32_t make_idesc2(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N,
+                                                   uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
 }
 
 }  // namespace mfv

@@ -6,16 +6,24 @@
 namespace mfv {
 
 // ----------------------------------------------------------------------------------------------- cast / fill
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+// one read of the fp32 master, up to two 16-bit shadows (bf16 for backward GEMMs, fp16 for forward GEMMs)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                     __half* __restrict__ dst_h, long long n) {
   const long long n8 = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
-    reinterpret_cast<uint4*>(dst)[i] =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    if (dst)
+      reinterpret_cast<uint4*>(dst)[i] =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    if (dst_h)
+      reinterpret_cast<uint4*>(dst_h)[i] =
+          make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
   }
-  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16_rn(src[i]);
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (dst) dst[i] = __float2bfloat16_rn(src[i]);
+    if (dst_h) dst_h[i] = __float2half_rn(src[i]);
+  }
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ dst, float v, long long n) {
@@ -106,8 +114,8 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 
 // ----------------------------------------------------------------------------------------------- patch embedding glue
 // img f32 [GB][3][HW][HW] -> patches bf16 [GB*np][768], k = c*256 + i*16 + j.  One thread per 8 pixels of a row.
-__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches, long long GB,
-                                int HW) {
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ patches, int is_f16,
+                                __nv_bfloat16* __restrict__ patches_bf, long long GB, int HW) {
   const int chunks = HW / 8;
   const int pw = HW / 16;
   const long long total = GB * 3LL * HW * chunks;
@@ -122,8 +130,10 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
     const float4 a = __ldg(src), b = __ldg(src + 1);
     const long long p = gb * (long long)(pw * pw) + (y / 16) * pw + (x8 / 2);
     const int k = c * 256 + (y % 16) * 16 + (x8 % 2) * 8;
+    const uint4 bfv = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
     *reinterpret_cast<uint4*>(patches + p * 768 + k) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        is_f16 ? make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w)) : bfv;
+    if (patches_bf) *reinterpret_cast<uint4*>(patches_bf + p * 768 + k) = bfv;
   }
 }
 
@@ -255,7 +265,8 @@ ce_small_kernel(const float* __restrict__ a, const float* __restrict__ b, const 
 
 // ----------------------------------------------------------------------------------------------- optimiser steps
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                           __nv_bfloat16* __restrict__ shadow, long long n, float lr, float mom, float wd, int first) {
+                           __nv_bfloat16* __restrict__ shadow, __half* __restrict__ shadow_h, long long n, float lr,
+                           float mom, float wd, int first) {
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -277,6 +288,7 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     if (buf) reinterpret_cast<float4*>(buf)[i] = make_float4(bb[0], bb[1], bb[2], bb[3]);
     if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16(pp[0], pp[1]), pack_bf16(pp[2], pp[3]));
+    if (shadow_h) reinterpret_cast<uint2*>(shadow_h)[i] = make_uint2(pack_f16(pp[0], pp[1]), pack_f16(pp[2], pp[3]));
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float d = g[i] + wd * p[i];
@@ -284,12 +296,14 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     const float np_ = p[i] - lr * d;
     p[i] = np_;
     if (shadow) shadow[i] = __float2bfloat16_rn(np_);
+    if (shadow_h) shadow_h[i] = __float2half_rn(np_);
   }
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m1,
-                            float* __restrict__ m2, __nv_bfloat16* __restrict__ shadow, long long n, float lr, float b1,
-                            float b2, float eps, float wd, int decoupled, float bc1, float bc2_sqrt) {
+                            float* __restrict__ m2, __nv_bfloat16* __restrict__ shadow, __half* __restrict__ shadow_h,
+                            long long n, float lr, float b1, float b2, float eps, float wd, int decoupled, float bc1,
+                            float bc2_sqrt) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -304,6 +318,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     pv -= step_size * (a / denom);
     p[i] = pv;
     if (shadow) shadow[i] = __float2bfloat16_rn(pv);
+    if (shadow_h) shadow_h[i] = __float2half_rn(pv);
   }
 }
 
@@ -319,11 +334,12 @@ static inline unsigned grid_for(long long work_items, int threads, int max_block
 using namespace mfv;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
-extern "C" int mfv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+extern "C" int mfv_cast_shadow(const float* src, void* dst_bf16, void* dst_f16, int64_t n, void* stream) {
   if (n <= 0) return MFV_OK;
-  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return MFV_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_bf16) | reinterpret_cast<uintptr_t>(dst_f16)) & 15)
+    return MFV_ERR_ALIGN;
   cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+      src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), reinterpret_cast<__half*>(dst_f16), n);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
@@ -364,11 +380,13 @@ extern "C" int mfv_colsum_bf16(const void* x, float* out, int64_t G, int64_t row
   return MFV_OK;
 }
 
-extern "C" int mfv_patchify(const float* img, void* patches, int64_t GB, int64_t HW, void* stream) {
+extern "C" int mfv_patchify(const float* img, void* patches, int is_f16, void* patches_bf16_copy, int64_t GB,
+                            int64_t HW, void* stream) {
   if (GB <= 0 || HW <= 0 || HW % 16) return MFV_ERR_SHAPE;
   const long long total = GB * 3 * HW * (HW / 8);
   patchify_kernel<<<grid_for(total, 256, 32 * num_sms()), 256, 0, STREAM(stream)>>>(
-      img, reinterpret_cast<__nv_bfloat16*>(patches), GB, (int)HW);
+      img, reinterpret_cast<__nv_bfloat16*>(patches), is_f16, reinterpret_cast<__nv_bfloat16*>(patches_bf16_copy), GB,
+      (int)HW);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
@@ -422,26 +440,27 @@ extern "C" int mfv_ce_small(const float* a, const float* b, const float* c, cons
   return MFV_OK;
 }
 
-extern "C" int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, int64_t n, float lr,
-                            float momentum, float weight_decay, int first_step, void* stream) {
+extern "C" int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, void* shadow_f16, int64_t n,
+                            float lr, float momentum, float weight_decay, int first_step, void* stream) {
   if (n <= 0) return MFV_OK;
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(buf)) & 15)
     return MFV_ERR_ALIGN;
   sgd_kernel<<<grid_for(n / 4 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
-      p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, momentum, weight_decay, first_step);
+      p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n, lr, momentum,
+      weight_decay, first_step);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
 
-extern "C" int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
-                             float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
-                             int64_t step, void* stream) {
+extern "C" int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                             void* shadow_f16, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int decoupled_wd, int64_t step, void* stream) {
   if (n <= 0) return MFV_OK;
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
   adam_kernel<<<grid_for(n, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
-      p, g, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps, weight_decay,
-      decoupled_wd, bc1, sqrtf(bc2));
+      p, g, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n,
+      lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, sqrtf(bc2));
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }

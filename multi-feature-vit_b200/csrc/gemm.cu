@@ -25,12 +25,14 @@ struct GemmParams {
   int M, N, K, G;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
   int a_mn, b_mn;  // 1 = MN-major operand
+  int a_f16, b_f16, out_f16;  // 1 = IEEE fp16 instead of bf16 (operands may be mixed)
   int epi;
   long long ldc, c_gstride;        // elements
   long long aux_ld, aux_gstride;   // residual (fp32) or pre-activation u (bf16)
   long long bias_gstride;
   void* C;
   void* C2;
+  void* C3;
   const float* bias;
   const void* aux;
 };
@@ -124,7 +126,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(1u, BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kadv = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
       const uint32_t b_kadv = p.b_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
@@ -198,10 +200,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         switch (p.epi) {
           case MFV_EPI_BF16: {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + crow + n0);
+            if (p.out_f16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                                  pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_uint4(pack_f16(f[8 * i], f[8 * i + 1]), pack_f16(f[8 * i + 2], f[8 * i + 3]),
+                                    pack_f16(f[8 * i + 4], f[8 * i + 5]), pack_f16(f[8 * i + 6], f[8 * i + 7]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
+                                    pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+            }
           } break;
           case MFV_EPI_GELU: {  // C = u (pre-activation, saved for backward), C2 = gelu(u)
             uint4* du = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + crow + n0);
@@ -213,8 +222,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float gl[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) gl[j] = gelu_erf(f[8 * i + j]);
-              dg[i] = make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
-                                 pack_bf16(gl[6], gl[7]));
+              if (p.C3)
+                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C3) + crow + n0)[i] =
+                    make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
+                               pack_bf16(gl[6], gl[7]));
+              dg[i] = p.out_f16 ? make_uint4(pack_f16(gl[0], gl[1]), pack_f16(gl[2], gl[3]), pack_f16(gl[4], gl[5]),
+                                             pack_f16(gl[6], gl[7]))
+                                : make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
+                                             pack_bf16(gl[6], gl[7]));
             }
           } break;
           case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream)
@@ -273,7 +288,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ---------------------------------------------------------------------------------------------------- host side
 static int encode_operand_map(CUtensorMap* map, const void* base, int mn_major, long long rows_mn, long long k,
-                              long long ld, long long gstride, int groups, int box_mn) {
+                              long long ld, long long gstride, int groups, int box_mn, int is_f16) {
   // K-major : dims (k, rows_mn, G), strides (1, ld, gstride), box (64, box_mn, 1)
   // MN-major: dims (rows_mn, k, G), strides (1, ld, gstride), box (64, 64, 1)
   cuuint64_t dims[3];
@@ -292,7 +307,7 @@ static int encode_operand_map(CUtensorMap* map, const void* base, int mn_major, 
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MFV_ERR_ALIGN;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MFV_ERR_INIT;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
@@ -317,14 +332,15 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (p.splits > 1 && a->epilogue != MFV_EPI_ATOMIC_F32) return MFV_ERR_ARG;
   p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major; p.epi = a->epilogue;
+  p.a_f16 = a->dtype_flags & 1; p.b_f16 = (a->dtype_flags >> 1) & 1; p.out_f16 = (a->dtype_flags >> 2) & 1;
   p.ldc = a->ldc; p.c_gstride = a->c_gstride;
   p.aux_ld = a->aux_ld; p.aux_gstride = a->aux_gstride; p.bias_gstride = a->bias_gstride;
-  p.C = a->C; p.C2 = a->C2; p.bias = (const float*)a->bias; p.aux = a->aux;
+  p.C = a->C; p.C2 = a->C2; p.C3 = a->C3; p.bias = (const float*)a->bias; p.aux = a->aux;
 
   CUtensorMap tmA, tmB;
-  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM);
+  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, a->dtype_flags & 1);
   if (rc) return rc;
-  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN);
+  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN, (a->dtype_flags >> 1) & 1);
   if (rc) return rc;
 
   const int total = p.tiles_m * p.tiles_n * p.splits * p.G;

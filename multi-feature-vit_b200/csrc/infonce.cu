@@ -150,8 +150,8 @@ nce_finalize_kernel(const float* __restrict__ logits, const float* __restrict__ 
 // grid = (ctas, ceil(N/128)); each CTA walks key tiles ctas apart; 8 x 16 register tile per thread (128 x 256 out).
 __global__ void __launch_bounds__(NCE_THREADS)
 nce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ lse, const float* __restrict__ dlogits_ext,
-               const float* __restrict__ queue, float* __restrict__ dqn_accum, int N, int D, int K, float invT,
-               float gcoef) {
+               const float* __restrict__ queue, const float* __restrict__ ov, int ov_start, int ov_n,
+               float* __restrict__ dqn_accum, int N, int D, int K, float invT, float gcoef) {
   constexpr int TJ = 16;
   __shared__ float sP[TJ][NCE_TM + 4];  // g^T chunk: [j][n]
   __shared__ float sQ[TJ][256 + 4];     // queue^T chunk: [j][c]
@@ -174,7 +174,8 @@ nce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ lse, 
     }
     for (int i = threadIdx.x; i < D * TJ; i += NCE_THREADS) {
       const int c = i / TJ, j = i % TJ;
-      sQ[j][c] = queue[(size_t)c * K + j0 + j];
+      const int jj = j0 + j - ov_start;  // columns overwritten by the enqueue since the forward: use the saved copy
+      sQ[j][c] = (ov && jj >= 0 && jj < ov_n) ? ov[(size_t)c * ov_n + jj] : queue[(size_t)c * K + j0 + j];
     }
     __syncthreads();
 #pragma unroll 4
@@ -275,7 +276,8 @@ extern "C" int mfv_infonce_fwd(const float* q_raw, const float* k_raw, const flo
 }
 
 extern "C" int mfv_infonce_bwd(const float* q_raw, const float* qn, const float* kn, const float* queue,
-                               const float* logits, const float* lse, const float* dlogits_ext, float gscale,
+                               const float* logits, const float* lse, const float* dlogits_ext,
+                               const float* queue_override, int64_t ov_start, int64_t ov_n, float gscale,
                                float* dq_raw, int64_t N, int64_t D, int64_t K, float T, void* stream) {
   if (N <= 0 || D != 256 || K <= 0 || K % 32) return MFV_ERR_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -285,7 +287,8 @@ extern "C" int mfv_infonce_bwd(const float* q_raw, const float* qn, const float*
   if (rc) return rc;
   const unsigned ctas = (unsigned)num_sms();
   nce_bwd_kernel<<<dim3(ctas, (unsigned)((N + NCE_TM - 1) / NCE_TM)), NCE_THREADS, 0, st>>>(
-      logits, lse, dlogits_ext, queue, dq_raw, (int)N, (int)D, (int)K, invT, gcoef);
+      logits, lse, dlogits_ext, queue, queue_override, (int)ov_start, (int)ov_n, dq_raw, (int)N, (int)D, (int)K, invT,
+      gcoef);
   MFV_LAUNCH_CHECK();
   nce_bwd_finish_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(q_raw, qn, kn, logits, lse, dlogits_ext, dq_raw,
                                                                  (int)N, (int)D, K + 1, invT, gcoef);

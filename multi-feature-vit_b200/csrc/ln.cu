@@ -10,9 +10,9 @@ constexpr int LN_WARPS = 8;
 template <int NV>  // NV float4 per lane; C = NV * 128
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              __nv_bfloat16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long long rows_per_group, long long total_rows, long long gb_gstride,
-              float eps) {
+              __nv_bfloat16* __restrict__ y16, int y16_is_f16, __nv_bfloat16* __restrict__ y16b,
+              float* __restrict__ y32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              long long rows_per_group, long long total_rows, long long gb_gstride, float eps) {
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -49,9 +49,12 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
     o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
     if (y16) {
-      uint2 pk = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      uint2 pk = y16_is_f16 ? make_uint2(pack_f16(o.x, o.y), pack_f16(o.z, o.w))
+                            : make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       reinterpret_cast<uint2*>(y16 + row * C)[lane + 32 * i] = pk;
     }
+    if (y16b)  // bf16 copy kept for the backward GEMMs when the forward operand is fp16
+      reinterpret_cast<uint2*>(y16b + row * C)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     if (y32) reinterpret_cast<float4*>(y32 + row * C)[lane + 32 * i] = o;
   }
 }
@@ -140,19 +143,20 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
 
 }  // namespace mfv
 
-extern "C" int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
-                                 float* mean, float* rstd, int64_t G, int64_t rows, int64_t C, int64_t gb_gstride,
-                                 float eps, void* stream) {
+extern "C" int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16v, int y16_is_f16,
+                                 void* y_bf16_copy, float* y_f32, float* mean, float* rstd, int64_t G, int64_t rows,
+                                 int64_t C, int64_t gb_gstride, float eps, void* stream) {
   using namespace mfv;
   if (G <= 0 || rows <= 0) return MFV_ERR_SHAPE;
   const long long total = G * rows;
   const unsigned grid = (unsigned)((total + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16v);
+  __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y_bf16_copy);
   switch (C) {
-    case 256: ln_fwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
-    case 384: ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
-    case 768: ln_fwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
+    case 256: ln_fwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
+    case 384: ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
+    case 768: ln_fwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
     default: return MFV_ERR_SHAPE;
   }
   MFV_LAUNCH_CHECK();

@@ -35,14 +35,32 @@ struct PlanView {
   long long boff(int l, long long rel) const { return p->off_block0 + (long long)l * p->block_stride + rel; }
   const float* w32(long long off) const { return p->master + off; }
   const __nv_bfloat16* w16(long long off) const { return reinterpret_cast<const __nv_bfloat16*>(p->shadow) + off; }
+  // forward GEMM weight operand: fp16 shadow in fwd_f16 mode
+  const __nv_bfloat16* wf(long long off) const {
+    return reinterpret_cast<const __nv_bfloat16*>(p->fwd_f16 ? p->shadow16 : p->shadow) + off;
+  }
+  bool dual() const { return p->fwd_f16 && p->save_for_backward; }
+  // bf16 copies for the backward GEMMs (same slot indexing); alias the forward buffers in pure-bf16 mode
+  __nv_bfloat16* xn_b(int i) const {
+    return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->xn_bf) + (long long)slot(i) * MC : xn(i);
+  }
+  __nv_bfloat16* ao_b(int l) const {
+    return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->attn_o_bf) + (long long)slot(l) * MC : ao(l);
+  }
+  __nv_bfloat16* g_b(int l) const {
+    return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->gact_bf) + (long long)slot(l) * Mh : g(l);
+  }
+  const void* patches_b() const { return p->fwd_f16 ? p->patches_bf : p->patches; }
   float* gr(long long off) const { return p->grad + off; }
 };
 
 // y = x W^T (+bias): A = activations [G][M][K] bf16 K-major, B = weight [N][K] bf16 K-major
 static int linear_fwd(const PlanView& v, const void* A, long long K, long long w_off, long long b_off, long long N,
-                      int epi, void* C, void* C2, const void* aux, long long aux_ld, cudaStream_t st) {
+                      int epi, void* C, void* C2, void* C3, const void* aux, long long aux_ld, cudaStream_t st) {
   mfv_gemm_args a = {};
-  a.A = A; a.B = v.w16(w_off); a.C = C; a.C2 = C2;
+  a.A = A; a.B = v.wf(w_off); a.C = C; a.C2 = C2; a.C3 = C3;
+  // fp16 operands in fwd_f16 mode; 16-bit outputs consumed by the forward (GELU out, qkv) are fp16 too
+  a.dtype_flags = v.p->fwd_f16 ? (3 | 4) : 0;
   a.bias = b_off >= 0 ? v.w32(b_off) : nullptr;
   a.aux = aux;
   a.M = v.M; a.N = N; a.K = K; a.G = v.p->G;
@@ -102,6 +120,9 @@ static int check_plan(const mfv_vit_plan* p) {
   const long long d = p->C / p->H;
   if (d != 64 && d != 32) return MFV_ERR_SHAPE;
   if (p->P % 8) return MFV_ERR_ALIGN;
+  if (p->fwd_f16 && !p->shadow16) return MFV_ERR_ARG;
+  if (p->fwd_f16 && p->save_for_backward && (!p->patches_bf || !p->xn_bf || !p->attn_o_bf || !p->gact_bf))
+    return MFV_ERR_ARG;
   return MFV_OK;
 }
 
@@ -118,11 +139,14 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
   const long long rows_pe = p->B * p->np;
   // patch embedding: patchify (per group: images are separate caller tensors) -> GEMM(+bias) -> +cls, +pos
   for (int g = 0; g < G; ++g)
-    RC(mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768, p->B,
-                    p->img, st));
+    RC(mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768,
+                    p->fwd_f16,
+                    v.dual() ? reinterpret_cast<__nv_bfloat16*>(p->patches_bf) + (long long)g * rows_pe * 768 : nullptr,
+                    p->B, p->img, st));
   {
     mfv_gemm_args a = {};
-    a.A = p->patches; a.B = v.w16(p->off_pe_w); a.C = p->acc; a.bias = v.w32(p->off_pe_b);
+    a.A = p->patches; a.B = v.wf(p->off_pe_w); a.C = p->acc; a.bias = v.w32(p->off_pe_b);
+    a.dtype_flags = p->fwd_f16 ? 3 : 0;
     a.M = rows_pe; a.N = C; a.K = 768; a.G = G;
     a.lda = 768; a.ldb = 768; a.ldc = C;
     a.a_gstride = rows_pe * 768; a.b_gstride = p->P; a.c_gstride = rows_pe * C; a.bias_gstride = p->P;
@@ -135,23 +159,27 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
     float* x_in = v.x(2 * l);
     float* x_mid = v.x(2 * l + 1);
     float* x_out = v.x(2 * l + 2);
-    RC(mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), nullptr,
-                         v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f, st));
+    const bool dual = v.dual();
+    RC(mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), p->fwd_f16,
+                         dual ? v.xn_b(2 * l) : nullptr, nullptr, v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f,
+                         st));
     RC(linear_fwd(v, v.xn(2 * l), C, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), 3 * C, MFV_EPI_BF16, v.qkv(l),
-                  nullptr, nullptr, 0, st));
-    RC(mfv_attn_fwd(v.qkv(l), v.ao(l), v.lse(l), G * p->B, p->S, p->H, D, scale, st));
+                  nullptr, nullptr, nullptr, 0, st));
+    RC(mfv_attn_fwd(v.qkv(l), p->fwd_f16, v.ao(l), p->fwd_f16, dual ? v.ao_b(l) : nullptr, v.lse(l), G * p->B, p->S, p->H, D, scale,
+                    st));
     RC(linear_fwd(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), C, MFV_EPI_RESID_F32, x_mid, nullptr,
-                  x_in, C, st));
-    RC(mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), nullptr,
-                         v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C, p->P, 1e-6f, st));
+                  nullptr, x_in, C, st));
+    RC(mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), p->fwd_f16,
+                         dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C,
+                         p->P, 1e-6f, st));
     RC(linear_fwd(v, v.xn(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), Hd, MFV_EPI_GELU, v.u(l),
-                  v.g(l), nullptr, 0, st));
+                  v.g(l), dual ? v.g_b(l) : nullptr, nullptr, 0, st));
     RC(linear_fwd(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), C, MFV_EPI_RESID_F32, x_out, nullptr,
-                  x_mid, C, st));
+                  nullptr, x_mid, C, st));
   }
   const int last = 2 * (int)p->depth;
-  RC(mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, p->tokens, v.mean(last),
-                       v.rstd(last), G, M, C, p->P, 1e-6f, st));
+  RC(mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, 0, nullptr, p->tokens,
+                       v.mean(last), v.rstd(last), G, M, C, p->P, 1e-6f, st));
   return MFV_OK;
 }
 
@@ -171,19 +199,19 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
                        p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b), G, M, C, p->P, st));
   for (int l = (int)p->depth - 1; l >= 0; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
-    RC(linear_wgrad(v, p->dx16[cur], C, v.g(l), Hd, M, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), st));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), st));
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid, v.u(l), Hd, st));
-    RC(linear_wgrad(v, p->dhid, Hd, v.xn(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
+    RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
     RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
                          v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
                          v.gr(v.boff(l, p->r_ln2_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-    RC(linear_wgrad(v, p->dx16[cur], C, v.ao(l), C, M, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), st));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), st));
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, 0, st));
-    RC(mfv_attn_bwd(v.qkv(l), v.ao(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
-    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
+    RC(mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
+    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
     RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
                          v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
@@ -195,6 +223,6 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
   RC(mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
                           p->B, p->np, C, p->P, st));
   if (!p->stop_grad_conv1)
-    RC(linear_wgrad(v, p->dacc, C, p->patches, 768, rows_pe, p->off_pe_w, -1, st));
+    RC(linear_wgrad(v, p->dacc, C, v.patches_b(), 768, rows_pe, p->off_pe_w, -1, st));
   return MFV_OK;
 }

@@ -20,13 +20,13 @@ class MfvError(RuntimeError):
 
 class GemmArgs(C.Structure):
     _fields_ = [
-        ("A", c_vp), ("B", c_vp), ("C", c_vp), ("C2", c_vp), ("bias", c_vp), ("aux", c_vp),
+        ("A", c_vp), ("B", c_vp), ("C", c_vp), ("C2", c_vp), ("C3", c_vp), ("bias", c_vp), ("aux", c_vp),
         ("M", i64), ("N", i64), ("K", i64), ("G", i64),
         ("lda", i64), ("ldb", i64), ("ldc", i64),
         ("a_gstride", i64), ("b_gstride", i64), ("c_gstride", i64),
         ("aux_ld", i64), ("aux_gstride", i64), ("bias_gstride", i64),
         ("a_mn_major", i32), ("b_mn_major", i32), ("epilogue", i32), ("splits", i32), ("block_n", i32),
-        ("reserved", i32),
+        ("dtype_flags", i32),
     ]
 
 
@@ -49,13 +49,14 @@ class EmaChunk(C.Structure):
 class VitPlan(C.Structure):
     _fields_ = (
         [(n, i64) for n in ["G", "B", "S", "C", "H", "depth", "hidden", "img", "np", "P"]]
-        + [("master", c_vp), ("shadow", c_vp), ("grad", c_vp)]
+        + [("master", c_vp), ("shadow", c_vp), ("shadow16", c_vp), ("grad", c_vp)]
         + [(n, i64) for n in ["off_cls", "off_pos", "off_pe_w", "off_pe_b", "off_norm_w", "off_norm_b", "off_block0",
                               "block_stride", "r_ln1_w", "r_ln1_b", "r_qkv_w", "r_qkv_b", "r_proj_w", "r_proj_b",
                               "r_ln2_w", "r_ln2_b", "r_fc1_w", "r_fc1_b", "r_fc2_w", "r_fc2_b"]]
         + [("images", c_vp * 2)]
         + [(n, c_vp) for n in ["patches", "acc", "x", "xn", "stats", "qkv", "attn_o", "lse", "u", "gact", "tokens"]]
-        + [("save_for_backward", i32), ("stop_grad_conv1", i32)]
+        + [("save_for_backward", i32), ("stop_grad_conv1", i32), ("fwd_f16", i32), ("reserved", i32)]
+        + [(n, c_vp) for n in ["patches_bf", "xn_bf", "attn_o_bf", "gact_bf"]]
         + [("dtokens", c_vp), ("dx", c_vp * 2), ("dx16", c_vp * 2)]
         + [(n, c_vp) for n in ["dhid", "dxn", "d_o", "dqkv", "delta", "dacc"]]
     )
@@ -70,11 +71,11 @@ SIGNATURES = {
     "mfv_strerror": (C.c_char_p, [C.c_int]),
     "mfv_num_sms": (C.c_int, []),
     "mfv_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
-    "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
+    "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_layernorm_bwd": (C.c_int, [c_vp] * 11 + [i64, i64, i64, i64, c_vp]),
-    "mfv_attn_fwd": (C.c_int, [c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
-    "mfv_attn_bwd": (C.c_int, [c_vp] * 6 + [i64, i64, i64, i64, f32, c_vp]),
-    "mfv_patchify": (C.c_int, [c_vp, c_vp, i64, i64, c_vp]),
+    "mfv_attn_fwd": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
+    "mfv_attn_bwd": (C.c_int, [c_vp, C.c_int] + [c_vp] * 5 + [i64, i64, i64, i64, f32, c_vp]),
+    "mfv_patchify": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, i64, i64, c_vp]),
     "mfv_embed_finish": (C.c_int, [c_vp] * 5 + [i64] * 5 + [c_vp]),
     "mfv_embed_finish_bwd": (C.c_int, [c_vp] * 4 + [i64] * 5 + [c_vp]),
     "mfv_colsum_bf16": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
@@ -87,14 +88,14 @@ SIGNATURES = {
     "mfv_ce_small": (C.c_int, [c_vp] * 6 + [i64, i64, c_vp]),
     "mfv_ema_update": (C.c_int, [c_vp, i64, i64, f32, f32, c_vp]),
     "mfv_infonce_fwd": (C.c_int, [c_vp] * 8 + [i64, i64, i64, f32, c_vp]),
-    "mfv_infonce_bwd": (C.c_int, [c_vp] * 7 + [f32, c_vp, i64, i64, i64, f32, c_vp]),
+    "mfv_infonce_bwd": (C.c_int, [c_vp] * 8 + [i64, i64, f32, c_vp, i64, i64, i64, f32, c_vp]),
     "mfv_enqueue_keys": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
     "mfv_vit_forward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
     "mfv_vit_backward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
-    "mfv_cast_f32_bf16": (C.c_int, [c_vp, c_vp, i64, c_vp]),
+    "mfv_cast_shadow": (C.c_int, [c_vp, c_vp, c_vp, i64, c_vp]),
     "mfv_fill_f32": (C.c_int, [c_vp, f32, i64, c_vp]),
-    "mfv_sgd_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, i64, f32, f32, f32, C.c_int, c_vp]),
-    "mfv_adam_step": (C.c_int, [c_vp] * 5 + [i64, f32, f32, f32, f32, f32, C.c_int, i64, c_vp]),
+    "mfv_sgd_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, i64, f32, f32, f32, C.c_int, c_vp]),
+    "mfv_adam_step": (C.c_int, [c_vp] * 6 + [i64, f32, f32, f32, f32, f32, C.c_int, i64, c_vp]),
 }
 
 _lib = None

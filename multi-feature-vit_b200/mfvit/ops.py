@@ -24,24 +24,27 @@ def _stream():
 
 
 def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c_gstride=0, bias=None,
-         bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
-         splits=1, block_n=0):
+         bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, C3=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
+         splits=1, block_n=0, dtype_flags=0):
     lib = _lib_for(A)
     a = GemmArgs()
     a.A, a.B, a.C, a.C2, a.bias, a.aux = (A.data_ptr(), B.data_ptr(), Cout.data_ptr(),
                                            C2.data_ptr() if C2 is not None else None,
                                            bias.data_ptr() if bias is not None else None,
                                            aux.data_ptr() if aux is not None else None)
+    a.C3 = C3.data_ptr() if C3 is not None else None
     a.M, a.N, a.K, a.G = M, N, K, G
     a.lda, a.ldb, a.ldc = lda, ldb, ldc
     a.a_gstride, a.b_gstride, a.c_gstride = a_gstride, b_gstride, c_gstride
     a.aux_ld, a.aux_gstride, a.bias_gstride = aux_ld, aux_gstride, bias_gstride
     a.a_mn_major, a.b_mn_major, a.epilogue, a.splits, a.block_n = int(a_mn), int(b_mn), epilogue, splits, block_n
+    a.dtype_flags = dtype_flags
     check(lib.mfv_gemm(C.byref(a), _stream()), "mfv_gemm")
     return Cout
 
 
-def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=None, block_n=0):
+def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=None, block_n=0, dtype_flags=0,
+               out3=None):
     """x16 [G,M,K] bf16, w16 [G,N,K] bf16, bias [G,N] f32."""
     G, M, K = x16.shape
     N = w16.shape[1]
@@ -49,8 +52,8 @@ def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=
         out = torch.empty(G, M, N, device=x16.device,
                           dtype=torch.float32 if epilogue in (EPI_RESID_F32, EPI_F32) else torch.bfloat16)
     return gemm(x16, w16, out, M=M, N=N, K=K, G=G, lda=K, ldb=K, ldc=N, a_gstride=M * K, b_gstride=N * K,
-                c_gstride=M * N, bias=bias, bias_gstride=N, aux=aux, aux_ld=N, aux_gstride=M * N, C2=out2,
-                epilogue=epilogue, block_n=block_n)
+                c_gstride=M * N, bias=bias, bias_gstride=N, aux=aux, aux_ld=N, aux_gstride=M * N, C2=out2, C3=out3,
+                epilogue=epilogue, block_n=block_n, dtype_flags=dtype_flags)
 
 
 def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0):
@@ -71,15 +74,19 @@ def linear_wgrad(dy16, x16, dw, splits=8, block_n=128):
                 c_gstride=N * K, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, splits=splits, block_n=block_n)
 
 
-def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False):
+def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False, f16=False, bf16_copy=False):
     G, rows, Cd = x.shape
     lib = _lib_for(x)
-    y16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
+    y16 = torch.empty_like(x, dtype=torch.float16 if f16 else torch.bfloat16) if want_bf16 else None
+    ycopy = torch.empty_like(x, dtype=torch.bfloat16) if bf16_copy else None
     y32 = torch.empty_like(x) if want_f32 else None
     mean = torch.empty(G, rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
-    check(lib.mfv_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd), G, rows, Cd,
-                                gamma.stride(0) if gamma.dim() > 1 else 0, eps, _stream()), "mfv_layernorm_fwd")
+    check(lib.mfv_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y16), int(f16), _p(ycopy), _p(y32), _p(mean), _p(rstd),
+                                G, rows, Cd, gamma.stride(0) if gamma.dim() > 1 else 0, eps, _stream()),
+          "mfv_layernorm_fwd")
+    if bf16_copy:
+        return y16, y32, mean, rstd, ycopy
     return y16, y32, mean, rstd
 
 
@@ -96,23 +103,27 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, 
     return dx, dx16
 
 
-def attn_fwd(qkv, H):
-    """qkv bf16 [NB,S,3,H,D] -> o bf16 [NB,S,H,D], lse f32 [NB,H,S]."""
+def attn_fwd(qkv, H, f16=False, bf16_copy=False):
+    """qkv bf16 [NB,S,3,H,D] -> o (bf16 | fp16) [NB,S,H,D], lse f32 [NB,H,S] (+ optional bf16 copy of o)."""
     NB, S, three, Hh, D = qkv.shape
     assert three == 3 and Hh == H
     lib = _lib_for(qkv)
-    o = torch.empty(NB, S, H, D, device=qkv.device, dtype=torch.bfloat16)
+    o = torch.empty(NB, S, H, D, device=qkv.device, dtype=torch.float16 if f16 else torch.bfloat16)
+    ocopy = torch.empty(NB, S, H, D, device=qkv.device, dtype=torch.bfloat16) if bf16_copy else None
     lse = torch.empty(NB, H, S, device=qkv.device, dtype=torch.float32)
-    check(lib.mfv_attn_fwd(_p(qkv), _p(o), _p(lse), NB, S, H, D, float(D) ** -0.5, _stream()), "mfv_attn_fwd")
+    check(lib.mfv_attn_fwd(_p(qkv), int(qkv.dtype == torch.float16), _p(o), int(f16), _p(ocopy), _p(lse), NB, S, H, D, float(D) ** -0.5, _stream()),
+          "mfv_attn_fwd")
+    if bf16_copy:
+        return o, lse, ocopy
     return o, lse
 
 
 def attn_bwd(qkv, o, d_o, lse):
     NB, S, _, H, D = qkv.shape
     lib = _lib_for(qkv)
-    dqkv = torch.empty_like(qkv)
+    dqkv = torch.empty_like(qkv, dtype=torch.bfloat16)
     delta = torch.empty_like(lse)
-    check(lib.mfv_attn_bwd(_p(qkv), _p(o), _p(d_o), _p(lse), _p(delta), _p(dqkv), NB, S, H, D, float(D) ** -0.5,
+    check(lib.mfv_attn_bwd(_p(qkv), int(qkv.dtype == torch.float16), _p(o), _p(d_o), _p(lse), _p(delta), _p(dqkv), NB, S, H, D, float(D) ** -0.5,
                            _stream()), "mfv_attn_bwd")
     return dqkv
 
@@ -127,8 +138,13 @@ def colsum_bf16(x, out):
 def cast_bf16(src, dst=None):
     if dst is None:
         dst = torch.empty_like(src, dtype=torch.bfloat16)
-    check(_lib_for(src).mfv_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "mfv_cast_f32_bf16")
+    check(_lib_for(src).mfv_cast_shadow(_p(src), _p(dst), None, src.numel(), _stream()), "mfv_cast_shadow")
     return dst
+
+
+def cast_shadow(src, dst_bf16=None, dst_f16=None):
+    """One pass over the fp32 master writing the bf16 and/or fp16 GEMM-operand copies."""
+    check(_lib_for(src).mfv_cast_shadow(_p(src), _p(dst_bf16), _p(dst_f16), src.numel(), _stream()), "mfv_cast_shadow")
 
 
 def fill_(t, value=0.0):
@@ -228,12 +244,14 @@ def infonce_fwd(q_raw, k_raw, queue, T):
     return qn, kn, logits, lse, loss
 
 
-def infonce_bwd(q_raw, qn, kn, queue, logits, lse, T, dlogits=None, gscale=1.0):
+def infonce_bwd(q_raw, qn, kn, queue, logits, lse, T, dlogits=None, gscale=1.0, override=None, ov_start=0):
     N, D = q_raw.shape
     K = queue.shape[1]
     dq = torch.empty_like(q_raw)
+    ov_n = 0 if override is None else override.shape[1]
     check(_lib_for(q_raw).mfv_infonce_bwd(_p(q_raw), _p(qn), _p(kn), _p(queue), _p(logits), _p(lse), _p(dlogits),
-                                          float(gscale), _p(dq), N, D, K, float(T), _stream()), "mfv_infonce_bwd")
+                                          _p(override), int(ov_start), int(ov_n), float(gscale), _p(dq), N, D, K,
+                                          float(T), _stream()), "mfv_infonce_bwd")
     return dq
 
 
@@ -243,12 +261,12 @@ def enqueue_keys_(keys, queue, ptr):
     check(_lib_for(keys).mfv_enqueue_keys(_p(keys), _p(queue), n, D, K, int(ptr), _stream()), "mfv_enqueue_keys")
 
 
-def sgd_step_(p, g, buf, shadow, lr, momentum, weight_decay, first_step):
-    check(_lib_for(p).mfv_sgd_step(_p(p), _p(g), _p(buf), _p(shadow), p.numel(), float(lr), float(momentum),
+def sgd_step_(p, g, buf, shadow, lr, momentum, weight_decay, first_step, shadow16=None):
+    check(_lib_for(p).mfv_sgd_step(_p(p), _p(g), _p(buf), _p(shadow), _p(shadow16), p.numel(), float(lr), float(momentum),
                                    float(weight_decay), int(bool(first_step)), _stream()), "mfv_sgd_step")
 
 
-def adam_step_(p, g, m1, m2, shadow, lr, betas, eps, weight_decay, decoupled, step):
-    check(_lib_for(p).mfv_adam_step(_p(p), _p(g), _p(m1), _p(m2), _p(shadow), p.numel(), float(lr), float(betas[0]),
+def adam_step_(p, g, m1, m2, shadow, lr, betas, eps, weight_decay, decoupled, step, shadow16=None):
+    check(_lib_for(p).mfv_adam_step(_p(p), _p(g), _p(m1), _p(m2), _p(shadow), _p(shadow16), p.numel(), float(lr), float(betas[0]),
                                     float(betas[1]), float(eps), float(weight_decay), int(bool(decoupled)), int(step),
                                     _stream()), "mfv_adam_step")

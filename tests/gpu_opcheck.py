@@ -136,15 +136,20 @@ def t_ln():
 
 
 # ------------------------------------------------------------------------------------------------------------ attention
-def t_attn(NB, S, H, D):
+def t_attn(NB, S, H, D, f16=False):
     def f():
         torch.manual_seed(4)
-        qkv = bf(torch.randn(NB, S, 3, H, D, device=dev))
-        o, lse = ops.attn_fwd(qkv, H)
+        qkv = torch.randn(NB, S, 3, H, D, device=dev)
+        qkv = qkv.half() if f16 else bf(qkv)
+        if f16:
+            o16, lse, o = ops.attn_fwd(qkv, H, f16=True, bf16_copy=True)
+            report("attn fwd o fp16 vs bf16 copy", o16, o, 1e-2, rel=True)
+        else:
+            o, lse = ops.attn_fwd(qkv, H)
         q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3)]
         s = (q @ k.transpose(-1, -2)) * D ** -0.5
         ref = (s.softmax(-1) @ v)
-        tag = "NB%d S%d H%d D%d" % (NB, S, H, D)
+        tag = "NB%d S%d H%d D%d%s" % (NB, S, H, D, " f16" if f16 else "")
         report("attn fwd o " + tag, o.permute(0, 2, 1, 3), ref, 2e-2, rel=True)
         report("attn fwd lse " + tag, lse, torch.logsumexp(s, -1), 1e-3)
         do = bf(torch.randn(NB, S, H, D, device=dev))
@@ -331,6 +336,8 @@ def main():
     run("attn 577/64", t_attn(2, 577, 6, 64), flt)
     run("attn 197/32", t_attn(2, 197, 12, 32), flt)
     run("attn 50/64", t_attn(3, 50, 2, 64), flt)
+    run("attn 197/64 f16", t_attn(4, 197, 6, 64, True), flt)
+    run("attn 577/32 f16", t_attn(1, 577, 12, 32, True), flt)
     run("fusion", t_fusion, flt)
     run("ema", t_ema, flt)
     run("infonce", t_infonce, flt)

@@ -1,0 +1,143 @@
+"""CPU: the drop-in boundary - the C-ABI library exports exactly what include/mfvit.h declares, and the Python module
+surface matches what the reference scripts touch.  No compute calls (no GPU here)."""
+import importlib
+import os
+import re
+from functools import partial
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FUS_MOD = ("model.crossvit_2vits_2additionaloutputs_changenormlayer_location_removeextralclayer_"
+           "changemodelinputlocation_std002_sum")
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mfvit.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mfv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mfvit import _lib
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libmfvit.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with include/mfvit.h"
+    assert lib.mfv_abi_version() == 1
+    assert b"unsupported shape" in lib.mfv_strerror(-1)
+
+
+def test_ctypes_struct_sizes_match_header_layout():
+    from mfvit import _lib
+    import ctypes
+    assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 13 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.FusionParams) == 13 * 2 * 8
+    assert ctypes.sizeof(_lib.EmaChunk) == 24
+    # mfv_vit_plan: 10 i64 + 4 ptr + 20 i64 + 2 ptr + 11 ptr + 4 i32 + 4 ptr + (1 + 2 + 2 + 6) ptr
+    assert ctypes.sizeof(_lib.VitPlan) == (10 + 4 + 20 + 2 + 11) * 8 + 16 + 4 * 8 + (1 + 2 + 2 + 6) * 8
+
+
+def test_cpu_forward_fails_loudly():
+    import vits_returnftrs as vits
+    from mfvit import MfvError
+    m = vits.vit_small(num_classes=3)
+    with pytest.raises(MfvError):
+        m(torch.randn(1, 3, 224, 224))
+    with pytest.raises(MfvError):
+        m.blocks[0](torch.randn(1, 197, 384))
+
+
+def test_vit_module_surface_and_init_parity():
+    import vits
+    import vits_returnftrs
+    from oracle import vit_ref
+    for name in ("vit_small", "vit_base", "vit_small_ori", "vit_base_ori", "vit_conv_small", "vit_conv_base"):
+        assert name in vits.__dict__ and name in vits_returnftrs.__dict__  # MAIN_CA:56-57,289
+    torch.manual_seed(7)
+    ours = vits_returnftrs.vit_small()
+    torch.manual_seed(7)
+    ref = vit_ref.vit_small()
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    assert list(sd_o.keys()) == list(sd_r.keys())
+    for k in sd_o:
+        assert torch.equal(sd_o[k], sd_r[k]), k  # identical RNG consumption -> identical init
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    assert not ours.pos_embed.requires_grad and ours.head.in_features == 384
+    # MAIN_CA:298-310: freeze all but head, replace head
+    for n, p in ours.named_parameters():
+        if n not in ("head.weight", "head.bias"):
+            p.requires_grad = False
+    ours.head = nn.Linear(ours.head.in_features, 3)
+    assert [n for n, p in ours.named_parameters() if p.requires_grad] == ["head.weight", "head.bias"]
+    # BLD:217-222: del head, assign an MLP
+    hidden = ours.head.weight.shape[1]
+    del ours.head
+    ours.head = nn.Sequential(nn.Linear(hidden, 8, bias=False), nn.BatchNorm1d(8))
+    assert "head.0.weight" in ours.state_dict()
+    sg = vits.vit_small(stop_grad_conv1=True)
+    assert not sg.patch_embed.proj.weight.requires_grad and not sg.patch_embed.proj.bias.requires_grad
+    assert vits.vit_small_ori().num_heads == 12 and vits.vit_small().num_heads == 6
+    with pytest.raises(NotImplementedError):
+        vits.vit_conv_small()
+
+
+def test_fusion_module_surface(golden_dir):
+    import vits_returnftrs as vits
+    fm = importlib.import_module(FUS_MOD)
+    inv = torch.load(os.path.join(golden_dir, "fusion_keys.pt"))
+    a, b = vits.vit_small(num_classes=3), vits.vit_small(num_classes=3)
+    f = fm.Fus_CrossViT(a, b)
+    assert {k: tuple(v.shape) for k, v in f.state_dict().items()} == inv["keys"]       # the reference's 22 keys
+    assert sum(p.numel() for p in f.parameters()) == inv["n_params"] == 1185798        # backbones NOT included
+    assert f.vit_features_cxr.__self__ is a and f.vit_features_enh.__self__ is b       # bound methods (FUS:80,83)
+    # same seed -> same init as the reference restatement (self.apply order)
+    from oracle import fusion_ref
+    torch.manual_seed(3)
+    f1 = fm.Fus_CrossViT(a, b)
+    torch.manual_seed(3)
+    f2 = fusion_ref.Fus_CrossViT(a, b)
+    for (k1, v1), (k2, v2) in zip(f1.state_dict().items(), f2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    mod = importlib.import_module("model.module")
+    for n in ("PreNorm", "CrossAttention", "Attention", "FeedForward"):
+        assert hasattr(mod, n)  # FUS:6 imports these names
+
+
+def test_moco_module_surface(golden_dir):
+    import vits
+    bm = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss")
+    inv = torch.load(os.path.join(golden_dir, "moco_keys.pt"))
+    m = bm.MoCo_ViT(partial(vits.vit_small, stop_grad_conv1=True), SimpleNamespace(arch="vit_small"), 256, 4096, 0.2)
+    assert sorted(m.state_dict().keys()) == inv["keys"]
+    assert sum(p.numel() for p in m.base_encoder.parameters()) == inv["n_base"] == 41080704
+    assert sum(p.numel() for p in m.predictor.parameters()) == inv["n_pred"] == 2105344
+    assert m.K == 65536 and m.queue.shape == (256, 65536) and m.queue_ptr.dtype == torch.long
+    assert all(not p.requires_grad for p in m.momentum_encoder.parameters())
+    for pb, pm in zip(m.base_encoder.parameters(), m.momentum_encoder.parameters()):
+        assert torch.equal(pb, pm)
+    assert hasattr(bm, "concat_all_gather") and hasattr(bm, "MoCo_ResNet")
+    # survives SyncBatchNorm conversion (MAIN_PRE:297)
+    m2 = nn.SyncBatchNorm.convert_sync_batchnorm(m)
+    assert any(isinstance(x, nn.SyncBatchNorm) for x in m2.modules())
+
+
+def test_layout_is_aligned_and_complete():
+    import vits
+    from mfvit.engine import ViTLayout
+    m = vits.vit_small(num_classes=3)
+    lay = ViTLayout(224, 16, 384, 12, 6, 1536)
+    names = [n for n, _ in m.named_parameters() if not n.startswith("head.")]
+    assert [n for n, _, _ in lay.entries] == names
+    assert all(o % 8 == 0 for _, _, o in lay.entries) and lay.P % 8 == 0
+    assert sum(p.numel() for n, p in m.named_parameters() if not n.startswith("head.")) <= lay.P
+    for n, shape, _ in lay.entries:
+        assert tuple(m.get_parameter(n).shape) == shape
+    # blocks are equally strided (the native runtime addresses block l at off_block0 + l*block_stride)
+    for i in range(12):
+        assert lay.offset["blocks.%d.norm1.weight" % i] == lay.off_block0 + i * lay.block_stride

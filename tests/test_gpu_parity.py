@@ -1,0 +1,204 @@
+"""GPU (B200) parity tests proper: everything below goes through the C ABI of libmfvit.so and is compared with the
+oracle (oracle/*.py, pure PyTorch fp32) on the same seeded weights and synthetic inputs.
+
+Tolerances (BASELINE.json north_star):
+  * fp32-accumulate logits vs the fp32 oracle ........ max abs diff <= 2e-3
+  * logits vs the bf16-autocast oracle ............... <= 2e-2 relative
+  * gradients ........................................ per-tensor cosine similarity >= 0.999
+  * EMA update ....................................... bit-exact in fp32
+"""
+import importlib
+import os
+import sys
+from functools import partial
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import e2e_common as E  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ABS_TOL = 2e-3
+LOGIT_BF16_REL_TOL = 2e-2
+GRAD_COS_TOL = 0.999
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_math():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def test_kernels_op_by_op():
+    """Every C-ABI kernel against a PyTorch fp32 reference of the same op (tests/gpu_opcheck.py)."""
+    import gpu_opcheck
+    gpu_opcheck.RESULTS.clear()
+    sys.argv = [sys.argv[0]]
+    assert gpu_opcheck.main() == 0, [n for n, ok in gpu_opcheck.RESULTS if not ok]
+
+
+@pytest.mark.parametrize("heads", [6, 12])
+def test_single_vit_forward_backward(heads):
+    """BASELINE config 1 shape: single-branch ViT-S/16 + 3-class head, B=16, fwd+bwd (MAIN_LPFT:711-718)."""
+    ref, ours = E.build_vit_pair(num_heads=heads)
+    img, _, tgt = E.synthetic_pair(16, 224, device="cuda")
+    out_r = ref(img)
+    F.cross_entropy(out_r, tgt).backward()
+    out_o = ours(img)
+    F.cross_entropy(out_o, tgt).backward()
+    err = (out_o - out_r).abs().max().item()
+    assert err <= LOGIT_ABS_TOL, "logits max abs diff %.3e" % err
+    mn, worst, _ = E.grad_report(ref.named_parameters(), ours.named_parameters())
+    assert mn >= GRAD_COS_TOL, "gradient cosine %.5f at %s" % (mn, worst)
+    tok_r, tok_o = ref.features3D(img).detach(), ours.features3D(img).detach()
+    assert tok_o.shape == (16, 197, 384)
+    assert (tok_o - tok_r).abs().max().item() <= 5e-2 and E.cos(tok_o, tok_r) > 0.9999
+
+
+@pytest.mark.parametrize("B", [4, 32])
+def test_mfvit_ca_forward_backward(B):
+    """BASELINE config 2: MF-ViT CA, two ViT-S/16 branches + CLS cross-attention fusion + summed aux heads."""
+    (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair()
+    img_c, img_e, tgt = E.synthetic_pair(B, 224, device="cuda")
+    out_r, loss_r, parts_r = E.mfvit_step(r_f, r_c, r_e, img_c, img_e, tgt)  # as written: 4 backbone passes
+    out_o, loss_o, parts_o = E.mfvit_step(o_f, o_c, o_e, img_c, img_e, tgt)
+    for name, a, b in zip(("fused", "x_cxr", "x_enh"), parts_o, parts_r):
+        err = (a - b).abs().max().item()
+        assert err <= LOGIT_ABS_TOL, "%s max abs diff %.3e" % (name, err)
+    assert abs(loss_o.item() - loss_r.item()) <= 2e-3
+    for tag, rm, om in (("fusion", r_f, o_f), ("cxr", r_c, o_c), ("enh", r_e, o_e)):
+        mn, worst, _ = E.grad_report(rm.named_parameters(), om.named_parameters())
+        assert mn >= GRAD_COS_TOL, "%s gradient cosine %.5f at %s" % (tag, mn, worst)
+    # bf16-autocast reference (the "reference eager bf16" baseline): relative bound
+    for m in (r_f, r_c, r_e):
+        m.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        fused, x_c, x_e = r_f(r_c, r_e, img_c, img_e, dedup=True)
+    out_b = (fused + x_c + x_e).float()
+    rel = (out_o - out_b).abs().max().item() / out_b.abs().max().item()
+    assert rel <= LOGIT_BF16_REL_TOL, "relative diff to bf16-autocast reference %.3e" % rel
+
+
+def test_mfvit_ca_frozen_backbones_and_eval():
+    """MAIN_CA without --semi-supervised: only head + fusion parameters train (MAIN_CA:298-305,435)."""
+    (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair(seed=3)
+    for m in (r_c, r_e, o_c, o_e):
+        for n, p in m.named_parameters():
+            if n not in ("head.weight", "head.bias"):
+                p.requires_grad = False
+    img_c, img_e, tgt = E.synthetic_pair(8, 224, rank=1, device="cuda")
+    out_r, _, _ = E.mfvit_step(r_f, r_c, r_e, img_c, img_e, tgt, dedup=True)
+    out_o, _, _ = E.mfvit_step(o_f, o_c, o_e, img_c, img_e, tgt)
+    assert (out_o - out_r).abs().max().item() <= LOGIT_ABS_TOL
+    assert o_c.blocks[0].attn.qkv.weight.grad is None
+    mn, worst, _ = E.grad_report(r_f.named_parameters(), o_f.named_parameters())
+    assert mn >= GRAD_COS_TOL, (mn, worst)
+    assert E.cos(o_c.head.weight.grad, r_c.head.weight.grad) >= GRAD_COS_TOL
+    with torch.no_grad():
+        f2, _, _ = o_f(o_c, o_e, img_c, img_e)
+    assert f2.shape == (8, 3)
+
+
+def test_mfvit_ca_384():
+    """BASELINE config 5 shape: 384x384 inputs, 577 tokens per branch (small batch for the parity check)."""
+    (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair(img_size=384, seed=5)
+    img_c, img_e, tgt = E.synthetic_pair(2, 384, device="cuda")
+    out_r, _, _ = E.mfvit_step(r_f, r_c, r_e, img_c, img_e, tgt, dedup=True)
+    out_o, _, _ = E.mfvit_step(o_f, o_c, o_e, img_c, img_e, tgt)
+    assert (out_o - out_r).abs().max().item() <= LOGIT_ABS_TOL
+    mn, worst, _ = E.grad_report(r_c.named_parameters(), o_c.named_parameters())
+    assert mn >= GRAD_COS_TOL, (mn, worst)
+
+
+def test_gradients_are_linear_in_upstream():
+    """Size-independent property at full config-2 size: backward is linear in the upstream gradient."""
+    _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=7)
+    img_c, img_e, tgt = E.synthetic_pair(32, 224, device="cuda")
+
+    def grads(scale):
+        for m in (o_f, o_c, o_e):
+            m.zero_grad(set_to_none=True)
+        fused, x_c, x_e = o_f(o_c, o_e, img_c, img_e)
+        (F.cross_entropy(fused + x_c + x_e, tgt) * scale).backward()
+        return {n: p.grad.clone() for n, p in o_c.named_parameters() if p.grad is not None}
+
+    g1, g3 = grads(1.0), grads(3.0)
+    for n in g1:
+        assert E.cos(g3[n], g1[n]) > 0.9999, n  # not bit-linear: bf16 rounding of scaled gradients, red.add order
+        ratio = (g3[n].norm() / g1[n].norm().clamp_min(1e-20)).item()
+        assert abs(ratio - 3.0) < 0.05, (n, ratio)
+
+
+def test_ema_bit_exact_full_model_and_moco_step():
+    """BASELINE config 4 logic on one GPU: EMA bit-exact (BLD:83-89), logits/labels/queue semantics (BLD:154-199)."""
+    import vits
+    from oracle import moco_ref, vit_ref
+    bm = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss")
+    torch.manual_seed(0)
+    model = bm.MoCo_ViT(partial(vits.vit_small, stop_grad_conv1=True), SimpleNamespace(arch="vit_small"), 256, 4096, 0.2)
+    with torch.no_grad():
+        for p in model.base_encoder.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    model = model.cuda().train()
+    B, m = 16, 0.99
+    im_q, im_k, _ = E.synthetic_pair(B, 224, device="cuda")
+    # oracle replica of the pieces that are not bit-trivial
+    ref_q = vit_ref.vit_small(num_classes=4096, stop_grad_conv1=True)
+    ref_q.head = moco_ref.build_mlp(3, 384, 4096, 256)
+    ref_q.load_state_dict(model.base_encoder.state_dict(), strict=True)
+    ref_q = ref_q.cuda().train()
+    pk_before = [p.detach().clone() for p in model.momentum_encoder.parameters()]
+    pq = [p.detach().clone() for p in model.base_encoder.parameters()]
+    queue0 = model.queue.clone()
+
+    logits, labels = model(im_q, im_k, m)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+
+    # EMA: bit-exact against the eager 3-op sequence over all 41 080 704 parameters
+    bad = 0
+    for k0, q0, k1 in zip(pk_before, pq, model.momentum_encoder.parameters()):
+        bad += int(((k0 * m + q0 * (1. - m)) != k1).sum().item())
+    assert bad == 0, "%d EMA elements differ" % bad
+    assert logits.shape == (B, 65537) and labels.dtype == torch.long and int(labels.abs().sum()) == 0
+    assert int(model.queue_ptr) == B
+    # oracle forward of the query path (same predictor module, train-mode BN)
+    pred_ref = moco_ref.build_mlp(2, 256, 4096, 256).cuda().train()
+    pred_ref.load_state_dict(model.predictor.state_dict())
+    q_ref = pred_ref(ref_q(im_q))
+    kn = model.queue[:, :B].t()  # keys enqueued by the step = normalised keys
+    assert torch.allclose(kn.norm(dim=1), torch.ones(B, device="cuda"), atol=1e-5)
+    logits_ref, _, _, _ = moco_ref.infonce_logits(q_ref, kn, queue0, 0.2)
+    # train-mode BatchNorm over 16 nearly identical random-init CLS tokens divides by a tiny batch std, so operand
+    # rounding is amplified: the logits (|.| <= 5) agree to a few 1e-2, and gradients are compared in eval mode below
+    err = (logits - logits_ref).abs().max().item()
+    assert err <= 5e-2, "InfoNCE logits max abs diff %.3e" % err
+    assert torch.equal(model.queue[:, B:], queue0[:, B:])
+    for p in model.base_encoder.parameters():
+        assert p.grad is None or bool(torch.isfinite(p.grad).all())
+
+    # ---- second step in eval mode (BatchNorm running statistics: well conditioned) -> gradient parity
+    model.zero_grad(set_to_none=True)
+    model.eval(); ref_q.eval(); pred_ref.eval()
+    ref_q.load_state_dict(model.base_encoder.state_dict(), strict=True)  # BN buffers moved during the train step
+    pred_ref.load_state_dict(model.predictor.state_dict())
+    queue1 = model.queue.clone()
+    im_q2, im_k2, _ = E.synthetic_pair(B, 224, rank=3, device="cuda")
+    logits2, labels2 = model(im_q2, im_k2, m)
+    F.cross_entropy(logits2, labels2).backward()
+    assert int(model.queue_ptr) == 2 * B
+    kn2 = model.queue[:, B:2 * B].t()
+    logits2_ref, _, _, _ = moco_ref.infonce_logits(pred_ref(ref_q(im_q2)), kn2, queue1, 0.2)
+    err = (logits2 - logits2_ref).abs().max().item()
+    assert err <= 5e-3, "eval-mode InfoNCE logits max abs diff %.3e" % err
+    F.cross_entropy(logits2_ref, labels2).backward()
+    mn, worst, _ = E.grad_report([(n, p) for n, p in ref_q.named_parameters() if p.requires_grad],
+                                 model.base_encoder.named_parameters())
+    assert mn >= GRAD_COS_TOL, "MoCo query-path gradient cosine %.5f at %s" % (mn, worst)
+    mn, worst, _ = E.grad_report(pred_ref.named_parameters(), model.predictor.named_parameters())
+    assert mn >= GRAD_COS_TOL, "MoCo predictor gradient cosine %.5f at %s" % (mn, worst)
