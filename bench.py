@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py - MF-ViT CA training throughput (image-pairs/s, fwd+bwd+optimizer step) on N B200 GPUs of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps K --warmup W      # the reference path on the host CPU cores
+
+Workload (BASELINE.json): MF-ViT CA = two ViT-S/16 branches (CXR + enhanced CXR) + CLS cross-attention fusion + two summed
+aux heads, 224x224 synthetic CXR tensors, random-init weights.  N=1: configs[1] (32 pairs); N>1: configs[2] (64 pairs per
+GPU, data parallel, gradient all-reduce over NCCL/NVLink).  One "step" = H-resident batch -> forward -> CE(fused+x_cxr+
+x_enh) -> backward through both backbones and the fusion -> [all-reduce] -> SGD-momentum step on every parameter.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "multi-feature-vit_b200"), os.path.join(ROOT, "multi-feature-vit_b200", "dropin"),
+          os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "MF-ViT CA train image-pairs/s"
+UNIT = "pairs/s"
+
+
+# ------------------------------------------------------------------------------------------------ work accounting
+def vit_fwd_flops(img, C=384, depth=12, hidden=1536):
+    """2*MAC FLOPs of one ViT-S/16 forward for one image (9.197 GF @224)."""
+    np_ = (img // 16) ** 2
+    S = np_ + 1
+    patch = 2 * np_ * 768 * C
+    blk = 2 * S * C * 3 * C + 4 * S * S * C + 2 * S * C * C + 4 * S * C * hidden
+    return patch + depth * blk
+
+
+def pair_flops(img):
+    """fwd+bwd FLOPs of one MF-ViT CA pair on the de-duplicated graph (55.65 GF @224)."""
+    C, S = 384, (img // 16) ** 2 + 1
+    vit = vit_fwd_flops(img)
+    fusion = 2 * (2 * 2 * S * C * C)  # both directions, wk/wv GEMMs as written
+    fwd = 2 * vit + fusion
+    patch = 2 * (img // 16) ** 2 * 768 * C
+    return fwd + 2 * fwd - 2 * patch  # no dgrad for the pixels
+
+
+def gemm_class_flops(img, B, G=2, C=384, depth=12, hidden=1536):
+    """FLOPs per step of the three GEMM kernel classes (forward, dgrad, wgrad) for G branches of B images."""
+    np_ = (img // 16) ** 2
+    S = np_ + 1
+    lin = 2 * S * C * (3 * C + C + 2 * hidden) * depth  # per image, all Linear layers
+    patch = 2 * np_ * 768 * C
+    return {"gemm_fwd": G * B * (lin + patch), "gemm_dgrad": G * B * lin, "gemm_wgrad": G * B * (lin + patch)}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops", 1590.0), "bf16_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def build_oracle(img):
+    """The reference path on CPU: oracle restatement of timm ViT-S/16 x2 + Fus_CrossViT (as written, FUS:126-157)."""
+    from oracle import fusion_ref, vit_ref
+    import e2e_common as E
+    torch.manual_seed(0)
+    cxr, enh = vit_ref.vit_small(img_size=img), vit_ref.vit_small(img_size=img)
+    for v in (cxr, enh):
+        E.reference_head_init_(v)
+    fus = fusion_ref.Fus_CrossViT(cxr, enh)
+    params = [p for m in (fus, cxr, enh) for p in m.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9)
+    return fus, cxr, enh, opt
+
+
+def cpu_reference_rate(img, sample_pairs, steps, warmup):
+    """pairs/s of the reference's own CPU path (fp32, all host threads), as written: 4 backbone passes per step."""
+    import e2e_common as E
+    torch.set_num_threads(os.cpu_count() or 1)
+    fus, cxr, enh, opt = build_oracle(img)
+    img_c, img_e, tgt = E.synthetic_pair(sample_pairs, img)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        fused, x_c, x_e = fus(cxr, enh, img_c, img_e)  # MAIN_CA:862
+        loss = torch.nn.functional.cross_entropy(fused + x_c + x_e, tgt)  # MAIN_CA:868-873
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return sample_pairs / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = args.cpu_sample_pairs
+    rate, dt, cores = cpu_reference_rate(args.img_size, sample, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_gpu=args.pairs_per_gpu),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d pairs per step, as-written graph (4 backbone passes, FUS:128-135), oracle port of "
+                                   "the reference (timm ViT is absent from the reference tree), fp32, %d threads"
+                                   % (sample, cores)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu):
+    return {
+        "workload": "MF-ViT CA: 2x ViT-S/16 (CXR + enhanced) + CLS cross-attention fusion + 2 summed aux heads, "
+                    "fwd+bwd+SGD step, %dx%d, %d pairs/GPU" % (args.img_size, args.img_size, per_gpu),
+        "pairs_per_gpu": per_gpu, "global_batch": per_gpu * args.gpus, "img_size": args.img_size,
+        "tokens_per_branch": (args.img_size // 16) ** 2 + 1, "parallelism": "dp%d" % args.gpus,
+        "baseline_config": "configs[1]" if args.gpus == 1 and per_gpu == 32 else "configs[2]",
+        "l2_policy": "per-step working set (activations of 24 blocks, >2 GB) and 4 rotating input batches exceed the "
+                     "126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mfvit", choices=["mfvit", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=0, help="default: 32 at N=1 (configs[1]), 64 at N>1 (configs[2])")
+    ap.add_argument("--img-size", type=int, default=224)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "mfvit":
+        args.warmup = 3
+    if args.pairs_per_gpu <= 0:
+        args.pairs_per_gpu = 32 if args.gpus == 1 else 64
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import importlib
+
+    import e2e_common as E
+    import vits_returnftrs as vits
+    from mfvit import _lib
+    from mfvit.trainer import MFViTCATrainer
+    lib = _lib.init(local_rank)
+
+    B, img = args.pairs_per_gpu, args.img_size
+    torch.manual_seed(0)  # identical replicas on every rank
+    fm = importlib.import_module(E.FUS_MOD)
+    cxr, enh = vits.vit_small(img_size=img), vits.vit_small(img_size=img)
+    for v in (cxr, enh):
+        E.reference_head_init_(v)
+    fus = fm.Fus_CrossViT(cxr, enh)
+    cxr.to(device), enh.to(device), fus.to(device)
+    trainer = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, weight_decay=0.0)
+
+    # synthetic data: 4 rotating batches per rank, pinned host copies for the end-to-end leg
+    nb = 4
+    host = []
+    for i in range(nb):
+        c, e, t = E.synthetic_pair(B, img, rank=rank * 16 + i)
+        host.append((c.pin_memory(), e.pin_memory(), t.pin_memory()))
+    dev_batches = [(c.to(device), e.to(device), t.to(device)) for c, e, t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (allocations, cudaFuncSetAttribute, NCCL channels)
+    for i in range(args.warmup):
+        trainer.step(*dev_batches[i % nb])
+    barrier()
+
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mfv_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        loss = trainer.step(*dev_batches[i % nb])
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    launches = (lib.mfv_launch_count() - launches0) / args.steps
+    loss_val = float(loss)
+
+    # ---- timed: end to end (pinned host -> device copies in, loss read back, every step)
+    copy_stream = torch.cuda.Stream(device=device)
+    slots = [[torch.empty_like(t, device=device) for t in dev_batches[0]] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(step):
+        s = step % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for dst, src in zip(slots[s], host[step % nb]):
+                dst.copy_(src, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_steps = args.steps
+    e_start.record()
+    prefetch(0)
+    for i in range(e_steps):
+        s = i % 2
+        if i + 1 < e_steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[s])
+        loss_e = trainer.step(*slots[s])
+        consumed[s].record()
+        loss_host = float(loss_e)  # device -> host read of the step's result (synchronises, as MAIN_CA:884 does)
+    e_end.record()
+    barrier()
+    e2e_ms = e_start.elapsed_time(e_end)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps
+    breakdown, dominant = {}, None
+    if rank == 0:
+        import ctypes as C
+        nl = lib.mfv_prof_num_labels()
+        ms = (C.c_float * nl)()
+        cnt = (C.c_int * nl)()
+        lib.mfv_prof_enable(1)
+        psteps = 3
+        for i in range(psteps):
+            trainer.forward_backward(*dev_batches[i % nb])
+        lib.mfv_prof_read(ms, cnt, nl)
+        lib.mfv_prof_enable(0)
+        for i in range(nl):
+            if cnt[i]:
+                breakdown[lib.mfv_prof_label_name(i).decode()] = {"ms_per_step": ms[i] / psteps,
+                                                                  "launches_per_step": cnt[i] / psteps}
+        dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        pairs = B * world
+        value = pairs * args.steps / (elapsed_ms * 1e-3)
+        e2e_value = pairs * e_steps / (e2e_ms * 1e-3)
+        gf = gemm_class_flops(img, B)
+        roof = None
+        if dominant in gf:
+            d = breakdown[dominant]
+            ach = gf[dominant] / (d["ms_per_step"] * 1e-3) / 1e12
+            roof = {"kernel": "gemm_bf16_kernel (%s launches of the step)" % dominant, "bound": "tensor",
+                    "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "launches_per_step": d["launches_per_step"], "ms_per_step": d["ms_per_step"]}
+        elif dominant is not None:
+            d = breakdown[dominant]
+            roof = {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": None, "traffic": None, "ms_per_step": d["ms_per_step"]}
+        step_tf = value * pair_flops(img) / 1e12
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands fwd / bf16 operands bwd, fp32 accumulate + fp32 residual stream and master weights",
+            "data": "synthetic", "config": workload_config(args, per_gpu=B),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / e_steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "step_tflops": step_tf,
+            "step_frac_of_bf16_peak": {"measured_sustained": step_tf / peaks["bf16_sustained"] / world,
+                                       "measured_burst": step_tf / peaks["bf16_burst"] / world,
+                                       "spec_2250": step_tf / 2250.0 / world},
+            "kernel_breakdown_ms": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
+            "final_loss": loss_val,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, cores = cpu_reference_rate(img, args.cpu_sample_pairs, 2, 1)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d pairs per step x (1 warm-up + 2 timed) steps of the as-written reference graph (4 backbone "
+                          "passes), oracle port, fp32" % args.cpu_sample_pairs}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

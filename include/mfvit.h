@@ -32,6 +32,14 @@ int mfv_abi_version(void);
 int mfv_init(int device);
 const char* mfv_strerror(int code);
 int mfv_num_sms(void);
+/* Number of kernels this library has launched so far in the process (bench.py reports the per-step delta). */
+uint64_t mfv_launch_count(void);
+/* Optional device-side timing of mfv_vit_forward/backward per kernel class (CUDA events on the launching stream).
+ * mfv_prof_read synchronises the device, ACCUMULATES elapsed ms / launch counts per label into the arrays and resets. */
+int mfv_prof_enable(int on);
+int mfv_prof_num_labels(void);
+const char* mfv_prof_label_name(int label);
+int mfv_prof_read(float* ms_per_label, int* count_per_label, int nlabels);
 
 /* ---- GEMM (tcgen05 / TMEM / TMA) ----------------------------------------------------------------------------------
  * C[g][m][n] = epilogue( sum_k A[g][m][k] * B[g][n][k] ), bf16 operands, fp32 accumulation in TMEM.

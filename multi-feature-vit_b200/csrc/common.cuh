@@ -21,10 +21,13 @@
     if (_e != cudaSuccess) return (int)_e;           \
   } while (0)
 
+namespace mfv { extern unsigned long long g_launch_count; }
+// every kernel launch in the library is followed by this macro: error check + launch accounting (mfv_launch_count)
 #define MFV_LAUNCH_CHECK()                           \
   do {                                               \
     cudaError_t _e = cudaGetLastError();             \
     if (_e != cudaSuccess) return (int)_e;           \
+    ++mfv::g_launch_count;                           \
   } while (0)
 
 namespace mfv {

@@ -10,4 +10,18 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
+
+// Optional per-kernel-class device timing of the encoder executor (CUDA events on the launching stream).
+enum ProfLabel {
+  PROF_PATCHIFY = 0, PROF_GEMM_FWD, PROF_LN_FWD, PROF_ATTN_FWD, PROF_EMBED, PROF_GEMM_DGRAD, PROF_GEMM_WGRAD,
+  PROF_COLSUM, PROF_LN_BWD, PROF_ATTN_BWD, PROF_EMBED_BWD, PROF_NUM_LABELS
+};
+bool prof_enabled();
+void prof_begin(int label, cudaStream_t st);
+void prof_end(int label, cudaStream_t st);
+struct ProfScope {
+  int label; cudaStream_t st; bool on;
+  ProfScope(int l, cudaStream_t s) : label(l), st(s), on(prof_enabled()) { if (on) prof_begin(label, st); }
+  ~ProfScope() { if (on) prof_end(label, st); }
+};
 }  // namespace mfv

@@ -2,7 +2,29 @@
 #include "common.cuh"
 #include "mfvit_internal.h"
 
+#include <vector>
+
 namespace mfv {
+unsigned long long g_launch_count = 0;
+static bool g_prof_on = false;
+struct ProfRec { int label; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<ProfRec> g_prof_pool;
+static ProfRec g_prof_open[PROF_NUM_LABELS];
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(int label, cudaStream_t st) {
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+  r.label = label;
+  cudaEventRecord(r.a, st);
+  g_prof_open[label] = r;
+}
+void prof_end(int label, cudaStream_t st) {
+  ProfRec r = g_prof_open[label];
+  cudaEventRecord(r.b, st);
+  g_prof_recs.push_back(r);
+}
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_device = -1;
@@ -12,6 +34,35 @@ int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 }  // namespace mfv
 
 extern "C" int mfv_abi_version(void) { return MFV_ABI_VERSION; }
+
+extern "C" uint64_t mfv_launch_count(void) { return mfv::g_launch_count; }
+
+extern "C" int mfv_prof_enable(int on) {
+  mfv::g_prof_on = on != 0;
+  return MFV_OK;
+}
+
+extern "C" int mfv_prof_num_labels(void) { return mfv::PROF_NUM_LABELS; }
+
+extern "C" const char* mfv_prof_label_name(int label) {
+  static const char* names[] = {"patchify", "gemm_fwd", "ln_fwd", "attn_fwd", "embed", "gemm_dgrad", "gemm_wgrad",
+                                "colsum", "ln_bwd", "attn_bwd", "embed_bwd"};
+  return (label >= 0 && label < mfv::PROF_NUM_LABELS) ? names[label] : "?";
+}
+
+// Synchronises the device, adds the elapsed time of every recorded scope to ms[label] / count[label], resets.
+extern "C" int mfv_prof_read(float* ms, int* count, int nlabels) {
+  using namespace mfv;
+  MFV_CUDA_CHECK(cudaDeviceSynchronize());
+  for (const ProfRec& r : g_prof_recs) {
+    float t = 0.f;
+    MFV_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.label < nlabels) { ms[r.label] += t; count[r.label] += 1; }
+    g_prof_pool.push_back(r);
+  }
+  g_prof_recs.clear();
+  return MFV_OK;
+}
 
 extern "C" int mfv_num_sms(void) { return mfv::num_sms(); }
 

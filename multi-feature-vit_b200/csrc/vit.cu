@@ -68,6 +68,7 @@ static int linear_fwd(const PlanView& v, const void* A, long long K, long long w
   a.a_gstride = v.M * K; a.b_gstride = v.p->P; a.c_gstride = v.M * N;
   a.aux_ld = aux_ld; a.aux_gstride = v.M * aux_ld; a.bias_gstride = v.p->P;
   a.epilogue = epi;
+  ProfScope ps(PROF_GEMM_FWD, st);
   return mfv_gemm(&a, st);
 }
 // dx = dy W: A = dy [G][M][N] K-major (reduction over N), B = W [N][K] read MN-major
@@ -81,6 +82,7 @@ static int linear_dgrad(const PlanView& v, const void* dY, long long N, long lon
   a.aux_ld = aux_ld; a.aux_gstride = v.M * aux_ld;
   a.b_mn_major = 1;
   a.epilogue = epi;
+  ProfScope ps(PROF_GEMM_DGRAD, st);
   return mfv_gemm(&a, st);
 }
 // dW[N][K] += dy^T x (reduction over `rows` tokens), db[N] += colsum(dy)
@@ -100,9 +102,16 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
   if (splits > kb) splits = kb;
   if (splits < 1) splits = 1;
   a.splits = (int)splits;
-  int rc = mfv_gemm(&a, st);
+  int rc;
+  {
+    ProfScope ps(PROF_GEMM_WGRAD, st);
+    rc = mfv_gemm(&a, st);
+  }
   if (rc) return rc;
-  if (b_off >= 0) rc = mfv_colsum_bf16(dY, v.gr(b_off), v.p->G, rows, N, v.p->P, st);
+  if (b_off >= 0) {
+    ProfScope ps(PROF_COLSUM, st);
+    rc = mfv_colsum_bf16(dY, v.gr(b_off), v.p->G, rows, N, v.p->P, st);
+  }
   return rc;
 }
 
@@ -110,6 +119,13 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
   do {                      \
     int _rc = (expr);       \
     if (_rc) return _rc;    \
+  } while (0)
+// same, with the launch(es) inside timed under a profiling label
+#define RCP(label, expr)              \
+  do {                                \
+    ProfScope _ps(label, st);         \
+    int _rc = (expr);                 \
+    if (_rc) return _rc;              \
   } while (0)
 
 static int check_plan(const mfv_vit_plan* p) {
@@ -139,7 +155,7 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
   const long long rows_pe = p->B * p->np;
   // patch embedding: patchify (per group: images are separate caller tensors) -> GEMM(+bias) -> +cls, +pos
   for (int g = 0; g < G; ++g)
-    RC(mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768,
+    RCP(PROF_PATCHIFY, mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768,
                     p->fwd_f16,
                     v.dual() ? reinterpret_cast<__nv_bfloat16*>(p->patches_bf) + (long long)g * rows_pe * 768 : nullptr,
                     p->B, p->img, st));
@@ -151,25 +167,25 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
     a.lda = 768; a.ldb = 768; a.ldc = C;
     a.a_gstride = rows_pe * 768; a.b_gstride = p->P; a.c_gstride = rows_pe * C; a.bias_gstride = p->P;
     a.epilogue = MFV_EPI_F32;
-    RC(mfv_gemm(&a, st));
+    RCP(PROF_GEMM_FWD, mfv_gemm(&a, st));
   }
-  RC(mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
+  RCP(PROF_EMBED, mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
 
   for (int l = 0; l < p->depth; ++l) {
     float* x_in = v.x(2 * l);
     float* x_mid = v.x(2 * l + 1);
     float* x_out = v.x(2 * l + 2);
     const bool dual = v.dual();
-    RC(mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), p->fwd_f16,
+    RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), p->fwd_f16,
                          dual ? v.xn_b(2 * l) : nullptr, nullptr, v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f,
                          st));
     RC(linear_fwd(v, v.xn(2 * l), C, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), 3 * C, MFV_EPI_BF16, v.qkv(l),
                   nullptr, nullptr, nullptr, 0, st));
-    RC(mfv_attn_fwd(v.qkv(l), p->fwd_f16, v.ao(l), p->fwd_f16, dual ? v.ao_b(l) : nullptr, v.lse(l), G * p->B, p->S, p->H, D, scale,
+    RCP(PROF_ATTN_FWD, mfv_attn_fwd(v.qkv(l), p->fwd_f16, v.ao(l), p->fwd_f16, dual ? v.ao_b(l) : nullptr, v.lse(l), G * p->B, p->S, p->H, D, scale,
                     st));
     RC(linear_fwd(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), C, MFV_EPI_RESID_F32, x_mid, nullptr,
                   nullptr, x_in, C, st));
-    RC(mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), p->fwd_f16,
+    RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), p->fwd_f16,
                          dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C,
                          p->P, 1e-6f, st));
     RC(linear_fwd(v, v.xn(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), Hd, MFV_EPI_GELU, v.u(l),
@@ -178,7 +194,7 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
                   nullptr, x_mid, C, st));
   }
   const int last = 2 * (int)p->depth;
-  RC(mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, 0, nullptr, p->tokens,
+  RCP(PROF_LN_FWD, mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, 0, nullptr, p->tokens,
                        v.mean(last), v.rstd(last), G, M, C, p->P, 1e-6f, st));
   return MFV_OK;
 }
@@ -195,7 +211,7 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
   const int last = 2 * (int)p->depth;
   int cur = 0;  // dx[cur] holds the gradient of the residual stream
   // final norm
-  RC(mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
+  RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
                        p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b), G, M, C, p->P, st));
   for (int l = (int)p->depth - 1; l >= 0; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
@@ -203,24 +219,24 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid, v.u(l), Hd, st));
     RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
-    RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
                          v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
                          v.gr(v.boff(l, p->r_ln2_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
     RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), st));
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, 0, st));
-    RC(mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
+    RCP(PROF_ATTN_BWD, mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
     RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
-    RC(mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
                          v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
                          v.gr(v.boff(l, p->r_ln1_b)), G, M, C, p->P, st));
     cur ^= 1;
   }
   // ---- embedding: cls gradient, conv bias / weight gradient (pos_embed is a fixed table)
   const long long rows_pe = p->B * p->np;
-  RC(mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
+  RCP(PROF_EMBED_BWD, mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
                           p->B, p->np, C, p->P, st));
   if (!p->stop_grad_conv1)
     RC(linear_wgrad(v, p->dacc, C, v.patches_b(), 768, rows_pe, p->off_pe_w, -1, st));

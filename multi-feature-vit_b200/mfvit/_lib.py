@@ -70,6 +70,11 @@ SIGNATURES = {
     "mfv_init": (C.c_int, [C.c_int]),
     "mfv_strerror": (C.c_char_p, [C.c_int]),
     "mfv_num_sms": (C.c_int, []),
+    "mfv_launch_count": (C.c_uint64, []),
+    "mfv_prof_enable": (C.c_int, [C.c_int]),
+    "mfv_prof_num_labels": (C.c_int, []),
+    "mfv_prof_label_name": (C.c_char_p, [C.c_int]),
+    "mfv_prof_read": (C.c_int, [c_vp, c_vp, C.c_int]),
     "mfv_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_layernorm_bwd": (C.c_int, [c_vp] * 11 + [i64, i64, i64, i64, c_vp]),

@@ -1,0 +1,169 @@
+"""Sync-free MF-ViT CA training step (MAIN_CA:859-882 without the four host syncs per iteration).
+
+    trainer = MFViTCATrainer(fusion, vit_cxr, vit_enh, lr=..., momentum=..., weight_decay=...)
+    loss = trainer.step(img_cxr, img_enh, target)        # device tensors; returns a 1-element device tensor
+
+One step = grouped encoder forward (mfv_vit_forward, G=2) -> fused CLS cross-attention + heads (mfv_fusion_fwd) ->
+cross-entropy on fused + x_cxr + x_enh (mfv_ce_small) -> fusion backward -> encoder backward (mfv_vit_backward) ->
+[data-parallel: NCCL all-reduce of the flat gradient buffers] -> fused SGD-momentum step that also rewrites the 16-bit
+GEMM shadows (mfv_sgd_step).  No autograd graph, no per-parameter Python loop; parameters stay ordinary nn.Parameters
+(views into flat buffers), so state_dict()/checkpoints are unchanged.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import FusionGrads, MfvError
+from .engine import engine_for
+from .functions import FUSION_FIELDS
+
+
+class FlatParams:
+    """Packs a list of Parameters into one flat fp32 buffer (Parameters become views) with a matching grad buffer."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        self.n = max(sum(sizes), 4)
+        self.master = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.views, self.gviews = [], []
+        off = 0
+        for p, sz in zip(self.params, sizes):
+            v = self.master[off:off + p.numel()].view(p.shape)
+            v.copy_(p.detach().to(device=device, dtype=torch.float32))
+            p.data = v
+            self.views.append(v)
+            self.gviews.append(self.grad[off:off + p.numel()].view(p.shape))
+            off += sz
+
+    def adopted(self):
+        return all(p.data_ptr() == v.data_ptr() for p, v in zip(self.params, self.views))
+
+
+class MFViTCATrainer:
+    def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
+                 train_backbones=True):
+        self.fusion, self.vits = fusion, (vit_cxr, vit_enh)
+        self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.pg = process_group
+        self.train_backbones = train_backbones
+        self.engine = engine_for(vit_cxr, vit_enh)
+        self.heads = fusion.heads
+        self.NC = fusion.num_classes
+        self._small = None
+        self._bufs = {}
+        self.steps = 0
+        self._mom_engine = None
+        self._mom_small = None
+
+    # -- lazily bind to the device of the first batch
+    def _prepare(self, device):
+        eng = self.engine
+        if not eng.is_adopted() or eng.device != device:
+            eng.adopt(device)
+        if self._small is None or not self._small.adopted():
+            self.fusion.to(device)
+            params, vh = self.fusion._fusion_params(*self.vits)
+            if any(h is None for h in vh):
+                raise MfvError("MFViTCATrainer needs nn.Linear backbone heads with num_classes outputs (MAIN_CA:309)")
+            for v in self.vits:
+                v.head.to(device)
+            self._fparams = params  # 26 tensors, FUSION_FIELDS x direction
+            self._small = FlatParams(params, device)
+            self._pstruct = ops.fusion_param_struct(
+                {n: (params[2 * i].data, params[2 * i + 1].data) for i, n in enumerate(FUSION_FIELDS)})
+            g = self._small.gviews
+            self._gstruct = ops.fusion_param_struct({n: (g[2 * i], g[2 * i + 1]) for i, n in enumerate(FUSION_FIELDS)},
+                                                    cls=FusionGrads)
+            self._mom_small = torch.zeros_like(self._small.master)
+        if self._mom_engine is None or self._mom_engine.device != device:
+            self._mom_engine = torch.zeros_like(eng.master)
+
+    def _trainable_ranges(self):
+        eng, lay = self.engine, self.engine.layout
+        if getattr(self, "_ranges", None) is None:
+            out = []
+            for g in range(eng.G):
+                run = None
+                for (name, shape, off), (_, p) in zip(lay.entries, eng._params[g]):
+                    n = p.numel()
+                    if p.requires_grad:
+                        if run is not None and run[1] >= off - 8:  # adjacent up to alignment padding
+                            run[1] = off + n
+                        else:
+                            if run is not None:
+                                out.append((g, run[0], (run[1] + 3) // 4 * 4))
+                            run = [off, off + n]
+                    else:
+                        if run is not None:
+                            out.append((g, run[0], (run[1] + 3) // 4 * 4))
+                            run = None
+                if run is not None:
+                    out.append((g, run[0], min((run[1] + 3) // 4 * 4, lay.P)))
+            self._ranges = out
+            self._shadow_complete = False
+        return self._ranges
+
+    def forward_backward(self, img_cxr, img_enh, target):
+        """Forward + backward; gradients land in engine.grads[engine.grad_idx] and self._small.grad."""
+        device = img_cxr.device
+        self._prepare(device)
+        eng = self.engine
+        B = img_cxr.shape[0]
+        lay = eng.layout
+        tok, lease = eng.forward([img_cxr, img_enh], save=True)
+        fused, x = ops.fusion_fwd(tok, self._pstruct, B, lay.S, lay.C, self.heads, self.NC)
+        loss, dlogits = ops.ce_small(fused, x[0], x[1], target)
+        ops.fill_(self._small.grad, 0.0)
+        key = (B, device)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty_like(tok),
+                               torch.empty(2, B, self.NC, device=device, dtype=torch.float32))
+        dtok, d_x = self._bufs[key]
+        d_x[0].copy_(dlogits)
+        d_x[1].copy_(dlogits)
+        ops.fusion_bwd(tok, self._pstruct, self._gstruct, dlogits, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok)
+        grad = eng.backward(lease, dtok)
+        self._last = (fused, x)
+        return loss, grad
+
+    def all_reduce(self, grad):
+        if self.pg is None and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        ws = torch.distributed.get_world_size(self.pg)
+        if ws == 1:
+            return
+        # mean over ranks (DDP semantics): pre-divide on device, then sum
+        for t in (grad, self._small.grad):
+            t.div_(ws)
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def optimizer_step(self, grad):
+        eng = self.engine
+        first = self.steps == 0
+        if self.train_backbones:
+            # contiguous runs of trainable tensors (pos_embed is a frozen table; stop_grad_conv1 freezes the conv):
+            # frozen ranges must not see weight decay, so they are skipped rather than stepped with a zero gradient
+            for g, lo, hi in self._trainable_ranges():
+                sl = slice(lo, hi)
+                ops.sgd_step_(eng.master[g, sl], grad[g, sl], self._mom_engine[g, sl], eng.shadow[g, sl], self.lr,
+                              self.momentum, self.wd, first, shadow16=eng.shadow16[g, sl] if eng.fwd_f16 else None)
+            if not self._shadow_complete:
+                ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1),
+                                eng.shadow16.view(-1) if eng.fwd_f16 else None)  # frozen ranges, once
+                self._shadow_complete = True
+            eng.shadow_fresh = True  # the step rewrote the GEMM shadows: the next forward skips the cast pass
+        ops.sgd_step_(self._small.master, self._small.grad, self._mom_small, None, self.lr, self.momentum, self.wd, first)
+        self.steps += 1
+
+    def step(self, img_cxr, img_enh, target):
+        loss, grad = self.forward_backward(img_cxr, img_enh, target)
+        self.all_reduce(grad)
+        self.optimizer_step(grad)
+        return loss
+
+    def logits(self):
+        """(fused, x_cxr, x_enh) of the most recent step."""
+        fused, x = self._last
+        return fused, x[0], x[1]
