@@ -1,40 +1,42 @@
-// tcgen05/TMEM bf16 GEMM for every dense contraction of the ViT-S/16 block (SURVEY K3/K5/K6 and their dgrad/wgrad):
+// tcgen05/TMEM 16-bit GEMM for every dense contraction of the ViT-S/16 block (SURVEY K3/K5/K6 and their dgrad/wgrad):
 //
 //     C[g][m][n] = epilogue( sum_k A[g][m][k] * B[g][n][k] )          g < G groups (the two MF-ViT branches)
 //
 // * warp-specialised, persistent: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer (+TMEM owner),
-//   warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  Accumulators are double-buffered in TMEM so the
-//   epilogue of tile i overlaps the MMAs of tile i+1 (K is only 6 k-blocks for K=384).
+//   warps 2..5 = epilogue.  Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
+//   tile i+1 (K is only 6 k-blocks for K=384).
 // * operands are staged by TMA into 128B-swizzled shared memory through 3-D tensor maps (inner, rows, group); rows
 //   or reduction elements past the tensor end are zero-filled by TMA, so no padding of M=B*197 tokens is needed.
 // * each operand may be K-major (reduction dim contiguous: activations / nn.Linear weights in forward) or MN-major
 //   (reduction dim strided: W in dgrad, dY and X in wgrad) - selected by the UMMA descriptors, no transposed copies.
-// * split-K with fp32 red.global.add epilogue for the weight gradients (reduction over all tokens).
+// * epilogue: tcgen05.ld (lane = row) -> registers -> 128B-swizzled smem staging -> TMA bulk-tensor store, one
+//   32-row box per epilogue warp, so every global access of the epilogue is a full-line asynchronous bulk copy
+//   (round-1 ncu: per-thread row stores left the kernel latency-bound at 6-20 % tensor-pipe utilisation).  The fp32
+//   residual / pre-GELU operand of the fused epilogues arrives the same way (TMA load, prefetched one chunk ahead);
+//   split-K weight gradients leave through TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32).
 #include "common.cuh"
 #include "mfvit_internal.h"
 
 namespace mfv {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int EPI_BUF = 4096;                 // one staging buffer: 32 rows x 128 B
+constexpr int EPI_BUFS_PER_WARP = 3;          // out0 | out1 (or aux ping) | out2 (or aux pong)
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS_PER_WARP * EPI_BUF;
 
 struct GemmParams {
   int M, N, K, G;
   int tiles_m, tiles_n, splits, kb_total, kb_per_split;
-  int a_mn, b_mn;  // 1 = MN-major operand
-  int a_f16, b_f16, out_f16;  // 1 = IEEE fp16 instead of bf16 (operands may be mixed)
+  int a_mn, b_mn;             // 1 = MN-major operand
+  int a_f16, b_f16, out_f16;  // 1 = IEEE fp16 instead of bf16 (A and B must agree: mixed 16-bit operands trap)
   int epi;
-  long long ldc, c_gstride;        // elements
-  long long aux_ld, aux_gstride;   // residual (fp32) or pre-activation u (bf16)
+  int has_c3;
   long long bias_gstride;
-  void* C;
-  void* C2;
-  void* C3;
   const float* bias;
-  const void* aux;
 };
 
 template <int BN>
@@ -42,24 +44,48 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 4 : 6);
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
 };
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1,
+                                                  int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte chunk j (0..7) of row r in a 32 x 128 B staging buffer laid out with the TMA 128B swizzle
+__device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                 const __grid_constant__ CUtensorMap tmC3, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + S::STAGES * S::STAGE_BYTES;
+  uint8_t* epi_base = smem + S::STAGES * S::STAGE_BYTES;
+  uint8_t* bar_base = epi_base + EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,6 +94,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -76,6 +103,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], NUM_EPI_WARPS * 32);
     }
+    for (int s = 0; s < 2 * NUM_EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -162,7 +190,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;      // TMEM lane quarter this warp may access
+    const int ew = warp - 2;     // 0..3: staging slice / aux barriers
+    uint8_t* st0 = epi_base + ew * (EPI_BUFS_PER_WARP * EPI_BUF);
+    uint8_t* st1 = st0 + EPI_BUF;
+    uint8_t* st2 = st1 + EPI_BUF;
+    uint64_t* abar = aux_bar + 2 * ew;
+    uint32_t aux_phase0 = 0u, aux_phase1 = 0u;
+    const bool has_aux = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_DGELU);
+    // column chunk handled per staging round: 128 B per row -> 32 fp32 or 64 16-bit columns
+    const bool out32 = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_F32 || p.epi == MFV_EPI_ATOMIC_F32);
+    const int CW = out32 ? 32 : 64;
+    const int nchunks = BN / CW;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int r = t;
@@ -172,110 +211,143 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = r / p.tiles_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_tile * BM + q * 32;   // first row of this warp's 32-row slice
+      const int ncol0 = n_tile * BN;
+      const bool rows_ok = row0 < p.M;  // warp-uniform: slices fully past M do nothing (TMA clips partial ones)
+      const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
+      // prefetch the aux operand of chunk 0 while the MMAs of this tile are still running
+      if (has_aux && lane == 0 && rows_ok) {
+        mbar_arrive_expect_tx(&abar[0], EPI_BUF);
+        tma_load_3d(st1, &tmAux, &abar[0], ncol0, row0, g);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m = m_tile * BM + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      const long long crow = (long long)g * p.c_gstride + (long long)m * p.ldc;
-      const long long arow = (long long)g * p.aux_gstride + (long long)m * p.aux_ld;
-      const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_tile * BN + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), v);
-        tmem_ld_wait();
-        float f[32];
+      for (int c = 0; c < nchunks; ++c) {
+        const int n0 = ncol0 + c * CW;
+        if (n0 >= p.N || !rows_ok) break;  // warp-uniform
+        // next aux chunk: its buffer was last read in round c-1 and every lane is past that round (syncwarp below)
+        if (has_aux && lane == 0 && c + 1 < nchunks && n0 + CW < p.N) {
+          uint8_t* nb = ((c + 1) & 1) ? st2 : st1;
+          mbar_arrive_expect_tx(&abar[(c + 1) & 1], EPI_BUF);
+          tma_load_3d(nb, &tmAux, &abar[(c + 1) & 1], n0 + CW, row0, g);
+        }
+        float f[64];
+        {
+          uint32_t v[32];
+          tmem_ld32(trow + (uint32_t)(c * CW), v);
+          if (!out32) {
+            uint32_t v2[32];
+            tmem_ld32(trow + (uint32_t)(c * CW + 32), v2);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) f[32 + i] = __uint_as_float(v2[i]);
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[32 + i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        }
         if (bias) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
-            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          for (int i = 0; i < 64; i += 4) {
+            if (i < CW) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
           }
         }
-        if (!row_ok) continue;
+        const uint8_t* ab = (c & 1) ? st2 : st1;
+        if (has_aux) {
+          if (c & 1) { mbar_wait(&abar[1], aux_phase1); aux_phase1 ^= 1u; }
+          else       { mbar_wait(&abar[0], aux_phase0); aux_phase0 ^= 1u; }
+        }
+        // the previous round's bulk stores must have finished reading the staging buffers
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
         switch (p.epi) {
           case MFV_EPI_BF16: {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + crow + n0);
-            if (p.out_f16) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dst[i] = make_uint4(pack_f16(f[8 * i], f[8 * i + 1]), pack_f16(f[8 * i + 2], f[8 * i + 3]),
-                                    pack_f16(f[8 * i + 4], f[8 * i + 5]), pack_f16(f[8 * i + 6], f[8 * i + 7]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                dst[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                                    pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              if (p.out_f16)
+                o = make_uint4(pack_f16(f[8 * j], f[8 * j + 1]), pack_f16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_f16(f[8 * j + 4], f[8 * j + 5]), pack_f16(f[8 * j + 6], f[8 * j + 7]));
+              else
+                o = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) = o;
             }
           } break;
-          case MFV_EPI_GELU: {  // C = u (pre-activation, saved for backward), C2 = gelu(u)
-            uint4* du = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + crow + n0);
-            uint4* dg = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + n0);
+          case MFV_EPI_GELU: {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = bf16 copy of C2
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              du[i] = make_uint4(pack_bf16(f[8 * i], f[8 * i + 1]), pack_bf16(f[8 * i + 2], f[8 * i + 3]),
-                                 pack_bf16(f[8 * i + 4], f[8 * i + 5]), pack_bf16(f[8 * i + 6], f[8 * i + 7]));
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
+                  make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
               float gl[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) gl[j] = gelu_erf(f[8 * i + j]);
-              if (p.C3)
-                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C3) + crow + n0)[i] =
-                    make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
-                               pack_bf16(gl[6], gl[7]));
-              dg[i] = p.out_f16 ? make_uint4(pack_f16(gl[0], gl[1]), pack_f16(gl[2], gl[3]), pack_f16(gl[4], gl[5]),
-                                             pack_f16(gl[6], gl[7]))
-                                : make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
-                                             pack_bf16(gl[6], gl[7]));
+              for (int i = 0; i < 8; ++i) gl[i] = gelu_erf(f[8 * j + i]);
+              const uint4 gb = make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
+                                          pack_bf16(gl[6], gl[7]));
+              *reinterpret_cast<uint4*>(st1 + stage_off(lane, j)) =
+                  p.out_f16 ? make_uint4(pack_f16(gl[0], gl[1]), pack_f16(gl[2], gl[3]), pack_f16(gl[4], gl[5]),
+                                         pack_f16(gl[6], gl[7]))
+                            : gb;
+              if (p.has_c3) *reinterpret_cast<uint4*>(st2 + stage_off(lane, j)) = gb;
             }
           } break;
           case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream)
-            const float4* res = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + arow + n0);
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + crow + n0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 rr = res[i];
-              dst[i] = make_float4(f[4 * i] + rr.x, f[4 * i + 1] + rr.y, f[4 * i + 2] + rr.z, f[4 * i + 3] + rr.w);
+            for (int j = 0; j < 8; ++j) {
+              const float4 rr = *reinterpret_cast<const float4*>(ab + stage_off(lane, j));
+              *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
+                  make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
             }
           } break;
           case MFV_EPI_DGELU: {  // C(bf16) = acc * gelu'(u), u = aux (bf16)
-            const uint4* up = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + arow + n0);
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + crow + n0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 uu = up[i];
+            for (int j = 0; j < 8; ++j) {
+              const uint4 uu = *reinterpret_cast<const uint4*>(ab + stage_off(lane, j));
               const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
               uint32_t o[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 u2 = unpack_bf16(uw[j]);
-                o[j] = pack_bf16(f[8 * i + 2 * j] * gelu_erf_grad(u2.x), f[8 * i + 2 * j + 1] * gelu_erf_grad(u2.y));
+              for (int i = 0; i < 4; ++i) {
+                const float2 u2 = unpack_bf16(uw[i]);
+                o[i] = pack_bf16(f[8 * j + 2 * i] * gelu_erf_grad(u2.x), f[8 * j + 2 * i + 1] * gelu_erf_grad(u2.y));
               }
-              dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           } break;
-          case MFV_EPI_F32: {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + crow + n0);
+          default: {  // MFV_EPI_F32 / MFV_EPI_ATOMIC_F32: raw fp32 tile
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } break;
-          case MFV_EPI_ATOMIC_F32: {  // split-K weight gradients: accumulate into the fp32 grad buffer
-            float* dst = reinterpret_cast<float*>(p.C) + crow + n0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(f[4 * i]),
-                           "f"(f[4 * i + 1]), "f"(f[4 * i + 2]), "f"(f[4 * i + 3])
-                           : "memory");
-          } break;
-          default: break;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.epi == MFV_EPI_ATOMIC_F32) {
+            tma_reduce_add_3d(&tmC, st0, n0, row0, g);
+          } else {
+            tma_store_3d(&tmC, st0, n0, row0, g);
+            if (p.epi == MFV_EPI_GELU) {
+              tma_store_3d(&tmC2, st1, n0, row0, g);
+              if (p.has_c3) tma_store_3d(&tmC3, st2, n0, row0, g);
+            }
+          }
+          bulk_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (lane == 0) bulk_wait0();  // all global writes of this warp are complete before the CTA exits
   }
 
   tc_fence_before();
@@ -307,9 +379,27 @@ static int encode_operand_map(CUtensorMap* map, const void* base, int mn_major, 
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MFV_ERR_ALIGN;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MFV_ERR_INIT;
-  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
+}
+
+// Row-major [G][rows][cols] tensor written / read by the epilogue: box = (128 B of columns, 32 rows, 1), 128B swizzle.
+static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, int is_f16, long long rows,
+                           long long cols, long long ld, long long gstride, int groups) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * elem_bytes,
+                           (cuuint64_t)(groups > 1 ? gstride : rows * ld) * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem_bytes), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MFV_ERR_ALIGN;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MFV_ERR_INIT;
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
 }
 
@@ -333,19 +423,39 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   if (p.splits > 1 && a->epilogue != MFV_EPI_ATOMIC_F32) return MFV_ERR_ARG;
   p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major; p.epi = a->epilogue;
   p.a_f16 = a->dtype_flags & 1; p.b_f16 = (a->dtype_flags >> 1) & 1; p.out_f16 = (a->dtype_flags >> 2) & 1;
-  p.ldc = a->ldc; p.c_gstride = a->c_gstride;
-  p.aux_ld = a->aux_ld; p.aux_gstride = a->aux_gstride; p.bias_gstride = a->bias_gstride;
-  p.C = a->C; p.C2 = a->C2; p.C3 = a->C3; p.bias = (const float*)a->bias; p.aux = a->aux;
+  if (p.a_f16 != p.b_f16) return MFV_ERR_ARG;  // tcgen05 kind::f16 traps on mixed fp16 x bf16 operands
+  p.has_c3 = a->C3 != nullptr;
+  p.bias_gstride = a->bias_gstride;
+  p.bias = (const float*)a->bias;
 
-  CUtensorMap tmA, tmB;
-  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, a->dtype_flags & 1);
+  CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
+  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);
   if (rc) return rc;
-  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN, (a->dtype_flags >> 1) & 1);
+  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN, p.b_f16);
   if (rc) return rc;
+  const int e = a->epilogue;
+  const bool c32 = (e == MFV_EPI_RESID_F32 || e == MFV_EPI_F32 || e == MFV_EPI_ATOMIC_F32);
+  // C: u of the GELU epilogue is always bf16; other 16-bit outputs follow out_f16
+  rc = encode_tile_map(&tmC, a->C, c32 ? 4 : 2, (e == MFV_EPI_BF16) ? p.out_f16 : 0, a->M, a->N, a->ldc, a->c_gstride,
+                       p.G);
+  if (rc) return rc;
+  tmC2 = tmC; tmC3 = tmC; tmAux = tmC;
+  if (e == MFV_EPI_GELU) {
+    rc = encode_tile_map(&tmC2, a->C2, 2, p.out_f16, a->M, a->N, a->ldc, a->c_gstride, p.G);
+    if (rc) return rc;
+    if (a->C3) {
+      rc = encode_tile_map(&tmC3, a->C3, 2, 0, a->M, a->N, a->ldc, a->c_gstride, p.G);
+      if (rc) return rc;
+    }
+  }
+  if (e == MFV_EPI_RESID_F32 || e == MFV_EPI_DGELU) {
+    rc = encode_tile_map(&tmAux, a->aux, e == MFV_EPI_RESID_F32 ? 4 : 2, 0, a->M, a->N, a->aux_ld, a->aux_gstride, p.G);
+    if (rc) return rc;
+  }
 
   const int total = p.tiles_m * p.tiles_n * p.splits * p.G;
   int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmC2, tmC3, tmAux, p);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
