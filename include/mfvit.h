@@ -84,10 +84,11 @@ int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
                       int64_t gb_gstride, float eps, void* stream);
 /* dx = dres (optional residual-path gradient, f32) + LN'(dy); dy is bf16 (dy_bf16) or f32 (dy_f32).
  * Writes dx as f32 and (optionally) a bf16 copy that feeds the next dgrad/wgrad GEMMs.
- * dgamma/dbeta f32 [G][C] are ACCUMULATED (+=) with red.global.add.                                                   */
+ * dgamma/dbeta f32 [G][C] are ACCUMULATED (+=) with red.global.add; dx_colsum (optional, f32 [G][C], +=) receives the
+ * column sums of dx, i.e. the bias gradient of the Linear whose output was added into x (proj / fc2), for free.                                                   */
 int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x, const float* mean,
                       const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                      int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, void* stream);
+                      float* dx_colsum, int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, void* stream);
 
 /* ---- fused softmax self-attention -----------------------------------------------------------------------------------
  * Replaces timm Attention: q@k^T*scale -> softmax -> @v and the transpose copies around it (same math

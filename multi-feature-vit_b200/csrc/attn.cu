@@ -9,8 +9,8 @@
 
 namespace mfv {
 
-constexpr int ATT_WARPS = 4;
-constexpr int ATT_ROWS = ATT_WARPS * 16;  // 64 rows per CTA
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_ROWS = ATT_WARPS * 16;  // 128 rows per CTA pass (one 16-row MMA slab per warp)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -169,29 +169,32 @@ __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// grid = (ceil(S/64), NB*H).  smem: K[Spad][D], V[Spad][D], Q[64][D].
+// grid = (ceil(S/q_rows), NB*H).  smem: K[Spad][D], V[Spad][D], Q[q_rows][D]; q_rows is a multiple of 128 and the CTA
+// walks it in passes of 128 rows (8 warps x 16), so K/V of a head are fetched once (S=197) or ceil(S/128) times.
 template <int D, bool F16>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o, int o_is_f16,
-                __nv_bfloat16* __restrict__ o_bf, float* __restrict__ lse, int S, int H, float scale_log2) {
+                __nv_bfloat16* __restrict__ o_bf, float* __restrict__ lse, int S, int H, float scale_log2, int q_rows) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Spad = (S + 63) & ~63;
   uint8_t* sK = smem;
   uint8_t* sV = sK + Spad * D * 2;
   uint8_t* sQ = sV + Spad * D * 2;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
-  const int q0 = blockIdx.x * ATT_ROWS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long rs = 3LL * H * D;
   const __nv_bfloat16* qb = qkv + (long long)b * S * rs + h * D;
-  load_tile<D>(sQ, qb, rs, q0, ATT_ROWS, S);
+  load_tile<D>(sQ, qb, rs, blockIdx.x * q_rows, q_rows, S);
   load_tile<D>(sK, qb + H * D, rs, 0, Spad, S);
   load_tile<D>(sV, qb + 2 * H * D, rs, 0, Spad, S);
   cp_async_wait_all();
   __syncthreads();
 
+  for (int pass = 0; pass < q_rows / ATT_ROWS; ++pass) {
+  const int q0 = blockIdx.x * q_rows + pass * ATT_ROWS;
+  if (q0 + warp * 16 >= S) break;  // warp-uniform; no block-level sync below
   uint32_t qf[D / 16][4];
-  load_afrag<D>(qf, sQ, warp * 16, lane);
+  load_afrag<D>(qf, sQ, pass * ATT_ROWS + warp * 16, lane);
   float oacc[D / 8][4];
 #pragma unroll
   for (int j = 0; j < D / 8; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
@@ -250,10 +253,11 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     if (row0 + g < S) lb[row0 + g] = (m0 + log2f(l0)) * LN2;
     if (row0 + g + 8 < S) lb[row0 + g + 8] = (m1 + log2f(l1)) * LN2;
   }
+  }  // pass
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-// grid = (ceil(S/64), NB*H).  smem: K[Spad][D], V[Spad][D], Q[64][D], dO[64][D].  Also emits delta = rowsum(dO*O).
+// grid = (ceil(S/128), NB*H).  smem: K[Spad][D], V[Spad][D], Q[128][D], dO[128][D].  Also emits delta = rowsum(dO*O).
 template <int D>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
@@ -347,7 +351,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-// grid = (ceil(S/64), NB*H) over key tiles.  smem: Q[Spad][D], dO[Spad][D], K[64][D], V[64][D], lse2[Spad], delta[Spad].
+// grid = (ceil(S/128), NB*H) over key tiles.  smem: Q[Spad][D], dO[Spad][D], K[128][D], V[128][D], lse2[Spad], delta[Spad].
 template <int D>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
@@ -439,8 +443,11 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
   if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
   if (NB * H > 65535) return MFV_ERR_SHAPE;
   const int Spad = ((int)S + 63) & ~63;
-  const size_t smem = (size_t)(2 * Spad + ATT_ROWS) * D * 2;
-  dim3 grid((unsigned)((S + ATT_ROWS - 1) / ATT_ROWS), (unsigned)(NB * H));
+  // whole query range in one CTA when K, V and Q of a head fit twice per SM (S=197: 96 KB); else 128-row chunks
+  const int Sq = ((int)S + ATT_ROWS - 1) / ATT_ROWS * ATT_ROWS;
+  int q_rows = ((size_t)(2 * Spad + Sq) * D * 2 <= 110 * 1024) ? Sq : ATT_ROWS;
+  const size_t smem = (size_t)(2 * Spad + q_rows) * D * 2;
+  dim3 grid((unsigned)((S + q_rows - 1) / q_rows), (unsigned)(NB * H));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(o);
@@ -450,7 +457,7 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
   do {                                                                                                               \
     if ((rc = set_smem(attn_fwd_kernel<DD, FF>, smem))) return rc;                                                   \
     attn_fwd_kernel<DD, FF><<<grid, ATT_WARPS * 32, smem, st>>>(q, op, o_is_f16, obf, lse, (int)S, (int)H,           \
-                                                                 scale * LOG2E);                                      \
+                                                                 scale * LOG2E, q_rows);                              \
   } while (0)
   if (D == 64) { if (qkv_is_f16) MFV_ATT_FWD(64, true); else MFV_ATT_FWD(64, false); }
   else { if (qkv_is_f16) MFV_ATT_FWD(32, true); else MFV_ATT_FWD(32, false); }

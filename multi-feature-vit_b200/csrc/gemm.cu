@@ -22,11 +22,11 @@ namespace mfv {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;              // two warps per TMEM lane quarter: each converts half of the columns
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
-constexpr int EPI_BUF = 4096;                 // one staging buffer: 32 rows x 128 B
-constexpr int EPI_BUFS_PER_WARP = 3;          // out0 | out1 (or aux ping) | out2 (or aux pong)
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS_PER_WARP * EPI_BUF;
+constexpr int EPI_BUF = 4096;                 // one staging buffer: 32 rows x 128 B (shared by the two warps of a quarter)
+constexpr int EPI_BUFS_PER_WARP = 3;          // per quarter: out0 | out1 (or aux ping) | out2 (or aux pong)
+constexpr int EPI_BYTES = 4 * EPI_BUFS_PER_WARP * EPI_BUF;
 
 struct GemmParams {
   int M, N, K, G;
@@ -84,8 +84,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * NUM_EPI_WARPS);
+  uint64_t* aux_bar = tempty_bar + 2;  // [4 quarters][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,7 +103,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], NUM_EPI_WARPS * 32);
     }
-    for (int s = 0; s < 2 * NUM_EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < 2 * 4; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -190,18 +190,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;      // TMEM lane quarter this warp may access
-    const int ew = warp - 2;     // 0..3: staging slice / aux barriers
-    uint8_t* st0 = epi_base + ew * (EPI_BUFS_PER_WARP * EPI_BUF);
+    // Two warps (h = 0, 1) serve each TMEM lane quarter q: both hold row (q*32 + lane), warp h converts the h-th half
+    // of every 128-byte staging row (16-byte chunks 4h..4h+3).  They meet at named barrier 1+q; warp h=0 lane 0 is the
+    // quarter's leader and issues all TMA traffic (aux prefetch, stores).
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int h = (warp - 2) >> 2;     // column half
+    const bool leader = (h == 0) && (lane == 0);
+    uint8_t* st0 = epi_base + q * (EPI_BUFS_PER_WARP * EPI_BUF);
     uint8_t* st1 = st0 + EPI_BUF;
     uint8_t* st2 = st1 + EPI_BUF;
-    uint64_t* abar = aux_bar + 2 * ew;
+    uint64_t* abar = aux_bar + 2 * q;
     uint32_t aux_phase0 = 0u, aux_phase1 = 0u;
     const bool has_aux = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_DGELU);
     // column chunk handled per staging round: 128 B per row -> 32 fp32 or 64 16-bit columns
     const bool out32 = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_F32 || p.epi == MFV_EPI_ATOMIC_F32);
     const int CW = out32 ? 32 : 64;
+    const int HW = CW >> 1;            // columns per warp per round: 16 (fp32) or 32 (16-bit)
     const int nchunks = BN / CW;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int r = t;
@@ -211,12 +217,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = r / p.tiles_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row0 = m_tile * BM + q * 32;   // first row of this warp's 32-row slice
+      const int row0 = m_tile * BM + q * 32;   // first row of this quarter's 32-row slice
       const int ncol0 = n_tile * BN;
-      const bool rows_ok = row0 < p.M;  // warp-uniform: slices fully past M do nothing (TMA clips partial ones)
+      const bool rows_ok = row0 < p.M;  // quarter-uniform: slices fully past M do nothing (TMA clips partial ones)
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
-      // prefetch the aux operand of chunk 0 while the MMAs of this tile are still running
-      if (has_aux && lane == 0 && rows_ok) {
+      // prefetch the aux operand of chunk 0 while the MMAs of this tile are still running (st1 is free: the pair
+      // passed the second barrier of the previous round after its last read)
+      if (has_aux && leader && rows_ok) {
         mbar_arrive_expect_tx(&abar[0], EPI_BUF);
         tma_load_3d(st1, &tmAux, &abar[0], ncol0, row0, g);
       }
@@ -226,36 +233,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         const int n0 = ncol0 + c * CW;
-        if (n0 >= p.N || !rows_ok) break;  // warp-uniform
-        // next aux chunk: its buffer was last read in round c-1 and every lane is past that round (syncwarp below)
-        if (has_aux && lane == 0 && c + 1 < nchunks && n0 + CW < p.N) {
+        if (n0 >= p.N || !rows_ok) break;  // quarter-uniform
+        if (has_aux && leader && c + 1 < nchunks && n0 + CW < p.N) {
           uint8_t* nb = ((c + 1) & 1) ? st2 : st1;
           mbar_arrive_expect_tx(&abar[(c + 1) & 1], EPI_BUF);
           tma_load_3d(nb, &tmAux, &abar[(c + 1) & 1], n0 + CW, row0, g);
         }
-        float f[64];
+        float f[32];
         {
           uint32_t v[32];
-          tmem_ld32(trow + (uint32_t)(c * CW), v);
           if (!out32) {
-            uint32_t v2[32];
-            tmem_ld32(trow + (uint32_t)(c * CW + 32), v2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[32 + i] = __uint_as_float(v2[i]);
+            tmem_ld32(trow + (uint32_t)(c * CW + h * 32), v);
           } else {
-            tmem_ld_wait();
+            tmem_ld16(trow + (uint32_t)(c * CW + h * 16), v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[32 + i] = 0.f;
+            for (int i = 16; i < 32; ++i) v[i] = 0u;
           }
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         }
         if (bias) {
+          const float* bp = bias + n0 + h * HW;
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            if (i < CW) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
+          for (int i = 0; i < 32; i += 4) {
+            if (i < HW) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
               f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
             }
           }
@@ -266,12 +269,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else       { mbar_wait(&abar[0], aux_phase0); aux_phase0 ^= 1u; }
         }
         // the previous round's bulk stores must have finished reading the staging buffers
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
+        if (leader) bulk_wait_read0();
+        pair_sync();
+        const int j0 = h * 4;  // this warp's 16-byte chunks of the staging row
         switch (p.epi) {
           case MFV_EPI_BF16: {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               uint4 o;
               if (p.out_f16)
                 o = make_uint4(pack_f16(f[8 * j], f[8 * j + 1]), pack_f16(f[8 * j + 2], f[8 * j + 3]),
@@ -279,13 +283,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               else
                 o = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) = o;
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) = o;
             }
           } break;
           case MFV_EPI_GELU: {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = bf16 copy of C2
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) =
                   make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                              pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
               float gl[8];
@@ -293,25 +297,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int i = 0; i < 8; ++i) gl[i] = gelu_erf(f[8 * j + i]);
               const uint4 gb = make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
                                           pack_bf16(gl[6], gl[7]));
-              *reinterpret_cast<uint4*>(st1 + stage_off(lane, j)) =
+              *reinterpret_cast<uint4*>(st1 + stage_off(lane, j0 + j)) =
                   p.out_f16 ? make_uint4(pack_f16(gl[0], gl[1]), pack_f16(gl[2], gl[3]), pack_f16(gl[4], gl[5]),
                                          pack_f16(gl[6], gl[7]))
                             : gb;
-              if (p.has_c3) *reinterpret_cast<uint4*>(st2 + stage_off(lane, j)) = gb;
+              if (p.has_c3) *reinterpret_cast<uint4*>(st2 + stage_off(lane, j0 + j)) = gb;
             }
           } break;
           case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 rr = *reinterpret_cast<const float4*>(ab + stage_off(lane, j));
-              *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
+            for (int j = 0; j < 4; ++j) {
+              const float4 rr = *reinterpret_cast<const float4*>(ab + stage_off(lane, j0 + j));
+              *reinterpret_cast<float4*>(st0 + stage_off(lane, j0 + j)) =
                   make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
             }
           } break;
           case MFV_EPI_DGELU: {  // C(bf16) = acc * gelu'(u), u = aux (bf16)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 uu = *reinterpret_cast<const uint4*>(ab + stage_off(lane, j));
+            for (int j = 0; j < 4; ++j) {
+              const uint4 uu = *reinterpret_cast<const uint4*>(ab + stage_off(lane, j0 + j));
               const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
               uint32_t o[4];
 #pragma unroll
@@ -319,19 +323,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float2 u2 = unpack_bf16(uw[i]);
                 o[i] = pack_bf16(f[8 * j + 2 * i] * gelu_erf_grad(u2.x), f[8 * j + 2 * i + 1] * gelu_erf_grad(u2.y));
               }
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           } break;
           default: {  // MFV_EPI_F32 / MFV_EPI_ATOMIC_F32: raw fp32 tile
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(st0 + stage_off(lane, j0 + j)) =
                   make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } break;
         }
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        pair_sync();
+        if (leader) {
           if (p.epi == MFV_EPI_ATOMIC_F32) {
             tma_reduce_add_3d(&tmC, st0, n0, row0, g);
           } else {
@@ -347,7 +351,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
-    if (lane == 0) bulk_wait0();  // all global writes of this warp are complete before the CTA exits
+    if (leader) bulk_wait0();  // all global writes of this quarter are complete before the CTA exits
   }
 
   tc_fence_before();

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ dres,
               const float* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ gamma, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows_per_group, long long gb_gstride) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+              long long rows_per_group, long long gb_gstride) {
   constexpr int C = NV * 128;
   __shared__ float red[LN_WARPS][C + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,9 +76,9 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
   float4 gam[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gam[i] = __ldg(gm + lane + 32 * i);
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], ds[NV];  // ds: column sums of dx = bias gradient of the Linear that produced x's residual branch
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows_per_group; r += (long long)gridDim.x * LN_WARPS) {
     const long long row = g * rows_per_group + r;
@@ -113,20 +114,21 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
         const float4 rr = reinterpret_cast<const float4*>(dres + row * C)[lane + 32 * i];
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
       }
+      ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
       if (dx32) reinterpret_cast<float4*>(dx32 + row * C)[lane + 32 * i] = o;
       if (dx16)
         reinterpret_cast<uint2*>(dx16 + row * C)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     }
   }
-  if (!dgamma && !dbeta) return;
-  // block reduction of the column partials: two rounds through smem (dgamma, then dbeta)
+  if (!dgamma && !dbeta && !dxsum) return;
+  // block reduction of the column partials: three rounds through smem (dgamma, dbeta, sum of dx)
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    float* out = pass == 0 ? dgamma : dbeta;
+  for (int pass = 0; pass < 3; ++pass) {
+    float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 t = pass == 0 ? dg[i] : db[i];
+      const float4 t = pass == 0 ? dg[i] : (pass == 1 ? db[i] : ds[i]);
       *reinterpret_cast<float4*>(&red[warp][(lane + 32 * i) * 4]) = t;
     }
     __syncthreads();
@@ -165,8 +167,8 @@ extern "C" int mfv_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x,
                                  const float* mean, const float* rstd, const float* gamma, float* dx_f32,
-                                 void* dx_bf16, float* dgamma, float* dbeta, int64_t G, int64_t rows, int64_t C,
-                                 int64_t gb_gstride, void* stream) {
+                                 void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t G, int64_t rows,
+                                 int64_t C, int64_t gb_gstride, void* stream) {
   using namespace mfv;
   if (G <= 0 || rows <= 0) return MFV_ERR_SHAPE;
   if (!dy_bf16 && !dy_f32) return MFV_ERR_ARG;
@@ -178,9 +180,9 @@ extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
   const __nv_bfloat16* dy16 = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   switch (C) {
-    case 256: ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, gb_gstride); break;
-    case 384: ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, gb_gstride); break;
-    case 768: ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, gb_gstride); break;
+    case 256: ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
+    case 384: ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
+    case 768: ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
     default: return MFV_ERR_SHAPE;
   }
   MFV_LAUNCH_CHECK();

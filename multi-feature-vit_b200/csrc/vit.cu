@@ -211,27 +211,30 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
   const int last = 2 * (int)p->depth;
   int cur = 0;  // dx[cur] holds the gradient of the residual stream
   // final norm
+  // each LN backward also emits colsum(dx) = bias gradient of the Linear feeding that residual add (fc2 / proj)
   RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
-                       p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b), G, M, C, p->P, st));
+                       p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
+                       v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
   for (int l = (int)p->depth - 1; l >= 0; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
-    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), st));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), -1, st));  // bias: LN backward above
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid, v.u(l), Hd, st));
     RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
                          v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
-                         v.gr(v.boff(l, p->r_ln2_b)), G, M, C, p->P, st));
+                         v.gr(v.boff(l, p->r_ln2_b)), v.gr(v.boff(l, p->r_proj_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), st));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, st));  // bias: LN2 backward above
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, 0, st));
     RCP(PROF_ATTN_BWD, mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
     RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
                          v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
-                         v.gr(v.boff(l, p->r_ln1_b)), G, M, C, p->P, st));
+                         v.gr(v.boff(l, p->r_ln1_b)), l > 0 ? v.gr(v.boff(l - 1, p->r_fc2_b)) : nullptr, G, M, C, p->P,
+                         st));
     cur ^= 1;
   }
   // ---- embedding: cls gradient, conv bias / weight gradient (pos_embed is a fixed table)

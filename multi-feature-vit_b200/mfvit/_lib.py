@@ -77,7 +77,7 @@ SIGNATURES = {
     "mfv_prof_read": (C.c_int, [c_vp, c_vp, C.c_int]),
     "mfv_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
-    "mfv_layernorm_bwd": (C.c_int, [c_vp] * 11 + [i64, i64, i64, i64, c_vp]),
+    "mfv_layernorm_bwd": (C.c_int, [c_vp] * 12 + [i64, i64, i64, i64, c_vp]),
     "mfv_attn_fwd": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_attn_bwd": (C.c_int, [c_vp, C.c_int] + [c_vp] * 5 + [i64, i64, i64, i64, f32, c_vp]),
     "mfv_patchify": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, i64, i64, c_vp]),

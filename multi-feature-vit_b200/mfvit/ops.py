@@ -90,7 +90,7 @@ def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False, f16=False
     return y16, y32, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, want_bf16=True):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, want_bf16=True, dx_colsum=None):
     G, rows, Cd = x.shape
     lib = _lib_for(x)
     dx = torch.empty_like(x)
@@ -98,7 +98,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, 
     dy16 = dy if dy.dtype == torch.bfloat16 else None
     dy32 = dy if dy.dtype == torch.float32 else None
     check(lib.mfv_layernorm_bwd(_p(dy16), _p(dy32), _p(dres), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx16),
-                                _p(dgamma), _p(dbeta), G, rows, Cd, gamma.stride(0) if gamma.dim() > 1 else 0,
+                                _p(dgamma), _p(dbeta), _p(dx_colsum), G, rows, Cd,
+                                gamma.stride(0) if gamma.dim() > 1 else 0,
                                 _stream()), "mfv_layernorm_bwd")
     return dx, dx16
 

@@ -126,7 +126,9 @@ def t_ln():
     ref.backward(dy)
     dgam = torch.zeros_like(gam)
     dbet = torch.zeros_like(bet)
-    dx, dx16 = ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dgam, dbeta=dbet)
+    dxs = torch.zeros_like(gam)
+    dx, dx16 = ops.layernorm_bwd(dy, x, mean, rstd, gam, dres=dres, dgamma=dgam, dbeta=dbet, dx_colsum=dxs)
+    report("layernorm bwd colsum(dx) (folded bias grad)", dxs, (xr.grad + dres).sum(1), 1e-3, rel=True)
     report("layernorm bwd dx (f32 dy, +dres)", dx, xr.grad + dres, 1e-4)
     report("layernorm bwd dx bf16 copy", dx16, xr.grad + dres, 2e-2, rel=True)
     report("layernorm bwd dgamma", dgam, gr.grad, 1e-3, rel=True)
