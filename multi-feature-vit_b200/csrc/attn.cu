@@ -74,14 +74,14 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const __nv_bfloat16* ba
 
 // acc[j] (16 x 8 per n-tile j) += A(16 x D, register fragments) * Bt, with Bt rows = "n" index taken from a
 // [n][D] row-major tile (ldmatrix, no transpose).  Used for Q K^T, dO V^T, K Q^T, V dO^T.
-template <int D, bool F16 = false>
+template <int D, bool F16 = false, int NP = 4>  // NP: number of 16-row groups of the tile actually multiplied (tail trimming)
 __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&afrag)[D / 16][4], const uint8_t* tile,
                                          int n_row0, int lane) {
   const uint32_t tbase = smem_u32(tile);
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
+    for (int jp = 0; jp < NP; ++jp) {
       const int row = n_row0 + jp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
       const int chunk = 2 * kk + ((lane >> 3) & 1);
       uint32_t b0, b1, b2, b3;
@@ -94,12 +94,12 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&af
 
 // out[j] (16 x 8 per d-tile j, D/8 tiles) += P(16 x 64, from accumulator registers, rounded to bf16) * B, with B rows =
 // reduction index taken from a [k][D] row-major tile (ldmatrix.trans).  Used for P V, dS K, P^T dO, dS^T Q.
-template <int D, bool F16 = false>
+template <int D, bool F16 = false, int NP = 4>  // NP: number of 16-deep reduction steps actually taken
 __device__ __forceinline__ void mma_p_b(float (&out)[D / 8][4], const float (&p)[8][4], const uint8_t* tile,
                                         int k_row0, int lane) {
   const uint32_t tbase = smem_u32(tile);
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < NP; ++kk) {
     uint32_t a[4];
     if constexpr (F16) {
       a[0] = pack_f16(p[2 * kk][0], p[2 * kk][1]);
@@ -172,7 +172,7 @@ __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], __nv_bf
 // grid = (ceil(S/q_rows), NB*H).  smem: K[Spad][D], V[Spad][D], Q[q_rows][D]; q_rows is a multiple of 128 and the CTA
 // walks it in passes of 128 rows (8 warps x 16), so K/V of a head are fetched once (S=197) or ceil(S/128) times.
 template <int D, bool F16>
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+__global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o, int o_is_f16,
                 __nv_bfloat16* __restrict__ o_bf, float* __restrict__ lse, int S, int H, float scale_log2, int q_rows) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -201,11 +201,15 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int t = lane & 3;
 
-  for (int kb = 0; kb < Spad; kb += 64) {
+  for (int kb = 0; kb < S; kb += 64) {
+    const int np = min(4, (S - kb + 15) >> 4);  // 16-key groups holding valid keys in this block (tail: S=197 -> 1)
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mma_a_bt<D, F16>(s, qf, sK, kb, lane);
+    if (np == 4) mma_a_bt<D, F16, 4>(s, qf, sK, kb, lane);
+    else if (np == 3) mma_a_bt<D, F16, 3>(s, qf, sK, kb, lane);
+    else if (np == 2) mma_a_bt<D, F16, 2>(s, qf, sK, kb, lane);
+    else mma_a_bt<D, F16, 1>(s, qf, sK, kb, lane);
     float mx0 = m0, mx1 = m1;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -238,7 +242,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     for (int j = 0; j < D / 8; ++j) {
       oacc[j][0] *= a0; oacc[j][1] *= a0; oacc[j][2] *= a1; oacc[j][3] *= a1;
     }
-    mma_p_b<D, F16>(oacc, s, sV, kb, lane);
+    if (np == 4) mma_p_b<D, F16, 4>(oacc, s, sV, kb, lane);
+    else if (np == 3) mma_p_b<D, F16, 3>(oacc, s, sV, kb, lane);
+    else if (np == 2) mma_p_b<D, F16, 2>(oacc, s, sV, kb, lane);
+    else mma_p_b<D, F16, 1>(oacc, s, sV, kb, lane);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -325,15 +332,18 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < D / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 
-  for (int kb = 0; kb < Spad; kb += 64) {
+  for (int kb = 0; kb < S; kb += 64) {
+    const int np = min(4, (S - kb + 15) >> 4);
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
     }
-    mma_a_bt<D>(s, qf, sK, kb, lane);
-    mma_a_bt<D>(dp, dof, sV, kb, lane);
+    if (np == 4) { mma_a_bt<D, false, 4>(s, qf, sK, kb, lane); mma_a_bt<D, false, 4>(dp, dof, sV, kb, lane); }
+    else if (np == 3) { mma_a_bt<D, false, 3>(s, qf, sK, kb, lane); mma_a_bt<D, false, 3>(dp, dof, sV, kb, lane); }
+    else if (np == 2) { mma_a_bt<D, false, 2>(s, qf, sK, kb, lane); mma_a_bt<D, false, 2>(dp, dof, sV, kb, lane); }
+    else { mma_a_bt<D, false, 1>(s, qf, sK, kb, lane); mma_a_bt<D, false, 1>(dp, dof, sV, kb, lane); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int key = kb + j * 8 + 2 * t;
@@ -344,7 +354,10 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         s[j][e] = p * (dp[j][e] - (e < 2 ? dl0 : dl1)) * scale;  // dS
       }
     }
-    mma_p_b<D>(dq, s, sK, kb, lane);
+    if (np == 4) mma_p_b<D, false, 4>(dq, s, sK, kb, lane);
+    else if (np == 3) mma_p_b<D, false, 3>(dq, s, sK, kb, lane);
+    else if (np == 2) mma_p_b<D, false, 2>(dq, s, sK, kb, lane);
+    else mma_p_b<D, false, 1>(dq, s, sK, kb, lane);
   }
   __nv_bfloat16* dqb = dqkv + (long long)b * S * rs + h * D;
   store_rows<D>(dq, dqb, rs, row0, S, lane, 1.f, 1.f);
@@ -399,15 +412,19 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   const int t = lane & 3;
   const float scale_log2 = scale * LOG2E;
 
-  for (int qb0 = 0; qb0 < Spad; qb0 += 64) {
+  for (int qb0 = 0; qb0 < S; qb0 += 64) {
+    const int np = min(4, (S - qb0 + 15) >> 4);  // 16-query groups with valid queries (padded queries have p = 0)
     float st[8][4], dpt[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
       dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
     }
-    mma_a_bt<D>(st, kf, sQ, qb0, lane);     // S^T  = K Q^T   (rows: keys, cols: queries)
-    mma_a_bt<D>(dpt, vf, sdO, qb0, lane);   // dP^T = V dO^T
+    // S^T = K Q^T (rows: keys, cols: queries), dP^T = V dO^T
+    if (np == 4) { mma_a_bt<D, false, 4>(st, kf, sQ, qb0, lane); mma_a_bt<D, false, 4>(dpt, vf, sdO, qb0, lane); }
+    else if (np == 3) { mma_a_bt<D, false, 3>(st, kf, sQ, qb0, lane); mma_a_bt<D, false, 3>(dpt, vf, sdO, qb0, lane); }
+    else if (np == 2) { mma_a_bt<D, false, 2>(st, kf, sQ, qb0, lane); mma_a_bt<D, false, 2>(dpt, vf, sdO, qb0, lane); }
+    else { mma_a_bt<D, false, 1>(st, kf, sQ, qb0, lane); mma_a_bt<D, false, 1>(dpt, vf, sdO, qb0, lane); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int qi = qb0 + j * 8 + 2 * t;
@@ -419,8 +436,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
         dpt[j][e] = p * (dpt[j][e] - ((e & 1) ? de1 : de0)) * scale;     // dS^T
       }
     }
-    mma_p_b<D>(dv, st, sdO, qb0, lane);   // dV += P^T dO
-    mma_p_b<D>(dk, dpt, sQ, qb0, lane);   // dK += dS^T Q
+    // dV += P^T dO ; dK += dS^T Q
+    if (np == 4) { mma_p_b<D, false, 4>(dv, st, sdO, qb0, lane); mma_p_b<D, false, 4>(dk, dpt, sQ, qb0, lane); }
+    else if (np == 3) { mma_p_b<D, false, 3>(dv, st, sdO, qb0, lane); mma_p_b<D, false, 3>(dk, dpt, sQ, qb0, lane); }
+    else if (np == 2) { mma_p_b<D, false, 2>(dv, st, sdO, qb0, lane); mma_p_b<D, false, 2>(dk, dpt, sQ, qb0, lane); }
+    else { mma_p_b<D, false, 1>(dv, st, sdO, qb0, lane); mma_p_b<D, false, 1>(dk, dpt, sQ, qb0, lane); }
   }
   __nv_bfloat16* dkb = dqkv + (long long)b * S * rs + H * D + h * D;
   __nv_bfloat16* dvb = dqkv + (long long)b * S * rs + 2 * H * D + h * D;
