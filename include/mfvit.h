@@ -31,6 +31,8 @@ int mfv_abi_version(void);
 /* Binds the library to `device`; checks compute capability 10.x, resolves cuTensorMapEncodeTiled. */
 int mfv_init(int device);
 const char* mfv_strerror(int code);
+/* "file:line: expression" of the last CUDA runtime failure returned to this thread ("" if none); debugging aid. */
+const char* mfv_last_error_where(void);
 int mfv_num_sms(void);
 /* Number of kernels this library has launched so far in the process (bench.py reports the per-step delta). */
 uint64_t mfv_launch_count(void);
@@ -71,6 +73,8 @@ typedef struct {
   int32_t splits;  /* split-K factor (only with MFV_EPI_ATOMIC_F32) */
   int32_t block_n; /* 0 = auto, else 64/128/256 */
   int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere) */
+  int32_t cta_group;   /* 0 = auto, 1 = 128-row tiles, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) */
+  int32_t reserved;
 } mfv_gemm_args;
 int mfv_gemm(const mfv_gemm_args* args, void* stream);
 

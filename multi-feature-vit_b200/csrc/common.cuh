@@ -15,18 +15,27 @@
 #define MFV_ERR_INIT (-4)
 #define MFV_ERR_ARG (-5)
 
+namespace mfv {
+extern unsigned long long g_launch_count;
+void note_error(const char* file, int line, const char* expr);  // remembered for mfv_last_error_where()
+}
 #define MFV_CUDA_CHECK(expr)                         \
   do {                                               \
     cudaError_t _e = (expr);                         \
-    if (_e != cudaSuccess) return (int)_e;           \
+    if (_e != cudaSuccess) {                         \
+      mfv::note_error(__FILE__, __LINE__, #expr);    \
+      return (int)_e;                                \
+    }                                                \
   } while (0)
 
-namespace mfv { extern unsigned long long g_launch_count; }
 // every kernel launch in the library is followed by this macro: error check + launch accounting (mfv_launch_count)
 #define MFV_LAUNCH_CHECK()                           \
   do {                                               \
     cudaError_t _e = cudaGetLastError();             \
-    if (_e != cudaSuccess) return (int)_e;           \
+    if (_e != cudaSuccess) {                         \
+      mfv::note_error(__FILE__, __LINE__, "launch"); \
+      return (int)_e;                                \
+    }                                                \
     ++mfv::g_launch_count;                           \
   } while (0)
 
@@ -159,6 +168,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ clusters / cta_group::2 (CTA pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are signalled on the LEADER CTA's mbarrier
+// (peer bit 24 of the shared::cluster address cleared, as cute::SM100_TMA_2SM_LOAD does)
+__device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 split over the pair; issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at this offset in every CTA selected by cta_mask
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), SWIZZLE_128B, version 1.
 //   bits [0,14)  start address >> 4     bits [16,30) leading byte offset >> 4

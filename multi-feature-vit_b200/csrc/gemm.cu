@@ -25,7 +25,9 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;              // two warps per TMEM lane quarter: each converts half of the columns
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int EPI_BUF = 4096;                 // one staging buffer: 32 rows x 128 B (shared by the two warps of a quarter)
-constexpr int EPI_BUFS_PER_WARP = 3;          // per quarter: out0 | out1 (or aux ping) | out2 (or aux pong)
+constexpr int EPI_BUFS_PER_WARP = 6;          // per quarter: out0 x2 (double buffered) | 4 more: out1 x2, out2 x2 (GELU) or
+                                              // the aux chunks 0..3 of the tile
+constexpr int MAX_AUX_CHUNKS = 4;
 constexpr int EPI_BYTES = 4 * EPI_BUFS_PER_WARP * EPI_BUF;
 
 struct GemmParams {
@@ -39,12 +41,15 @@ struct GemmParams {
   const float* bias;
 };
 
-template <int BN>
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) computes 256 x BN; each CTA stages its own
+// 128 rows of A and HALF of the B tile, so the L2->SMEM ingest per MMA cycle is halved (128x128 tiles need 128 B/clk/SM,
+// about twice what an SM can ingest - measured 52 % of the tensor peak; the 256 x 256 pair needs 64 B/clk/SM).
+template <int BN, int CG>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 4 : 6);
+  static constexpr int STAGES = (STAGE_BYTES > 32768) ? 2 : (STAGE_BYTES > 24576 ? 4 : (STAGE_BYTES > 16384 ? 5 : 6));
   static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
 };
@@ -64,18 +69,19 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // 16-byte chunk j (0..7) of row r in a 32 x 128 B staging buffer laid out with the TMA 128B swizzle
 __device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                  const __grid_constant__ CUtensorMap tmC3, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + S::STAGES * S::STAGE_BYTES;
@@ -84,11 +90,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;  // [4 quarters][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * 4);
+  uint64_t* aux_bar = tempty_bar + 2;  // [4 quarters][MAX_AUX_CHUNKS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + MAX_AUX_CHUNKS * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair (issues the MMAs)
+  const int cta_id = blockIdx.x / CG, num_ctas = gridDim.x / CG;  // persistent schedule runs over clusters
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
@@ -101,14 +109,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], NUM_EPI_WARPS * 32);
+      mbar_init(&tempty_bar[s], NUM_EPI_WARPS * 32 * CG);
     }
-    for (int s = 0; s < 2 * 4; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < MAX_AUX_CHUNKS * 4; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -120,7 +130,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+        if (CG == 2) tma_load_3d_cg2(dst, map, bar, c0, c1, c2); else tma_load_3d(dst, map, bar, c0, c1, c2);
+      };
+      for (int t = cta_id; t < total_tiles; t += num_ctas) {
         int r = t;
         const int n_tile = r % p.tiles_n; r /= p.tiles_n;
         const int split = r % p.splits;   r /= p.splits;
@@ -128,24 +141,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int g = r / p.tiles_m;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int m0 = m_tile * (BM * CG) + (int)rank * BM;          // this CTA's 128 rows of A
+        const int n0 = n_tile * BN + (int)rank * (BN / CG);          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          // the leader's barrier collects the bytes of both CTAs' loads
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES * CG);
           if (!p.a_mn) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM, g);
+            load(sa, &tmA, &full_bar[stage], kb * BK, m0, g);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_3d(sa + j * 8192, &tmA, &full_bar[stage], m_tile * BM + j * 64, kb * BK, g);
+            for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK, g);
           }
           if (!p.b_mn) {
-            tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN, g);
+            load(sb, &tmB, &full_bar[stage], kb * BK, n0, g);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * 8192, &tmB, &full_bar[stage], n_tile * BN + j * 64, kb * BK, g);
+            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK, g);
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -153,15 +167,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kadv = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
       const uint32_t b_kadv = p.b_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
         int r = t / p.tiles_n;
         const int split = r % p.splits;
         const int kb0 = split * p.kb_per_split;
@@ -180,12 +194,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
+          if (CG == 2) umma_commit_cg2(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        if (CG == 2) umma_commit_cg2(&tfull_bar[as], 0x3); else umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -196,11 +212,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int h = (warp - 2) >> 2;     // column half
     const bool leader = (h == 0) && (lane == 0);
-    uint8_t* st0 = epi_base + q * (EPI_BUFS_PER_WARP * EPI_BUF);
-    uint8_t* st1 = st0 + EPI_BUF;
-    uint8_t* st2 = st1 + EPI_BUF;
-    uint64_t* abar = aux_bar + 2 * q;
-    uint32_t aux_phase0 = 0u, aux_phase1 = 0u;
+    uint8_t* stq = epi_base + q * (EPI_BUFS_PER_WARP * EPI_BUF);
+    uint8_t* auxb = stq + 2 * EPI_BUF;  // aux chunk buffers (RESID / DGELU)
+    uint32_t round = 0;                 // staging rounds issued so far: output buffers alternate, <=1 store in flight
+    uint64_t* abar = aux_bar + MAX_AUX_CHUNKS * q;
+    uint32_t aux_phase = 0u;  // all aux barriers of a quarter complete exactly once per tile
     const bool has_aux = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_DGELU);
     // column chunk handled per staging round: 128 B per row -> 32 fp32 or 64 16-bit columns
     const bool out32 = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_F32 || p.epi == MFV_EPI_ATOMIC_F32);
@@ -209,7 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nchunks = BN / CW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
       int r = t;
       const int n_tile = r % p.tiles_n; r /= p.tiles_n;
       r /= p.splits;
@@ -217,15 +233,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = r / p.tiles_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row0 = m_tile * BM + q * 32;   // first row of this quarter's 32-row slice
+      const int row0 = m_tile * (BM * CG) + (int)rank * BM + q * 32;   // first row of this quarter's 32-row slice
       const int ncol0 = n_tile * BN;
       const bool rows_ok = row0 < p.M;  // quarter-uniform: slices fully past M do nothing (TMA clips partial ones)
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
-      // prefetch the aux operand of chunk 0 while the MMAs of this tile are still running (st1 is free: the pair
-      // passed the second barrier of the previous round after its last read)
+      // prefetch the aux operand (fp32 residual / pre-GELU u) of the WHOLE tile while its MMAs are still running: one
+      // 4 KB buffer per chunk, so no TMA round trip is exposed inside the chunk loop.  The buffers are free: the pair
+      // passed the last barrier of the previous tile after its final read.
       if (has_aux && leader && rows_ok) {
-        mbar_arrive_expect_tx(&abar[0], EPI_BUF);
-        tma_load_3d(st1, &tmAux, &abar[0], ncol0, row0, g);
+        for (int c = 0; c < nchunks && ncol0 + c * CW < p.N; ++c) {
+          mbar_arrive_expect_tx(&abar[c], EPI_BUF);
+          tma_load_3d(auxb + c * EPI_BUF, &tmAux, &abar[c], ncol0 + c * CW, row0, g);
+        }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -234,11 +253,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < nchunks; ++c) {
         const int n0 = ncol0 + c * CW;
         if (n0 >= p.N || !rows_ok) break;  // quarter-uniform
-        if (has_aux && leader && c + 1 < nchunks && n0 + CW < p.N) {
-          uint8_t* nb = ((c + 1) & 1) ? st2 : st1;
-          mbar_arrive_expect_tx(&abar[(c + 1) & 1], EPI_BUF);
-          tma_load_3d(nb, &tmAux, &abar[(c + 1) & 1], n0 + CW, row0, g);
-        }
         float f[32];
         {
           uint32_t v[32];
@@ -263,13 +277,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        const uint8_t* ab = (c & 1) ? st2 : st1;
-        if (has_aux) {
-          if (c & 1) { mbar_wait(&abar[1], aux_phase1); aux_phase1 ^= 1u; }
-          else       { mbar_wait(&abar[0], aux_phase0); aux_phase0 ^= 1u; }
-        }
-        // the previous round's bulk stores must have finished reading the staging buffers
-        if (leader) bulk_wait_read0();
+        const uint8_t* ab = auxb + c * EPI_BUF;
+        if (has_aux) mbar_wait(&abar[c], aux_phase);
+        // double-buffered staging: only the stores issued two rounds ago must have finished reading their buffers
+        const uint32_t ob = round & 1u;
+        uint8_t* st0 = stq + ob * EPI_BUF;
+        uint8_t* st1 = stq + (2 + ob) * EPI_BUF;  // GELU only (aliases the aux area, unused there)
+        uint8_t* st2 = stq + (4 + ob) * EPI_BUF;
+        ++round;
+        if (leader) bulk_wait_read1();
         pair_sync();
         const int j0 = h * 4;  // this warp's 16-byte chunks of the staging row
         switch (p.epi) {
@@ -349,16 +365,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);  // the leader's MMA waits
+      if (has_aux && rows_ok) aux_phase ^= 1u;
     }
     if (leader) bulk_wait0();  // all global writes of this quarter are complete before the CTA exits
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's smem / TMEM stay alive until every MMA retired
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -407,17 +424,17 @@ static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, i
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   GemmParams p;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.G = (int)a->G;
-  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
   p.tiles_n = (p.N + BN - 1) / BN;
   p.kb_total = (p.K + BK - 1) / BK;
   int splits = a->splits > 0 ? a->splits : 1;
@@ -435,7 +452,7 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
   int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);
   if (rc) return rc;
-  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN, p.b_f16);
+  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN / CG, p.b_f16);
   if (rc) return rc;
   const int e = a->epilogue;
   const bool c32 = (e == MFV_EPI_RESID_F32 || e == MFV_EPI_F32 || e == MFV_EPI_ATOMIC_F32);
@@ -458,8 +475,19 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   }
 
   const int total = p.tiles_m * p.tiles_n * p.splits * p.G;
-  int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmC, tmC2, tmC3, tmAux, p);
+  int clusters = num_sms() / CG;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG == 2) ? 1 : 0;  // single-CTA tiles are plain (non-cluster) launches
+  MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
@@ -480,13 +508,25 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
     const long long tm = (a->M + BM - 1) / BM;
     const long long sp = a->splits > 0 ? a->splits : 1;
     bn = 128;
-    if (a->N % 256 == 0 && tm * (a->N / 256) * a->G * sp >= 2LL * num_sms()) bn = 256;
     if (tm * ((a->N + 127) / 128) * a->G * sp < num_sms() && a->N % 64 == 0) bn = 64;
   }
+  // the fused aux epilogues prefetch at most 4 chunks per tile: fp32 residual -> BN <= 128, bf16 u -> BN <= 256
+  if (a->epilogue == MFV_EPI_RESID_F32 && bn > 128) bn = 128;
+  // cta_group: 0 = auto.  Pairs (256-row tiles) whenever there are enough rows to fill the machine with pairs
+  int cg = a->cta_group;
+  if (cg == 0) cg = (a->M >= 256) ? 2 : 1;
+  if (cg == 2) {
+    if (a->epilogue == MFV_EPI_RESID_F32 && bn > 128) bn = 128;
+    switch (bn) {
+      case 128: return launch_gemm<128, 2>(a, s);
+      case 256: return launch_gemm<256, 2>(a, s);
+      default: cg = 1; break;
+    }
+  }
   switch (bn) {
-    case 64: return launch_gemm<64>(a, s);
-    case 128: return launch_gemm<128>(a, s);
-    case 256: return launch_gemm<256>(a, s);
+    case 64: return launch_gemm<64, 1>(a, s);
+    case 128: return launch_gemm<128, 1>(a, s);
+    case 256: return launch_gemm<256, 1>(a, s);
     default: return MFV_ERR_ARG;
   }
 }

@@ -6,6 +6,12 @@
 
 namespace mfv {
 unsigned long long g_launch_count = 0;
+static thread_local char g_err_where[256] = "";
+void note_error(const char* file, int line, const char* expr) {
+  const char* base = file;
+  for (const char* c = file; *c; ++c) if (*c == '/') base = c + 1;
+  snprintf(g_err_where, sizeof(g_err_where), "%s:%d: %s", base, line, expr);
+}
 static bool g_prof_on = false;
 struct ProfRec { int label; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_recs;
@@ -32,6 +38,9 @@ static int g_device = -1;
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 }  // namespace mfv
+
+// Source location and expression of the last CUDA runtime failure seen by this thread ("" if none).
+extern "C" const char* mfv_last_error_where(void) { return mfv::g_err_where; }
 
 extern "C" int mfv_abi_version(void) { return MFV_ABI_VERSION; }
 

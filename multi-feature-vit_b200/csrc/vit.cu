@@ -96,11 +96,22 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
   a.a_mn_major = 1; a.b_mn_major = 1;
   a.epilogue = MFV_EPI_ATOMIC_F32;
   a.block_n = 128;
+  // split-K: choose the split count whose tile count fills whole waves of the persistent grid best, while keeping
+  // at least 8 k-blocks (512 tokens) per split so the fp32 reduce-add traffic stays small against the mainloop
   const long long tiles = ((N + 127) / 128) * ((K + 127) / 128) * v.p->G;
-  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
   const long long kb = (rows + 63) / 64;
-  if (splits > kb) splits = kb;
-  if (splits < 1) splits = 1;
+  const long long sms = num_sms();
+  long long splits = 1;
+  double best = -1.0;
+  for (long long sp = 1; sp <= 32 && sp <= kb; ++sp) {
+    if (kb / sp < 8 && sp > 1) break;
+    const long long per = (kb + sp - 1) / sp;
+    const long long eff_sp = (kb + per - 1) / per;
+    const long long units = tiles * eff_sp;
+    const long long waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms) - 0.002 * (double)sp;
+    if (waves <= 3 && eff > best) { best = eff; splits = sp; }
+  }
   a.splits = (int)splits;
   int rc;
   {

@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("a_gstride", i64), ("b_gstride", i64), ("c_gstride", i64),
         ("aux_ld", i64), ("aux_gstride", i64), ("bias_gstride", i64),
         ("a_mn_major", i32), ("b_mn_major", i32), ("epilogue", i32), ("splits", i32), ("block_n", i32),
-        ("dtype_flags", i32),
+        ("dtype_flags", i32), ("cta_group", i32), ("reserved", i32),
     ]
 
 
@@ -69,6 +69,7 @@ SIGNATURES = {
     "mfv_abi_version": (C.c_int, []),
     "mfv_init": (C.c_int, [C.c_int]),
     "mfv_strerror": (C.c_char_p, [C.c_int]),
+    "mfv_last_error_where": (C.c_char_p, []),
     "mfv_num_sms": (C.c_int, []),
     "mfv_launch_count": (C.c_uint64, []),
     "mfv_prof_enable": (C.c_int, [C.c_int]),
@@ -129,7 +130,9 @@ def load():
 def check(rc, what="mfvit"):
     if rc != 0:
         msg = load().mfv_strerror(int(rc))
-        raise MfvError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", rc))
+        where = load().mfv_last_error_where() if rc > 0 else b""
+        raise MfvError("%s failed: %s (code %d)%s" % (what, msg.decode() if msg else "?", rc,
+                                                       " at " + where.decode() if where else ""))
 
 
 def init(device_index):
