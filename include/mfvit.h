@@ -60,7 +60,7 @@ typedef struct {
   const void* A;
   const void* B;
   void* C;
-  void* C2;
+  void* C2;         /* MFV_EPI_GELU: gelu(u) (required).  MFV_EPI_DGELU: optional bf16 gelu(aux) recomputed for the fc2 wgrad */
   void* C3;         /* MFV_EPI_GELU only: optional bf16 copy of C2 (kept for the backward GEMMs when C2 is fp16) */
   const void* bias; /* f32 [G][N] or NULL */
   const void* aux;
@@ -233,7 +233,8 @@ typedef struct {
    * (only when save_for_backward).  fwd_f16 = 0: everything bf16, the *_bf pointers are unused.                        */
   int32_t fwd_f16;
   int32_t reserved;
-  void* patches_bf; void* xn_bf; void* attn_o_bf; void* gact_bf;
+  void* patches_bf; void* xn_bf; void* attn_o_bf; /* same slot layout as patches / xn / attn_o */
+  void* gact_bf; /* bf16 [G][M][hidden], ONE slot: recomputed per block by the fc2-dgrad epilogue in the backward */
   /* backward only */
   const float* dtokens;   /* f32 [G][M][C] */
   float* dx[2];           /* f32 [G][M][C] ping-pong */

@@ -64,6 +64,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -86,6 +89,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// Blocks until every kernel this grid depends on has completed and its memory is visible.  A no-op when the kernel was
+// launched without cudaLaunchAttributeProgrammaticStreamSerialization.  EVERY global access of a kernel launched with that
+// attribute must come after this call.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel in the stream (if launched with the PDL attribute) start its CTAs as soon as SM resources free
+// up; it still blocks in griddep_wait() until this grid has completed.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -184,6 +196,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+// same without the release fence (.release.cluster costs a MEMBAR.ALL + ERRBAR per arrive): for hand-offs whose data
+// is ordered by other means (TMEM reads: tcgen05.wait::ld + tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 // TMA load issued by either CTA of a pair; the transaction bytes are signalled on the LEADER CTA's mbarrier
 // (peer bit 24 of the shared::cluster address cleared, as cute::SM100_TMA_2SM_LOAD does)
 __device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -268,29 +290,36 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);
 }
-// erf(x) to |err| <= 3e-7 (Abramowitz & Stegun 7.1.28): 1 - (1 + a1 x + ... + a6 x^6)^-16, x >= 0; 6 FMA, 4 squarings and
-// one MUFU.RCP - ~3x cheaper than erff in the GEMM epilogues, far below the 16-bit output rounding (2^-11).
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fminf(fabsf(x), 6.0f);
-  float p = 0.0000430638f;
-  p = fmaf(p, ax, 0.0002765672f);
-  p = fmaf(p, ax, 0.0001520143f);
-  p = fmaf(p, ax, 0.0092705272f);
-  p = fmaf(p, ax, 0.0422820123f);
-  p = fmaf(p, ax, 0.0705230784f);
-  p = fmaf(p, ax, 1.0f);
-  p = p * p; p = p * p; p = p * p; p = p * p;
-  float inv;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(p));  // single MUFU.RCP (p >= 1): 2^-23 relative error
-  const float r = 1.0f - inv;
-  return copysignf(r, x);
+// Exact (erf) GELU, as torch.nn.GELU() / timm Mlp, evaluated as x * Phi(x) with the normal CDF written as a
+// logistic of an odd polynomial:  Phi(x) = 1 / (1 + 2^(x * Q(x^2))),  Q = degree-4 minimax fit of -log2(e) * logit(Phi(x)) / x
+// over |x| <= 7 (monotone beyond, so no clamping).  Max |x * dPhi| = 3.4e-6 and |dgelu'| = 6.9e-6 in fp32 arithmetic
+// (tools/fit_gelu.py) - 70x below the fp16 rounding of the stored result - in 10 instructions: 6 FMA/MUL + 2 MUFU
+// (ex2, rcp) instead of ~20 for an erf polynomial; the GELU epilogue is issue-bound, so this is what sets its speed.
+__device__ __forceinline__ float normal_cdf_fast(float x, float x2) {
+  float q = -3.2289765385939972e-06f;
+  q = fmaf(q, x2, 8.82378953974694e-05f);
+  q = fmaf(q, x2, 0.0003602751239668578f);
+  q = fmaf(q, x2, -0.10522668808698654f);
+  q = fmaf(q, x2, -2.3020453453063965f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(q * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));  // t = +inf (x << 0) -> 0
+  return r;
 }
-// exact (erf) GELU, as torch.nn.GELU() / timm Mlp
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return x * normal_cdf_fast(x, x * x); }
+// gelu(x) and gelu'(x) = Phi(x) + x * phi(x) from one CDF evaluation (fc2-dgrad epilogue: dhid and the recomputed GELU)
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& dg) {
+  const float x2 = x * x;
+  const float cdf = normal_cdf_fast(x, x2);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x2 * -0.72134752044448170368f));  // exp(-x^2/2)
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float g, dg;
+  gelu_erf_both(x, g, dg);
+  return dg;
 }
 
 // same, with independent A / B element formats (0 = fp16, 1 = bf16): kind::f16 accepts mixed 16-bit operands

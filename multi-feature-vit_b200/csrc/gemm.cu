@@ -22,13 +22,12 @@ namespace mfv {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 16-bit = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;              // two warps per TMEM lane quarter: each converts half of the columns
+constexpr int NUM_EPI_WARPS = 16;             // four warps per TMEM lane quarter: each owns every fourth column piece
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
-constexpr int EPI_BUF = 4096;                 // one staging buffer: 32 rows x 128 B (shared by the two warps of a quarter)
-constexpr int EPI_BUFS_PER_WARP = 6;          // per quarter: out0 x2 (double buffered) | 4 more: out1 x2, out2 x2 (GELU) or
-                                              // the aux chunks 0..3 of the tile
-constexpr int MAX_AUX_CHUNKS = 4;
-constexpr int EPI_BYTES = 4 * EPI_BUFS_PER_WARP * EPI_BUF;
+constexpr int EPI_BUF = 2048;                 // one staging slot: 32 rows x 64 B = one 64B-swizzled TMA box
+constexpr int EPI_NBUF = 3;                   // slots in each epilogue warp's private ring
+constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux barriers: 2 per epilogue warp
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_NBUF * EPI_BUF;
 
 struct GemmParams {
   int M, N, K, G;
@@ -36,7 +35,8 @@ struct GemmParams {
   int a_mn, b_mn;             // 1 = MN-major operand
   int a_f16, b_f16, out_f16;  // 1 = IEEE fp16 instead of bf16 (A and B must agree: mixed 16-bit operands trap)
   int epi;
-  int has_c3;
+  int has_c2, has_c3;
+  int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..10): see launch_gemm
   long long bias_gstride;
   const float* bias;
 };
@@ -71,9 +71,17 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// at most n (clamped to 0..3) of this thread's newest bulk groups may still be reading their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_n(int n) {
+  if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
 
-// 16-byte chunk j (0..7) of row r in a 32 x 128 B staging buffer laid out with the TMA 128B swizzle
-__device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+// 16-byte chunk j (0..3) of row r in a 32 x 64 B staging slot laid out with the TMA 64B swizzle (chunk index XOR
+// address bits [7,9) = (r >> 1) & 3); a warp's 32 x 16 B store then covers every bank exactly 4 times (conflict-free)
+__device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -90,8 +98,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;  // [4 quarters][MAX_AUX_CHUNKS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + MAX_AUX_CHUNKS * 4);
+  uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + AUX_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,9 +117,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], NUM_EPI_WARPS * 32 * CG);
+      mbar_init(&tempty_bar[s], NUM_EPI_WARPS * CG);  // one arrival per epilogue warp of the pair
     }
-    for (int s = 0; s < MAX_AUX_CHUNKS * 4; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < AUX_BARS; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -121,6 +129,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
 
   const int tiles_per_group = p.tiles_m * p.tiles_n * p.splits;
   const int total_tiles = tiles_per_group * p.G;
@@ -128,6 +137,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      griddep_wait();  // PDL: operands may still be in flight in the previous kernel
       int stage = 0;
       uint32_t phase = 0;
       auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -206,24 +216,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Two warps (h = 0, 1) serve each TMEM lane quarter q: both hold row (q*32 + lane), warp h converts the h-th half
-    // of every 128-byte staging row (16-byte chunks 4h..4h+3).  They meet at named barrier 1+q; warp h=0 lane 0 is the
-    // quarter's leader and issues all TMA traffic (aux prefetch, stores).
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int h = (warp - 2) >> 2;     // column half
-    const bool leader = (h == 0) && (lane == 0);
-    uint8_t* stq = epi_base + q * (EPI_BUFS_PER_WARP * EPI_BUF);
-    uint8_t* auxb = stq + 2 * EPI_BUF;  // aux chunk buffers (RESID / DGELU)
-    uint32_t round = 0;                 // staging rounds issued so far: output buffers alternate, <=1 store in flight
-    uint64_t* abar = aux_bar + MAX_AUX_CHUNKS * q;
-    uint32_t aux_phase = 0u;  // all aux barriers of a quarter complete exactly once per tile
-    const bool has_aux = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_DGELU);
-    // column chunk handled per staging round: 128 B per row -> 32 fp32 or 64 16-bit columns
-    const bool out32 = (p.epi == MFV_EPI_RESID_F32 || p.epi == MFV_EPI_F32 || p.epi == MFV_EPI_ATOMIC_F32);
-    const int CW = out32 ? 32 : 64;
-    const int HW = CW >> 1;            // columns per warp per round: 16 (fp32) or 32 (16-bit)
-    const int nchunks = BN / CW;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    // 16 warps.  Warp (q, h): q = TMEM lane quarter it may access (rows q*32 + lane of the tile), h = 0..3 selects the
+    // column pieces it owns (piece index = h mod 4).  A piece is 32 rows x 64 B of the primary output (32 16-bit or 16
+    // fp32 columns) = one 64B-swizzled TMA box of 2 KB.  Every warp works alone - its own ring of EPI_NBUF staging
+    // slots, its own aux barriers, its own bulk-store groups; there is no CTA-level barrier in the epilogue - so four
+    // warps per scheduler hide each other's TMEM / MUFU / TMA latencies (8 warps left the GELU epilogue latency-bound at
+    // 17 % issue utilisation, profiles/r01_ncu_gemm_fc1_v2.md).
+    // Ring protocol: every slot use ends in exactly one committed bulk group (lane 0), so slot (use % EPI_NBUF) is free
+    // again once at most EPI_NBUF-1 newer groups are still reading (cp.async.bulk.wait_group.read).
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int h = ew >> 2;
+    uint8_t* ring = epi_base + ew * (EPI_NBUF * EPI_BUF);
+    uint64_t* abar = aux_bar + 2 * ew;  // <= 2 aux pieces per warp per tile
+    uint32_t use = 0;                   // ring uses so far
+    uint32_t aux_phase = 0u;            // bit i = parity of abar[i]
+    const int epi = p.epi;
+    const bool has_aux = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_DGELU);
+    const bool out32 = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_F32 || epi == MFV_EPI_ATOMIC_F32);
+    const int PW = out32 ? 16 : 32;  // columns per piece
+    const int npieces = BN / PW;
+    // ring uses per piece: GELU writes u, g (and the optional bf16 twin); DGELU optionally adds gelu(u)
+    const int upc = (epi == MFV_EPI_GELU) ? (p.has_c3 ? 3 : 2) : ((epi == MFV_EPI_DGELU && p.has_c2) ? 2 : 1);
+    auto slot_ptr = [&](uint32_t u) { return ring + (u % EPI_NBUF) * EPI_BUF; };
+    // make the next slot writable: the bulk store that used it EPI_NBUF uses ago has finished reading it
+    auto acquire_slot = [&]() {
+      if (lane == 0) bulk_wait_read_n(EPI_NBUF - 1);
+      __syncwarp();
+    };
+    auto publish = [&](const CUtensorMap* map, const uint8_t* src, int c0, int r0, int gg, bool reduce) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (!(p.dbg_skip_epilogue & 2)) {
+          if (reduce) tma_reduce_add_3d(map, src, c0, r0, gg); else tma_store_3d(map, src, c0, r0, gg);
+        }
+        bulk_commit();
+      }
+      ++use;
+    };
+    auto release_accumulator = [&](int as) {  // all tcgen05.ld of this warp have completed (wait::ld is warp-wide)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster_relaxed(&tempty_bar[as], 0); else mbar_arrive_relaxed(&tempty_bar[as]);
+      }
+    };
+    auto pack16 = [&](float a, float b) { return p.out_f16 ? pack_f16(a, b) : pack_bf16(a, b); };
+    griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
     int it = 0;
     for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
       int r = t;
@@ -233,142 +273,150 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = r / p.tiles_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row0 = m_tile * (BM * CG) + (int)rank * BM + q * 32;   // first row of this quarter's 32-row slice
+      const int row0 = m_tile * (BM * CG) + (int)rank * BM + q * 32;   // first row of this warp's 32-row slice
       const int ncol0 = n_tile * BN;
-      const bool rows_ok = row0 < p.M;  // quarter-uniform: slices fully past M do nothing (TMA clips partial ones)
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
-      // prefetch the aux operand (fp32 residual / pre-GELU u) of the WHOLE tile while its MMAs are still running: one
-      // 4 KB buffer per chunk, so no TMA round trip is exposed inside the chunk loop.  The buffers are free: the pair
-      // passed the last barrier of the previous tile after its final read.
-      if (has_aux && leader && rows_ok) {
-        for (int c = 0; c < nchunks && ncol0 + c * CW < p.N; ++c) {
-          mbar_arrive_expect_tx(&abar[c], EPI_BUF);
-          tma_load_3d(auxb + c * EPI_BUF, &tmAux, &abar[c], ncol0 + c * CW, row0, g);
+      // pieces owned by this warp that hold real output (slices past M / N are skipped; TMA clips partial ones)
+      int n_my = 0;
+      if (row0 < p.M)
+        for (int c = h; c < npieces && ncol0 + c * PW < p.N; c += 4) ++n_my;
+      // while the MMAs of the tile are still running: pull this warp's bias lines into L1, and prefetch the aux operand
+      // (fp32 residual / pre-GELU u) of its pieces by TMA; the result is later computed in place in the same slot
+      if (bias && lane < n_my) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
+      if (has_aux && lane == 0) {
+        for (int i = 0; i < n_my; ++i) {
+          bulk_wait_read_n((int)EPI_NBUF - 1 - i * upc);
+          mbar_arrive_expect_tx(&abar[i], EPI_BUF);
+          tma_load_3d(slot_ptr(use + i * upc), &tmAux, &abar[i], ncol0 + (h + 4 * i) * PW, row0, g);
         }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (n_my == 0 || (p.dbg_skip_epilogue & 1)) {
+        release_accumulator(as);
+        if (has_aux)
+          for (int i = 0; i < n_my; ++i) { mbar_wait(&abar[i], (aux_phase >> i) & 1u); aux_phase ^= (1u << i); }
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        const int n0 = ncol0 + c * CW;
-        if (n0 >= p.N || !rows_ok) break;  // quarter-uniform
+      for (int i = 0; i < n_my; ++i) {
+        const int c = h + 4 * i;
+        const int n0 = ncol0 + c * PW;
         float f[32];
         {
           uint32_t v[32];
           if (!out32) {
-            tmem_ld32(trow + (uint32_t)(c * CW + h * 32), v);
+            tmem_ld32(trow + (uint32_t)(c * PW), v);
           } else {
-            tmem_ld16(trow + (uint32_t)(c * CW + h * 16), v);
+            tmem_ld16(trow + (uint32_t)(c * PW), v);
 #pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] = 0u;
+            for (int k = 16; k < 32; ++k) v[k] = 0u;
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         }
+        if (i == n_my - 1) release_accumulator(as);  // last TMEM read of the tile: the MMA warp may start tile it+2
         if (bias) {
-          const float* bp = bias + n0 + h * HW;
+          const float* bp = bias + n0;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if (i < HW) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          for (int k = 0; k < 32; k += 4) {
+            if (k < PW) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + k));
+              f[k] += b4.x; f[k + 1] += b4.y; f[k + 2] += b4.z; f[k + 3] += b4.w;
             }
           }
         }
-        const uint8_t* ab = auxb + c * EPI_BUF;
-        if (has_aux) mbar_wait(&abar[c], aux_phase);
-        // double-buffered staging: only the stores issued two rounds ago must have finished reading their buffers
-        const uint32_t ob = round & 1u;
-        uint8_t* st0 = stq + ob * EPI_BUF;
-        uint8_t* st1 = stq + (2 + ob) * EPI_BUF;  // GELU only (aliases the aux area, unused there)
-        uint8_t* st2 = stq + (4 + ob) * EPI_BUF;
-        ++round;
-        if (leader) bulk_wait_read1();
-        pair_sync();
-        const int j0 = h * 4;  // this warp's 16-byte chunks of the staging row
-        switch (p.epi) {
+        uint8_t* st0 = slot_ptr(use);
+        if (has_aux) { mbar_wait(&abar[i], (aux_phase >> i) & 1u); aux_phase ^= (1u << i); } else acquire_slot();
+        switch (epi) {
           case MFV_EPI_BF16: {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              if (p.out_f16)
-                o = make_uint4(pack_f16(f[8 * j], f[8 * j + 1]), pack_f16(f[8 * j + 2], f[8 * j + 3]),
-                               pack_f16(f[8 * j + 4], f[8 * j + 5]), pack_f16(f[8 * j + 6], f[8 * j + 7]));
-              else
-                o = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) = o;
-            }
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
+                  make_uint4(pack16(f[8 * j], f[8 * j + 1]), pack16(f[8 * j + 2], f[8 * j + 3]),
+                             pack16(f[8 * j + 4], f[8 * j + 5]), pack16(f[8 * j + 6], f[8 * j + 7]));
+            publish(&tmC, st0, n0, row0, g, false);
           } break;
-          case MFV_EPI_GELU: {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = bf16 copy of C2
+          case MFV_EPI_GELU: {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = optional bf16 copy of C2
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) =
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
                   make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                              pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-              float gl[8];
+            publish(&tmC, st0, n0, row0, g, false);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) gl[i] = gelu_erf(f[8 * j + i]);
-              const uint4 gb = make_uint4(pack_bf16(gl[0], gl[1]), pack_bf16(gl[2], gl[3]), pack_bf16(gl[4], gl[5]),
-                                          pack_bf16(gl[6], gl[7]));
-              *reinterpret_cast<uint4*>(st1 + stage_off(lane, j0 + j)) =
-                  p.out_f16 ? make_uint4(pack_f16(gl[0], gl[1]), pack_f16(gl[2], gl[3]), pack_f16(gl[4], gl[5]),
-                                         pack_f16(gl[6], gl[7]))
-                            : gb;
-              if (p.has_c3) *reinterpret_cast<uint4*>(st2 + stage_off(lane, j0 + j)) = gb;
+            for (int k = 0; k < 32; ++k) f[k] = gelu_erf(f[k]);
+            uint8_t* st1 = slot_ptr(use);
+            acquire_slot();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(st1 + stage_off(lane, j)) =
+                  make_uint4(pack16(f[8 * j], f[8 * j + 1]), pack16(f[8 * j + 2], f[8 * j + 3]),
+                             pack16(f[8 * j + 4], f[8 * j + 5]), pack16(f[8 * j + 6], f[8 * j + 7]));
+            publish(&tmC2, st1, n0, row0, g, false);
+            if (p.has_c3) {
+              uint8_t* st2 = slot_ptr(use);
+              acquire_slot();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(st2 + stage_off(lane, j)) =
+                    make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+              publish(&tmC3, st2, n0, row0, g, false);
             }
           } break;
-          case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream)
+          case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream), computed in place
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 rr = *reinterpret_cast<const float4*>(ab + stage_off(lane, j0 + j));
-              *reinterpret_cast<float4*>(st0 + stage_off(lane, j0 + j)) =
-                  make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
+              float4* pp = reinterpret_cast<float4*>(st0 + stage_off(lane, j));
+              const float4 rr = *pp;
+              *pp = make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
             }
+            publish(&tmC, st0, n0, row0, g, false);
           } break;
-          case MFV_EPI_DGELU: {  // C(bf16) = acc * gelu'(u), u = aux (bf16)
+          case MFV_EPI_DGELU: {  // C(bf16) = acc * gelu'(u) in place over u = aux (bf16); C2 (optional) = gelu(u) bf16
+            uint32_t gk[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 uu = *reinterpret_cast<const uint4*>(ab + stage_off(lane, j0 + j));
+              uint4* pp = reinterpret_cast<uint4*>(st0 + stage_off(lane, j));
+              const uint4 uu = *pp;
               const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
               uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 u2 = unpack_bf16(uw[i]);
-                o[i] = pack_bf16(f[8 * j + 2 * i] * gelu_erf_grad(u2.x), f[8 * j + 2 * i + 1] * gelu_erf_grad(u2.y));
+              for (int k = 0; k < 4; ++k) {
+                const float2 u2 = unpack_bf16(uw[k]);
+                float g0, g1, d0, d1;
+                gelu_erf_both(u2.x, g0, d0);
+                gelu_erf_both(u2.y, g1, d1);
+                o[k] = pack_bf16(f[8 * j + 2 * k] * d0, f[8 * j + 2 * k + 1] * d1);
+                gk[4 * j + k] = pack_bf16(g0, g1);
               }
-              *reinterpret_cast<uint4*>(st0 + stage_off(lane, j0 + j)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *pp = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            publish(&tmC, st0, n0, row0, g, false);
+            if (p.has_c2) {
+              uint8_t* st1 = slot_ptr(use);
+              acquire_slot();
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(st1 + stage_off(lane, j)) =
+                    make_uint4(gk[4 * j], gk[4 * j + 1], gk[4 * j + 2], gk[4 * j + 3]);
+              publish(&tmC2, st1, n0, row0, g, false);
             }
           } break;
           default: {  // MFV_EPI_F32 / MFV_EPI_ATOMIC_F32: raw fp32 tile
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(st0 + stage_off(lane, j0 + j)) =
+              *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
                   make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            publish(&tmC, st0, n0, row0, g, epi == MFV_EPI_ATOMIC_F32);
           } break;
         }
-        fence_proxy_async_smem();
-        pair_sync();
-        if (leader) {
-          if (p.epi == MFV_EPI_ATOMIC_F32) {
-            tma_reduce_add_3d(&tmC, st0, n0, row0, g);
-          } else {
-            tma_store_3d(&tmC, st0, n0, row0, g);
-            if (p.epi == MFV_EPI_GELU) {
-              tma_store_3d(&tmC2, st1, n0, row0, g);
-              if (p.has_c3) tma_store_3d(&tmC3, st2, n0, row0, g);
-            }
-          }
-          bulk_commit();
-        }
       }
-      tc_fence_before();
-      if (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);  // the leader's MMA waits
-      if (has_aux && rows_ok) aux_phase ^= 1u;
     }
-    if (leader) bulk_wait0();  // all global writes of this quarter are complete before the CTA exits
+    if (lane == 0) bulk_wait0();  // all global writes of this warp are complete before the CTA exits
   }
 
   tc_fence_before();
@@ -406,13 +454,13 @@ static int encode_operand_map(CUtensorMap* map, const void* base, int mn_major, 
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
 }
 
-// Row-major [G][rows][cols] tensor written / read by the epilogue: box = (128 B of columns, 32 rows, 1), 128B swizzle.
+// Row-major [G][rows][cols] tensor written / read by the epilogue: box = (64 B of columns, 32 rows, 1), 64B swizzle.
 static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, int is_f16, long long rows,
                            long long cols, long long ld, long long gstride, int groups) {
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)groups};
   cuuint64_t strides[2] = {(cuuint64_t)ld * elem_bytes,
                            (cuuint64_t)(groups > 1 ? gstride : rows * ld) * elem_bytes};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / elem_bytes), 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(64 / elem_bytes), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return MFV_ERR_ALIGN;
   PFN_encodeTiled enc = get_encode_tiled();
@@ -420,7 +468,7 @@ static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, i
   const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : (is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
 }
 
@@ -445,7 +493,9 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major; p.epi = a->epilogue;
   p.a_f16 = a->dtype_flags & 1; p.b_f16 = (a->dtype_flags >> 1) & 1; p.out_f16 = (a->dtype_flags >> 2) & 1;
   if (p.a_f16 != p.b_f16) return MFV_ERR_ARG;  // tcgen05 kind::f16 traps on mixed fp16 x bf16 operands
+  p.has_c2 = a->C2 != nullptr;
   p.has_c3 = a->C3 != nullptr;
+  p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 3;  // bit0: skip everything, bit1: skip the bulk stores
   p.bias_gstride = a->bias_gstride;
   p.bias = (const float*)a->bias;
 
@@ -461,6 +511,10 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
                        p.G);
   if (rc) return rc;
   tmC2 = tmC; tmC3 = tmC; tmAux = tmC;
+  if (e == MFV_EPI_DGELU && a->C2) {  // gelu(u) for the fc2 weight gradient, always bf16
+    rc = encode_tile_map(&tmC2, a->C2, 2, 0, a->M, a->N, a->ldc, a->c_gstride, p.G);
+    if (rc) return rc;
+  }
   if (e == MFV_EPI_GELU) {
     rc = encode_tile_map(&tmC2, a->C2, 2, p.out_f16, a->M, a->N, a->ldc, a->c_gstride, p.G);
     if (rc) return rc;
@@ -482,11 +536,20 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {  // programmatic dependent launch: prologue overlaps the previous kernel's tail (griddep_wait)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CG == 2) {  // single-CTA tiles are plain (non-cluster) launches
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CG == 2) ? 1 : 0;  // single-CTA tiles are plain (non-cluster) launches
+  cfg.numAttrs = na;
   MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
   MFV_LAUNCH_CHECK();
   return MFV_OK;

@@ -10,6 +10,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
+bool pdl_enabled();  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
 
 // Optional per-kernel-class device timing of the encoder executor (CUDA events on the launching stream).
 enum ProfLabel {

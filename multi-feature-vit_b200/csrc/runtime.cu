@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "mfvit_internal.h"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace mfv {
@@ -37,6 +38,14 @@ static int g_device = -1;
 
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFVIT_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 }  // namespace mfv
 
 // Source location and expression of the last CUDA runtime failure seen by this thread ("" if none).

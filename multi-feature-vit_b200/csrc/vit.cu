@@ -47,8 +47,10 @@ struct PlanView {
   __nv_bfloat16* ao_b(int l) const {
     return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->attn_o_bf) + (long long)slot(l) * MC : ao(l);
   }
+  // fp16-forward mode: the bf16 GELU output for the fc2 weight gradient is NOT kept per block - the fc2-dgrad epilogue
+  // recomputes it from u (which it reads anyway) into one reusable [G][M][hidden] buffer just before the wgrad runs
   __nv_bfloat16* g_b(int l) const {
-    return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->gact_bf) + (long long)slot(l) * Mh : g(l);
+    return p->fwd_f16 ? reinterpret_cast<__nv_bfloat16*>(p->gact_bf) : g(l);
   }
   const void* patches_b() const { return p->fwd_f16 ? p->patches_bf : p->patches; }
   float* gr(long long off) const { return p->grad + off; }
@@ -73,9 +75,9 @@ static int linear_fwd(const PlanView& v, const void* A, long long K, long long w
 }
 // dx = dy W: A = dy [G][M][N] K-major (reduction over N), B = W [N][K] read MN-major
 static int linear_dgrad(const PlanView& v, const void* dY, long long N, long long w_off, long long K, int epi, void* C,
-                        const void* aux, long long aux_ld, cudaStream_t st) {
+                        void* C2, const void* aux, long long aux_ld, cudaStream_t st) {
   mfv_gemm_args a = {};
-  a.A = dY; a.B = v.w16(w_off); a.C = C; a.aux = aux;
+  a.A = dY; a.B = v.w16(w_off); a.C = C; a.C2 = C2; a.aux = aux;
   a.M = v.M; a.N = K; a.K = N; a.G = v.p->G;
   a.lda = N; a.ldb = K; a.ldc = K;
   a.a_gstride = v.M * N; a.b_gstride = v.p->P; a.c_gstride = v.M * K;
@@ -200,7 +202,7 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
                          dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C,
                          p->P, 1e-6f, st));
     RC(linear_fwd(v, v.xn(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), Hd, MFV_EPI_GELU, v.u(l),
-                  v.g(l), dual ? v.g_b(l) : nullptr, nullptr, 0, st));
+                  v.g(l), nullptr, nullptr, 0, st));
     RC(linear_fwd(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), C, MFV_EPI_RESID_F32, x_out, nullptr,
                   nullptr, x_mid, C, st));
   }
@@ -228,20 +230,21 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
                        v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
   for (int l = (int)p->depth - 1; l >= 0; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid,
+                    p->fwd_f16 ? v.g_b(l) : nullptr, v.u(l), Hd, st));
     RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), -1, st));  // bias: LN backward above
-    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid, v.u(l), Hd, st));
     RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
-    RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
+    RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
                          v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
                          v.gr(v.boff(l, p->r_ln2_b)), v.gr(v.boff(l, p->r_proj_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
     RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, st));  // bias: LN2 backward above
-    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, 0, st));
+    RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, nullptr, 0, st));
     RCP(PROF_ATTN_BWD, mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
     RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
-    RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, 0, st));
+    RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
                          v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
                          v.gr(v.boff(l, p->r_ln1_b)), l > 0 ? v.gr(v.boff(l - 1, p->r_fc2_b)) : nullptr, G, M, C, p->P,

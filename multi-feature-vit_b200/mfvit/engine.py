@@ -109,7 +109,7 @@ class _Workspace:
         self.patches_bf = e(G * B * lay.np * 768, bf) if dual else None
         self.xn_bf = e(nxn * G * M * C_, bf) if dual else None
         self.attn_o_bf = e(nblk * G * M * C_, bf) if dual else None
-        self.gact_bf = e(nblk * G * M * Hd, bf) if dual else None
+        self.gact_bf = e(G * M * Hd, bf) if dual else None  # one slot: recomputed per block in the backward
         self.bwd = None
 
     def ensure_bwd(self, lay, device):

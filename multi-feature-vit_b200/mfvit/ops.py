@@ -57,7 +57,7 @@ def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=
                 epilogue=epilogue, block_n=block_n, dtype_flags=dtype_flags, cta_group=cta_group)
 
 
-def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, cta_group=0):
+def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, cta_group=0, out2=None):
     """dy16 [G,M,N] bf16, w16 [G,N,K] bf16 -> dx [G,M,K]."""
     G, M, N = dy16.shape
     K = w16.shape[2]
@@ -65,7 +65,7 @@ def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, ct
         out = torch.empty(G, M, K, device=dy16.device, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16)
     return gemm(dy16, w16, out, M=M, N=K, K=N, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=N * K,
                 c_gstride=M * K, aux=aux, aux_ld=K, aux_gstride=M * K, b_mn=True, epilogue=epilogue, block_n=block_n,
-                cta_group=cta_group)
+                cta_group=cta_group, C2=out2)
 
 
 def linear_wgrad(dy16, x16, dw, splits=8, block_n=128, cta_group=0):

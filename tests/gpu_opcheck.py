@@ -91,6 +91,11 @@ def t_gemm_epilogues():
     F.gelu(uu).backward(torch.ones_like(uu))
     out = ops.linear_dgrad(dy, w2, EPI_DGELU, aux=upre)
     report("gemm dgrad + dgelu", out, dxr * uu.grad, 2e-2, rel=True)
+    g2 = torch.empty_like(upre)
+    for bn in (128, 256):
+        out = ops.linear_dgrad(dy, w2, EPI_DGELU, aux=upre, out2=g2, block_n=bn)
+        report("gemm dgrad + dgelu (+gelu out) bn%d" % bn, out, dxr * uu.grad, 2e-2, rel=True)
+        report("gemm dgrad recomputed gelu bn%d" % bn, g2, F.gelu(upre.float()), 1e-2, rel=True)
     out = ops.linear_dgrad(dy, w2, EPI_BF16)
     report("gemm dgrad (B mn-major)", out, dxr, 2e-2, rel=True)
 
