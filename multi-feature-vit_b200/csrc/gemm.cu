@@ -26,7 +26,7 @@ constexpr int NUM_EPI_WARPS = 16;             // four warps per TMEM lane quarte
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int EPI_BUF = 2048;                 // one staging slot: 32 rows x 64 B = one 64B-swizzled TMA box
 constexpr int EPI_NBUF = 3;                   // slots in each epilogue warp's private ring
-constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux barriers: 2 per epilogue warp
+constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux (residual / pre-GELU) TMA loads: 2 in flight per epilogue warp
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_NBUF * EPI_BUF;
 
 struct GemmParams {
@@ -36,7 +36,7 @@ struct GemmParams {
   int a_f16, b_f16, out_f16;  // 1 = IEEE fp16 instead of bf16 (A and B must agree: mixed 16-bit operands trap)
   int epi;
   int has_c2, has_c3;
-  int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..10): see launch_gemm
+  int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
   long long bias_gstride;
   const float* bias;
 };
@@ -44,12 +44,18 @@ struct GemmParams {
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) computes 256 x BN; each CTA stages its own
 // 128 rows of A and HALF of the B tile, so the L2->SMEM ingest per MMA cycle is halved (128x128 tiles need 128 B/clk/SM,
 // about twice what an SM can ingest - measured 52 % of the tensor peak; the 256 x 256 pair needs 64 B/clk/SM).
+// BN = 384 (pairs only): the 256 x 384 output tile of a CTA pair is two UMMAs per k-step (N = 256 and N = 128) into one
+// 384-column accumulator - for the N = 384 GEMMs (proj, fc2, every dgrad, qkv/fc1 wgrad) the A operand is then read from
+// L2 exactly once instead of three times.  These kernels are L2->SM bandwidth bound (about 10 TB/s on the chip, measured:
+// the mainloop-only time of every shape tracks its tile traffic), so tile traffic is what sets their speed.
 template <int BN, int CG>
 struct GemmSmem {
+  static_assert(BN != 384 || CG == 2, "384-wide tiles need a CTA pair");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES > 32768) ? 2 : (STAGE_BYTES > 24576 ? 4 : (STAGE_BYTES > 16384 ? 5 : 6));
+  static constexpr int STAGES = (STAGE_BYTES > 40960) ? 2 : (STAGE_BYTES > 32768) ? 3 : (STAGE_BYTES > 24576 ? 4 : (STAGE_BYTES > 16384 ? 5 : 6));
+  static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;  // TMEM accumulators: double-buffered when two fit in 512 columns
   static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
 };
@@ -83,7 +89,9 @@ __device__ __forceinline__ void bulk_wait_read_n(int n) {
 // address bits [7,9) = (r >> 1) & 3); a warp's 32 x 16 B store then covers every bank exactly 4 times (conflict-free)
 __device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
-template <int BN, int CG>
+// EPI is a template parameter (MFV_EPI_ATOMIC_F32 shares the MFV_EPI_F32 instance): the epilogue is the issue-bound
+// part of these kernels, and a specialised instruction stream keeps it small (I-cache) and spill-free.
+template <int BN, int CG, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -105,7 +113,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair (issues the MMAs)
   const int cta_id = blockIdx.x / CG, num_ctas = gridDim.x / CG;  // persistent schedule runs over clusters
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int NACC = S::NACC;
+  constexpr uint32_t TMEM_COLS = (NACC * BN <= 32) ? 32 : (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -165,7 +174,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK, g);
           }
-          if (!p.b_mn) {
+          if (BN == 384) {
+            // pair tile = UMMA N=256 (each CTA supplies rows [rank*128, +128) of it) + UMMA N=128 (rows 256 + rank*64)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int nn = n_tile * BN + (j < 2 ? (int)rank * 128 + j * 64 : 256 + (int)rank * 64);
+              if (!p.b_mn) load(sb + j * 8192, &tmB, &full_bar[stage], kb * BK, nn, g);
+              else load(sb + j * 8192, &tmB, &full_bar[stage], nn, kb * BK, g);
+            }
+          } else if (!p.b_mn) {
             load(sb, &tmB, &full_bar[stage], kb * BK, n0, g);
           } else {
 #pragma unroll
@@ -178,7 +195,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, BN == 384 ? 256 : BN,
+                                         (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      const uint32_t idesc2 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, 128, (uint32_t)p.a_mn,
+                                          (uint32_t)p.b_mn);  // second UMMA of a 384-wide tile
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kadv = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
       const uint32_t b_kadv = p.b_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
@@ -190,8 +210,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int split = r % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it % NACC;
+        const uint32_t aphase = (it / NACC) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -206,6 +226,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
             if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BN == 384) {
+              const uint64_t db2 = make_smem_desc_sw128(sb + 16384u + k * b_kadv, b_lbo, 1024u);
+              umma_bf16_cg2(tmem_d + 256u, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
           if (CG == 2) umma_commit_cg2(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
@@ -219,7 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // 16 warps.  Warp (q, h): q = TMEM lane quarter it may access (rows q*32 + lane of the tile), h = 0..3 selects the
     // column pieces it owns (piece index = h mod 4).  A piece is 32 rows x 64 B of the primary output (32 16-bit or 16
     // fp32 columns) = one 64B-swizzled TMA box of 2 KB.  Every warp works alone - its own ring of EPI_NBUF staging
-    // slots, its own aux barriers, its own bulk-store groups; there is no CTA-level barrier in the epilogue - so four
+    // slots and its own bulk-store groups; there is no CTA-level barrier in the epilogue - so four
     // warps per scheduler hide each other's TMEM / MUFU / TMA latencies (8 warps left the GELU epilogue latency-bound at
     // 17 % issue utilisation, profiles/r01_ncu_gemm_fc1_v2.md).
     // Ring protocol: every slot use ends in exactly one committed bulk group (lane 0), so slot (use % EPI_NBUF) is free
@@ -228,16 +252,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int h = ew >> 2;
     uint8_t* ring = epi_base + ew * (EPI_NBUF * EPI_BUF);
-    uint64_t* abar = aux_bar + 2 * ew;  // <= 2 aux pieces per warp per tile
-    uint32_t use = 0;                   // ring uses so far
-    uint32_t aux_phase = 0u;            // bit i = parity of abar[i]
-    const int epi = p.epi;
-    const bool has_aux = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_DGELU);
-    const bool out32 = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_F32 || epi == MFV_EPI_ATOMIC_F32);
-    const int PW = out32 ? 16 : 32;  // columns per piece
-    const int npieces = BN / PW;
-    // ring uses per piece: GELU writes u, g (and the optional bf16 twin); DGELU optionally adds gelu(u)
-    const int upc = (epi == MFV_EPI_GELU) ? (p.has_c3 ? 3 : 2) : ((epi == MFV_EPI_DGELU && p.has_c2) ? 2 : 1);
+    uint32_t use = 0;  // ring uses so far
+    uint64_t* abar = aux_bar + 2 * ew;
+    uint32_t aux_phase = 0u;  // bit j = parity of abar[j]
+    constexpr int epi = EPI;
+    constexpr bool has_aux = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_DGELU);
+    constexpr bool out32 = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_F32);
+    constexpr int PW = out32 ? 16 : 32;  // columns per piece
+    constexpr int npieces = BN / PW;
     auto slot_ptr = [&](uint32_t u) { return ring + (u % EPI_NBUF) * EPI_BUF; };
     // make the next slot writable: the bulk store that used it EPI_NBUF uses ago has finished reading it
     auto acquire_slot = [&]() {
@@ -271,8 +293,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       r /= p.splits;
       const int m_tile = r % p.tiles_m;
       const int g = r / p.tiles_m;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
       const int row0 = m_tile * (BM * CG) + (int)rank * BM + q * 32;   // first row of this warp's 32-row slice
       const int ncol0 = n_tile * BN;
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
@@ -280,23 +302,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int n_my = 0;
       if (row0 < p.M)
         for (int c = h; c < npieces && ncol0 + c * PW < p.N; c += 4) ++n_my;
-      // while the MMAs of the tile are still running: pull this warp's bias lines into L1, and prefetch the aux operand
-      // (fp32 residual / pre-GELU u) of its pieces by TMA; the result is later computed in place in the same slot
-      if (bias && lane < n_my) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
-      if (has_aux && lane == 0) {
-        for (int i = 0; i < n_my; ++i) {
-          bulk_wait_read_n((int)EPI_NBUF - 1 - i * upc);
-          mbar_arrive_expect_tx(&abar[i], EPI_BUF);
-          tma_load_3d(slot_ptr(use + i * upc), &tmAux, &abar[i], ncol0 + (h + 4 * i) * PW, row0, g);
-        }
+      // The aux operand (fp32 residual / bf16 pre-GELU u) of piece i arrives by TMA in the ring slot where the result
+      // of piece i is then computed in place.  AUX_AHEAD pieces are in flight: the load of piece i+AUX_AHEAD is issued
+      // right after the first store of piece i, into the slot whose previous store is then the second-newest bulk group
+      // (wait_group.read 1 - never a wait on the store just issued).  upc = ring slots used per piece.
+      const int upc = (epi == MFV_EPI_DGELU && p.has_c2) ? 2 : 1;
+      const int aux_ahead = (upc == 1) ? 2 : 1;
+      const uint32_t use0 = use;
+      auto issue_aux = [&](int i, int pending_ok) {  // lane 0 only
+        bulk_wait_read_n(pending_ok);
+        mbar_arrive_expect_tx(&abar[i & 1], EPI_BUF);
+        tma_load_3d(slot_ptr(use0 + (uint32_t)(i * upc)), &tmAux, &abar[i & 1], ncol0 + (h + 4 * i) * PW, row0, g);
+      };
+      if constexpr (has_aux) {
+        if (lane == 0)
+          for (int j = 0; j < aux_ahead && j < n_my; ++j) issue_aux(j, (int)EPI_NBUF - 1 - j * upc);
       }
+      // pull this warp's bias lines into L1 while the MMAs of the tile are still running
+      if (bias && lane < n_my) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      if (n_my == 0 || (p.dbg_skip_epilogue & 1)) {
+      if (n_my == 0) {
         release_accumulator(as);
-        if (has_aux)
-          for (int i = 0; i < n_my; ++i) { mbar_wait(&abar[i], (aux_phase >> i) & 1u); aux_phase ^= (1u << i); }
+        continue;
+      }
+      if (p.dbg_skip_epilogue & 1) {  // measurement aid: drain the aux loads already issued, touch nothing else
+        release_accumulator(as);
+        if constexpr (has_aux) {
+          for (int j = 0; j < aux_ahead && j < n_my; ++j) {
+            mbar_wait(&abar[j & 1], (aux_phase >> (j & 1)) & 1u);
+            aux_phase ^= 1u << (j & 1);
+          }
+        }
         continue;
       }
 #pragma unroll 1
@@ -306,7 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float f[32];
         {
           uint32_t v[32];
-          if (!out32) {
+          if constexpr (!out32) {
             tmem_ld32(trow + (uint32_t)(c * PW), v);
           } else {
             tmem_ld16(trow + (uint32_t)(c * PW), v);
@@ -317,7 +355,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         }
-        if (i == n_my - 1) release_accumulator(as);  // last TMEM read of the tile: the MMA warp may start tile it+2
+        if (i == n_my - 1) release_accumulator(as);  // last TMEM read of the tile: the MMA warp may reuse the buffer
         if (bias) {
           const float* bp = bias + n0;
 #pragma unroll
@@ -329,17 +367,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         uint8_t* st0 = slot_ptr(use);
-        if (has_aux) { mbar_wait(&abar[i], (aux_phase >> i) & 1u); aux_phase ^= (1u << i); } else acquire_slot();
-        switch (epi) {
-          case MFV_EPI_BF16: {
+        if constexpr (has_aux) {
+          mbar_wait(&abar[i & 1], (aux_phase >> (i & 1)) & 1u);
+          aux_phase ^= 1u << (i & 1);
+        } else {
+          acquire_slot();
+        }
+        if constexpr (epi == MFV_EPI_BF16) {
+          {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
                   make_uint4(pack16(f[8 * j], f[8 * j + 1]), pack16(f[8 * j + 2], f[8 * j + 3]),
                              pack16(f[8 * j + 4], f[8 * j + 5]), pack16(f[8 * j + 6], f[8 * j + 7]));
             publish(&tmC, st0, n0, row0, g, false);
-          } break;
-          case MFV_EPI_GELU: {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = optional bf16 copy of C2
+          }
+        } else if constexpr (epi == MFV_EPI_GELU) {
+          {  // C = u (bf16, saved for backward), C2 = gelu(u) (fp16|bf16), C3 = optional bf16 copy of C2
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(st0 + stage_off(lane, j)) =
@@ -366,8 +410,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
               publish(&tmC3, st2, n0, row0, g, false);
             }
-          } break;
-          case MFV_EPI_RESID_F32: {  // C(fp32) = acc + bias + aux(fp32 residual stream), computed in place
+          }
+        } else if constexpr (epi == MFV_EPI_RESID_F32) {
+          {  // C(fp32) = acc + bias + aux(fp32 residual stream), computed in place
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4* pp = reinterpret_cast<float4*>(st0 + stage_off(lane, j));
@@ -375,8 +420,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *pp = make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
             }
             publish(&tmC, st0, n0, row0, g, false);
-          } break;
-          case MFV_EPI_DGELU: {  // C(bf16) = acc * gelu'(u) in place over u = aux (bf16); C2 (optional) = gelu(u) bf16
+            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
+          }
+        } else if constexpr (epi == MFV_EPI_DGELU) {
+          {  // C(bf16) = acc * gelu'(u) in place over u = aux (bf16); C2 (optional) = gelu(u) bf16
             uint32_t gk[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -396,6 +443,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *pp = make_uint4(o[0], o[1], o[2], o[3]);
             }
             publish(&tmC, st0, n0, row0, g, false);
+            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
             if (p.has_c2) {
               uint8_t* st1 = slot_ptr(use);
               acquire_slot();
@@ -405,14 +453,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     make_uint4(gk[4 * j], gk[4 * j + 1], gk[4 * j + 2], gk[4 * j + 3]);
               publish(&tmC2, st1, n0, row0, g, false);
             }
-          } break;
-          default: {  // MFV_EPI_F32 / MFV_EPI_ATOMIC_F32: raw fp32 tile
+          }
+        } else {
+          {  // MFV_EPI_F32 (also serves MFV_EPI_ATOMIC_F32: p.epi selects the reduce-add store): raw fp32 tile
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
                   make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            publish(&tmC, st0, n0, row0, g, epi == MFV_EPI_ATOMIC_F32);
-          } break;
+            publish(&tmC, st0, n0, row0, g, p.epi == MFV_EPI_ATOMIC_F32);
+          }
         }
       }
     }
@@ -472,12 +521,13 @@ static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, i
   return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
 }
 
-template <int BN, int CG>
-static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
+template <int BN, int CG, int EPI>
+static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        S::TOTAL));
     attr_set = true;
   }
   GemmParams p;
@@ -502,7 +552,8 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
   int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);
   if (rc) return rc;
-  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN / CG, p.b_f16);
+  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN == 384 ? 64 : BN / CG,
+                          p.b_f16);
   if (rc) return rc;
   const int e = a->epilogue;
   const bool c32 = (e == MFV_EPI_RESID_F32 || e == MFV_EPI_F32 || e == MFV_EPI_ATOMIC_F32);
@@ -550,9 +601,22 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
+  MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, EPI>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
   MFV_LAUNCH_CHECK();
   return MFV_OK;
+}
+
+template <int BN, int CG>
+static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
+  switch (a->epilogue) {
+    case MFV_EPI_BF16: return launch_gemm_epi<BN, CG, MFV_EPI_BF16>(a, stream);
+    case MFV_EPI_GELU: return launch_gemm_epi<BN, CG, MFV_EPI_GELU>(a, stream);
+    case MFV_EPI_RESID_F32: return launch_gemm_epi<BN, CG, MFV_EPI_RESID_F32>(a, stream);
+    case MFV_EPI_DGELU: return launch_gemm_epi<BN, CG, MFV_EPI_DGELU>(a, stream);
+    case MFV_EPI_F32:
+    case MFV_EPI_ATOMIC_F32: return launch_gemm_epi<BN, CG, MFV_EPI_F32>(a, stream);
+    default: return MFV_ERR_ARG;
+  }
 }
 
 }  // namespace mfv
@@ -565,21 +629,27 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
   if ((a->epilogue == MFV_EPI_RESID_F32 || a->epilogue == MFV_EPI_DGELU) && !a->aux) return MFV_ERR_ARG;
   if (a->epilogue == MFV_EPI_GELU && !a->C2) return MFV_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // Tile selection (0 = auto).  These GEMMs are L2->SM bandwidth bound, so the widest tile that fits wins: CTA pairs
+  // (256 rows) whenever M allows, 384 columns when N is exactly 384 (A read once), else 256 columns for N >= 512.
   int bn = a->block_n;
-  if (bn == 0) {
-    // pick the widest tile that still gives at least ~2 waves of CTAs; N=384 prefers 128 (3 exact tiles)
-    const long long tm = (a->M + BM - 1) / BM;
-    const long long sp = a->splits > 0 ? a->splits : 1;
-    bn = 128;
-    if (tm * ((a->N + 127) / 128) * a->G * sp < num_sms() && a->N % 64 == 0) bn = 64;
-  }
-  // the fused aux epilogues prefetch at most 4 chunks per tile: fp32 residual -> BN <= 128, bf16 u -> BN <= 256
-  if (a->epilogue == MFV_EPI_RESID_F32 && bn > 128) bn = 128;
-  // cta_group: 0 = auto.  Pairs (256-row tiles) whenever there are enough rows to fill the machine with pairs
   int cg = a->cta_group;
-  if (cg == 0) cg = (a->M >= 256) ? 2 : 1;
+  const bool pair_ok = a->M > 128 && cg != 1;
+  if (bn == 0) {
+    if (a->N == 384 && pair_ok && a->epilogue != MFV_EPI_GELU) bn = 384;
+    else if (a->N >= 512 && pair_ok) bn = 256;
+    else {
+      const long long tm = (a->M + BM - 1) / BM;
+      const long long sp = a->splits > 0 ? a->splits : 1;
+      bn = 128;
+      if (tm * ((a->N + 127) / 128) * a->G * sp < num_sms() && a->N % 64 == 0) bn = 64;
+    }
+  }
+  if (cg == 0) cg = pair_ok ? 2 : 1;
+  if (bn == 384) {
+    if (cg != 2 || a->N % 384 != 0) return MFV_ERR_ARG;
+    return launch_gemm<384, 2>(a, s);
+  }
   if (cg == 2) {
-    if (a->epilogue == MFV_EPI_RESID_F32 && bn > 128) bn = 128;
     switch (bn) {
       case 128: return launch_gemm<128, 2>(a, s);
       case 256: return launch_gemm<256, 2>(a, s);

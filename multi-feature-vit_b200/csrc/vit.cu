@@ -97,12 +97,15 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
   a.a_gstride = rows * N; a.b_gstride = rows * K; a.c_gstride = v.p->P;
   a.a_mn_major = 1; a.b_mn_major = 1;
   a.epilogue = MFV_EPI_ATOMIC_F32;
-  a.block_n = 128;
+  // tile = what mfv_gemm's auto selection will pick: 256 x 384 pair tiles when the input width is 384 (qkv / fc1 /
+  // proj), else 256 x 256 (fc2: 384 x 1536 output)
+  const long long bn = (K == 384) ? 384 : (K >= 512 ? 256 : 128);
+  const long long bm = (N > 128) ? 256 : 128;
   // split-K: choose the split count whose tile count fills whole waves of the persistent grid best, while keeping
   // at least 8 k-blocks (512 tokens) per split so the fp32 reduce-add traffic stays small against the mainloop
-  const long long tiles = ((N + 127) / 128) * ((K + 127) / 128) * v.p->G;
+  const long long tiles = ((N + bm - 1) / bm) * ((K + bn - 1) / bn) * v.p->G;
   const long long kb = (rows + 63) / 64;
-  const long long sms = num_sms();
+  const long long sms = num_sms() / (bm == 256 ? 2 : 1);  // schedulable units: CTA pairs or single CTAs
   long long splits = 1;
   double best = -1.0;
   for (long long sp = 1; sp <= 32 && sp <= kb; ++sp) {

@@ -68,7 +68,7 @@ def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, ct
                 cta_group=cta_group, C2=out2)
 
 
-def linear_wgrad(dy16, x16, dw, splits=8, block_n=128, cta_group=0):
+def linear_wgrad(dy16, x16, dw, splits=8, block_n=0, cta_group=0):
     """dw [G,N,K] f32 += dy16[G,M,N]^T x16[G,M,K]."""
     G, M, N = dy16.shape
     K = x16.shape[2]

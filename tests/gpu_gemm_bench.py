@@ -62,27 +62,23 @@ print(torch.cuda.get_device_name(0))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 M = B * 197
 fwd(1, 8192, 8192, 8192, 256)
-for bn in (128, 256):
-    fwd(2, M, 1152, 384, bn, tag="qkv ")
-    fwd(2, M, 1536, 384, bn, EPI_GELU, tag="fc1 ")
-for bn in (64, 128):
-    for cg in (1, 2):
-        if bn == 64 and cg == 2:
-            continue
-        fwd(2, M, 384, 384, bn, EPI_RESID_F32, cg, tag="proj")
-        fwd(2, M, 384, 1536, bn, EPI_RESID_F32, cg, tag="fc2 ")
-for bn in (128, 256):
-    dgrad(2, M, 384, 1536, bn, EPI_DGELU, out2=True)   # fc2 dgrad
-    dgrad(2, M, 384, 1536, bn, EPI_DGELU)
-for bn in (64, 128):
+fwd(2, M, 1152, 384, 256, tag="qkv ")
+fwd(2, M, 1536, 384, 256, EPI_GELU, tag="fc1 ")
+for bn, cg in ((128, 1), (128, 2), (384, 2)):
+    fwd(2, M, 384, 384, bn, EPI_RESID_F32, cg, tag="proj")
+    fwd(2, M, 384, 1536, bn, EPI_RESID_F32, cg, tag="fc2 ")
+dgrad(2, M, 384, 1536, 256, EPI_DGELU, out2=True)   # fc2 dgrad
+for bn in (128, 384):
     dgrad(2, M, 1536, 384, bn)   # fc1 dgrad
     dgrad(2, M, 1152, 384, bn)   # qkv dgrad
     dgrad(2, M, 384, 384, bn)    # proj dgrad
-for s in (2, 4, 8):
+for s in (4, 7):
     wgrad(2, M, 1152, 384, s)
-wgrad(2, M, 1536, 384, 4); wgrad(2, M, 384, 1536, 4); wgrad(2, M, 384, 384, 16)
-for cg in (1, 2):
-    wgrad(2, M, 1536, 384, 4, cg); wgrad(2, M, 384, 1536, 4, cg)
+for s in (4, 6):
+    wgrad(2, M, 1536, 384, s)
+for s in (3, 4, 6):
+    wgrad(2, M, 384, 1536, s)
+wgrad(2, M, 384, 384, 16); wgrad(2, M, 384, 384, 8)
 # reference point: cuBLAS through torch on the same shapes
 for (m, n, k) in ((8192, 8192, 8192), (2 * M, 1536, 384), (2 * M, 1152, 384), (2 * M, 384, 1536), (2 * M, 384, 384)):
     a = torch.randn(m, k, device=dev).bfloat16(); b = torch.randn(n, k, device=dev).bfloat16()

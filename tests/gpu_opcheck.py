@@ -334,10 +334,14 @@ def main():
     run("gemm_fwd qkv", t_gemm_fwd(2, 6304, 1152, 384), flt)
     run("gemm_fwd qkv bn256", t_gemm_fwd(2, 6304, 1536, 384, 256), flt)
     run("gemm_fwd ragged", t_gemm_fwd(2, 197 * 3, 384, 1536, 128), flt)
+    run("gemm_fwd wide384", t_gemm_fwd(2, 6304, 384, 1536, 384), flt)
+    run("gemm_fwd wide384 ragged", t_gemm_fwd(2, 197 * 3, 384, 384, 384), flt)
+    run("gemm_fwd N768 bn384", t_gemm_fwd(1, 1000, 768, 128, 384), flt)
     run("gemm epilogues", t_gemm_epilogues, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
     run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
     run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)
+    run("gemm wgrad fc1", t_gemm_wgrad(2, 6304, 1536, 384, 6), flt)
     run("layernorm", t_ln, flt)
     run("attn 197/64", t_attn(4, 197, 6, 64), flt)
     run("attn 577/64", t_attn(2, 577, 6, 64), flt)
