@@ -1,0 +1,663 @@
+// Fused softmax self-attention on tcgen05 / TMEM for the 224^2 ViT-S/16 shape (S = 197 tokens, head_dim 64; any
+// S <= 256).  Replaces timm Attention: q @ k^T * scale -> softmax -> @ v (same math MOD:52-64).
+//
+// One CTA = one (image, head).  Q (<= 2 tiles of 128 rows), K and V of the head are brought in by TMA straight out of
+// the qkv GEMM's output layout [NB][S][3][H][64] (3-D tensor map: column, token, image - tokens past S zero-fill).
+// Per 128-query tile:
+//   S  = Q K^T          one accumulator of NK = ceil16(S) fp32 columns in TMEM (4 UMMAs 128 x NK x 16)
+//   P  = softmax(S)     4 warps, thread = query row: two passes over the row in TMEM (max; exp2 + sum); P is written
+//                       back over S as packed 16-bit (tcgen05.st) - scores never leave the SM
+//   O  = P V            A operand = P from TMEM, B = V tile read MN-major (NK/16 UMMAs 128 x 64 x 16)
+//   epilogue            O / rowsum -> 16-bit -> swizzled smem (the spent Q tile) -> TMA store (rows past S clipped)
+// 256 TMEM columns and ~100 KB of smem per CTA: two CTAs per SM overlap each other's load / MMA / softmax phases.
+#include "common.cuh"
+#include "mfvit_internal.h"
+
+namespace mfv {
+
+constexpr int FA_THREADS = 160;  // warps 0..3: softmax + epilogue (TMEM lane quarter = warp), warp 4: TMA + MMA issue
+constexpr uint32_t FA_TMEM_COLS = 256;
+constexpr uint32_t FA_O_COL = 128;  // O accumulator columns [128, 192): past P (<= 128 columns), inside the spent S
+constexpr float FA_LOG2E = 1.4426950408889634f;
+constexpr float FA_LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void fb_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fa_tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                   float* __restrict__ lse, int S, int H, int NK, float scale_log2, int has_o2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                  // 2 tiles x [128][64] 16-bit, 128B-swizzled; tile mt is reused as O staging
+  uint8_t* sK = sQ + 32768;            // [NK][64]
+  uint8_t* sV = sK + NK * 128;         // [NK][64]
+  uint8_t* sO2 = sV + NK * 128;        // 16 KB staging of the optional bf16 copy of O
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO2 + 16384);
+  uint64_t* bar_qk = bars;             // Q + K landed
+  uint64_t* bar_v = bars + 1;          // V landed
+  uint64_t* bar_s = bars + 2;          // S accumulator complete
+  uint64_t* bar_p = bars + 3;          // P written to TMEM (4 warp arrivals)
+  uint64_t* bar_o = bars + 4;          // O accumulator complete
+  uint64_t* bar_free = bars + 5;       // O read out: TMEM may be overwritten by the next tile (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh % H;
+  const int n_mt = (S + 127) >> 7;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmO);
+      mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+      mbar_init(bar_free, 4);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      griddep_wait();
+      mbar_arrive_expect_tx(bar_qk, (uint32_t)(n_mt * 16384 + NK * 128));
+      for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(sQ + mt * 16384, &tmQ, bar_qk, h * 64, mt * 128, b);
+      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * 64, 0, b);
+      mbar_arrive_expect_tx(bar_v, (uint32_t)(NK * 128));
+      tma_load_3d(sV, &tmKV, bar_v, (2 * H + h) * 64, 0, b);
+      const uint32_t fmt = F16 ? 0u : 1u;
+      const uint32_t idesc_s = make_idesc2(fmt, fmt, 128, (uint32_t)NK, 0, 0);
+      const uint32_t idesc_o = make_idesc2(fmt, fmt, 128, 64, 0, 1);
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      for (int mt = 0; mt < n_mt; ++mt) {
+        if (mt > 0) {
+          mbar_wait(bar_free, (uint32_t)((mt - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t qa = smem_u32(sQ + mt * 16384), ka = smem_u32(sK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, make_smem_desc_sw128(qa + k * 32, 0u, 1024u), make_smem_desc_sw128(ka + k * 32, 0u, 1024u),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, (uint32_t)(mt & 1));
+        tc_fence_after();
+        if (mt == 0) {
+          mbar_wait(bar_v, 0);
+          tc_fence_after();
+        }
+        const uint32_t va = smem_u32(sV);
+        for (int k = 0; k < NK / 16; ++k)
+          umma_f16_ts(tmem_base + FA_O_COL, tmem_base + (uint32_t)(k * 8),
+                      make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    griddep_wait();
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int mt = 0; mt < n_mt; ++mt) {
+      const uint32_t ph = (uint32_t)(mt & 1);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      // ---- pass 1: row maximum (columns >= S are padding)
+      float mx = -INFINITY;
+      for (int c0 = 0; c0 < NK; c0 += 32) {
+        uint32_t v[32];
+        const bool full = c0 + 32 <= NK;
+        if (full) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= S) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c0 + k < S && (full || k < 16)) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+      }
+      const float mc = mx * scale_log2;
+      // ---- pass 2: p = exp2(s * c - max * c), row sum, packed 16-bit P written back over S
+      float sum = 0.f;
+      for (int c0 = 0; c0 < NK; c0 += 32) {
+        uint32_t v[32];
+        const bool full = c0 + 32 <= NK;
+        if (full) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float pr[32];
+        if (c0 + 32 <= S) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) pr[k] = fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            pr[k] = (c0 + k < S && (full || k < 16)) ? fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc)) : 0.f;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          sum += pr[2 * k] + pr[2 * k + 1];
+          pk[k] = F16 ? pack_f16(pr[2 * k], pr[2 * k + 1]) : pack_bf16(pr[2 * k], pr[2 * k + 1]);
+        }
+        if (full) tmem_st16(trow + (uint32_t)(c0 >> 1), pk); else tmem_st8(trow + (uint32_t)(c0 >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      const int row = mt * 128 + warp * 32 + lane;
+      if (row < S) lse[(long long)bh * S + row] = (mc + log2f(sum)) * FA_LN2;
+      const float inv = 1.f / sum;
+      // ---- epilogue: O / sum -> 16-bit -> swizzled smem -> TMA store
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      float o[64];
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(trow + FA_O_COL, v0);
+        tmem_ld32(trow + FA_O_COL + 32u, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { o[k] = __uint_as_float(v0[k]) * inv; o[32 + k] = __uint_as_float(v1[k]) * inv; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+      if (mt * 128 + warp * 32 < S) {  // warp-uniform: slices fully past S store nothing
+        uint8_t* st = sQ + mt * 16384 + warp * 4096;  // this tile's Q rows are spent (S MMA complete)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 w;
+          if (F16)
+            w = make_uint4(pack_f16(o[8 * j], o[8 * j + 1]), pack_f16(o[8 * j + 2], o[8 * j + 3]),
+                           pack_f16(o[8 * j + 4], o[8 * j + 5]), pack_f16(o[8 * j + 6], o[8 * j + 7]));
+          else
+            w = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                           pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+          *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = w;
+        }
+        uint8_t* st2 = sO2 + warp * 4096;
+        if (has_o2) {
+          if (mt > 0) {  // the previous tile's copy store must have finished reading the staging buffer
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(st2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                           pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          fa_tma_store_3d(&tmO, st, h * 64, mt * 128 + warp * 32, b);
+          if (has_o2) fa_tma_store_3d(&tmO2, st2, h * 64, mt * 128 + warp * 32, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+
+// =====================================================================================================================
+// Backward.  One CTA = one (image, head); bf16 operands (fp16 q/k/v of the fp16-forward mode are converted in place in
+// shared memory), fp32 accumulation in TMEM.  With q-tiles i and key-blocks j of 128 (S <= 224 -> 2 x 2 steps):
+//   S_ij  = Q_i K_j^T            dP_ij = dO_i V_j^T                       (TMEM columns   0..127 / 128..255)
+//   P = exp2(S c - lse)          dS = P (dP - delta) scale                16 warps: thread = (row, 32-column segment);
+//                                                                         no row reductions are needed in the backward
+//   P, dS -> bf16 -> one swizzled smem tile each, read both K-major (dQ) and MN-major (dK, dV: the transposed use)
+//   dV_j += P^T dO_i             dK_j += dS^T Q_i       dQ_i += dS K_j    (TMEM 448..511 / 384..447 / 256..383)
+// The MMA warp runs one step ahead: S / dP of step n+1 are issued as soon as the compute warps have read step n out of
+// TMEM, so the tensor pipe works while P / dS of step n are being formed.  delta = rowsum(dO * O) is computed in the
+// prologue.  Gradients leave through 64B-swizzled staging + TMA stores straight into dqkv [NB][S][3][H][64].
+constexpr int FB_CWARPS = 16;
+constexpr int FB_THREADS = 32 * (FB_CWARPS + 1);
+constexpr uint32_t FB_S_COL = 0, FB_DP_COL = 128, FB_DQ_COL = 256, FB_DK_COL = 384, FB_DV_COL = 448;
+
+template <bool QKV_F16>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmG, const __nv_bfloat16* __restrict__ o,
+                   const float* __restrict__ lse, int S, int H, int NK, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int TILE = NK * 128;           // [NK][64] bf16, 128B-swizzled (multiple of 2 KB)
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + TILE;
+  uint8_t* sK = sdO + TILE;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sP = sV + TILE;             // [2 key halves of 64][128 q][128 B]
+  uint8_t* sdS = sP + 32768;
+  uint8_t* sStage = sdS + 32768;       // 16 warps x 2 KB
+  float* sDelta = reinterpret_cast<float*>(sStage + FB_CWARPS * 2048);
+  float* sLse = sDelta + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLse + 256);
+  uint64_t* bar_ld = bars;             // [2]: Q,K | V,dO landed
+  uint64_t* bar_conv = bars + 2;       // operands converted / ready (16 warp arrivals)
+  uint64_t* bar_sdp = bars + 3;        // S, dP accumulators complete
+  uint64_t* bar_sdp_free = bars + 4;   // S, dP read out of TMEM (16)
+  uint64_t* bar_pds = bars + 5;        // P, dS tiles written (16)
+  uint64_t* bar_mma = bars + 6;        // dV, dK, dQ MMAs of the step complete (P / dS tiles free, accumulators valid)
+  uint64_t* bar_acc_free = bars + 7;   // dK_j, dV_j read out (16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh % H;
+  const int n_t = (S + 127) >> 7;      // q-tiles == key-blocks
+  const int n_steps = n_t * n_t;
+  auto rows_of = [&](int t) { return min(128, S - 128 * t); };
+  auto r16 = [](int x) { return (x + 15) & ~15; };
+
+  if (warp == FB_CWARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmG);
+      mbar_init(&bar_ld[0], 1); mbar_init(&bar_ld[1], 1);
+      mbar_init(bar_conv, FB_CWARPS); mbar_init(bar_sdp, 1); mbar_init(bar_sdp_free, FB_CWARPS);
+      mbar_init(bar_pds, FB_CWARPS); mbar_init(bar_mma, 1); mbar_init(bar_acc_free, FB_CWARPS);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+
+  if (warp == FB_CWARPS) {
+    // ------------------------------------------------------------------------------------------ TMA + MMA issue
+    if (lane == 0) {
+      griddep_wait();
+      mbar_arrive_expect_tx(&bar_ld[0], (uint32_t)(2 * TILE));
+      tma_load_3d(sQ, &tmQKV, &bar_ld[0], h * 64, 0, b);
+      tma_load_3d(sK, &tmQKV, &bar_ld[0], (H + h) * 64, 0, b);
+      mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(2 * TILE));
+      tma_load_3d(sV, &tmQKV, &bar_ld[1], (2 * H + h) * 64, 0, b);
+      tma_load_3d(sdO, &tmDO, &bar_ld[1], h * 64, 0, b);
+      mbar_wait(bar_conv, 0);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+      const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+      auto issue_sdp = [&](int n) {
+        const int j = n / n_t, i = n % n_t;
+        const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FB_S_COL, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 0u, 1024u),
+                    make_smem_desc_sw128(aK + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc_sw128(adO + i * 16384 + k * 32, 0u, 1024u),
+                    make_smem_desc_sw128(aV + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
+      };
+      issue_sdp(0);
+      const uint32_t idesc_t = make_idesc2(1u, 1u, 128, 64, 1, 1);  // A = P / dS read MN-major (transposed use)
+      const uint32_t idesc_q = make_idesc2(1u, 1u, 128, 64, 0, 1);  // A = dS K-major
+      for (int n = 0; n < n_steps; ++n) {
+        const int j = n / n_t, i = n % n_t;
+        if (n + 1 < n_steps) {
+          mbar_wait(bar_sdp_free, (uint32_t)(n & 1));
+          tc_fence_after();
+          issue_sdp(n + 1);
+        }
+        mbar_wait(bar_pds, (uint32_t)(n & 1));
+        tc_fence_after();
+        if (i == 0 && j > 0) {
+          mbar_wait(bar_acc_free, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+        }
+        const int kq = r16(rows_of(i)) / 16;  // reduction over the q rows of tile i
+        for (int k = 0; k < kq; ++k) {
+          const uint64_t da_p = make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u);
+          const uint64_t da_s = make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u);
+          const uint64_t db_do = make_smem_desc_sw128(adO + i * 16384 + k * 2048, 8192u, 1024u);
+          const uint64_t db_q = make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192u, 1024u);
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          umma_bf16(tmem_base + FB_DV_COL, da_p, db_do, idesc_t, acc);
+          umma_bf16(tmem_base + FB_DK_COL, da_s, db_q, idesc_t, acc);
+        }
+        const int kk = r16(rows_of(j)) / 16;  // reduction over the keys of block j
+        for (int k = 0; k < kk; ++k) {
+          const uint64_t da = make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u);
+          const uint64_t db = make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192u, 1024u);
+          umma_bf16(tmem_base + FB_DQ_COL + (uint32_t)(i * 64), da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_mma);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ compute warps
+    griddep_wait();
+    const int tid = threadIdx.x;  // 0..511
+    const int q = warp & 3;       // TMEM lane quarter
+    const int cseg = warp >> 2;   // 32-column segment
+    mbar_wait(&bar_ld[0], 0);
+    mbar_wait(&bar_ld[1], 0);
+    if (QKV_F16) {  // fp16 -> bf16 in place (element-wise, so the swizzle is irrelevant); Q, K, V tiles
+      for (int t = 0; t < 3; ++t) {
+        uint8_t* base = (t == 0) ? sQ : (t == 1 ? sK : sV);
+        for (int c = tid; c < TILE / 16; c += FB_CWARPS * 32) {
+          uint4* pp = reinterpret_cast<uint4*>(base + c * 16);
+          uint4 w = *pp;
+          uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = unpack_f16(ww[e]);
+            ww[e] = pack_bf16(f2.x, f2.y);
+          }
+          *pp = w;
+        }
+      }
+    }
+    {  // delta = rowsum(dO * O), lse in the log2 domain (+inf for padded rows -> P = dS = 0 there)
+      const int row = tid >> 1, half = tid & 1;
+      float acc = 0.f;
+      if (row < S) {
+        const uint4* og = reinterpret_cast<const uint4*>(o + (((long long)b * S + row) * H + h) * 64 + half * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 ov = __ldg(og + c);
+          const uint4 dv = *reinterpret_cast<const uint4*>(sdO + row * 128 + (((half * 4 + c) ^ (row & 7)) << 4));
+          const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ov);
+          const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf16(ow[e]), d = unpack_bf16(dw[e]);
+            acc = fmaf(a.x, d.x, acc);
+            acc = fmaf(a.y, d.y, acc);
+          }
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (half == 0) {
+        sDelta[row] = acc;
+        sLse[row] = (row < S) ? lse[(long long)bh * S + row] * FA_LOG2E : INFINITY;
+      }
+    }
+    fence_proxy_async_smem();  // converted operands -> visible to the tensor core (async proxy)
+    asm volatile("bar.sync 1, %0;" ::"n"(FB_CWARPS * 32) : "memory");
+    if (lane == 0) mbar_arrive(bar_conv);
+
+    const float scale_log2 = scale * FA_LOG2E;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* stg = sStage + warp * 2048;
+    auto stage_store = [&](const float (&f)[32], int which, int colseg, int row0) {
+      // 32 rows x 32 bf16 columns -> 64B-swizzled staging -> TMA store into dqkv[.., which, h, colseg*32 ..]
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
+                       pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        fa_tma_store_3d(&tmG, stg, (which * H + h) * 64 + colseg * 32, row0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    for (int n = 0; n < n_steps; ++n) {
+      const int j = n / n_t, i = n % n_t;
+      const int qrows = rows_of(i), nk = r16(rows_of(j));
+      const bool active = (q * 32 < qrows) && (cseg * 32 < nk);
+      const int r = q * 32 + lane;
+      mbar_wait(bar_sdp, (uint32_t)(n & 1));
+      tc_fence_after();
+      uint32_t pk[16], dk[16];
+      if (active) {
+        const float l2 = sLse[i * 128 + r], dl = sDelta[i * 128 + r];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves keep the live register set small
+          uint32_t sv[16], dv[16];
+          fb_tmem_ld16(tlane + FB_S_COL + (uint32_t)(cseg * 32 + hh * 16), sv);
+          fb_tmem_ld16(tlane + FB_DP_COL + (uint32_t)(cseg * 32 + hh * 16), dv);
+          tmem_ld_wait();
+          const int key0 = j * 128 + cseg * 32 + hh * 16;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), scale_log2, -l2));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), scale_log2, -l2));
+            if (key0 + 2 * e >= S) p0 = 0.f;
+            if (key0 + 2 * e + 1 >= S) p1 = 0.f;
+            const float d0 = p0 * (__uint_as_float(dv[2 * e]) - dl) * scale;
+            const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dl) * scale;
+            pk[hh * 8 + e] = pack_bf16(p0, p1);
+            dk[hh * 8 + e] = pack_bf16(d0, d1);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sdp_free);
+      if (n > 0) mbar_wait(bar_mma, (uint32_t)((n - 1) & 1));  // the previous step's MMAs have finished reading P / dS
+      if (active) {
+        const uint32_t off = (uint32_t)((cseg >> 1) * 16384 + r * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t sw = off + ((((cseg & 1) * 4 + c) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4*>(sdS + sw) = make_uint4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pds);
+      if (i == n_t - 1) {  // dK_j, dV_j are complete once this step's MMAs retire
+        mbar_wait(bar_mma, (uint32_t)(n & 1));
+        tc_fence_after();
+        const bool rows_ok = q * 32 < rows_of(j);  // lanes = keys of block j
+        float f[32];
+        if (rows_ok) {
+          uint32_t v[32];
+          tmem_ld32(tlane + (cseg < 2 ? FB_DK_COL : FB_DV_COL) + (uint32_t)((cseg & 1) * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_free);
+        if (rows_ok) stage_store(f, cseg < 2 ? 1 : 2, cseg & 1, j * 128 + q * 32);
+      }
+    }
+    {  // dQ: tile = cseg >> 1 (lanes = its queries), columns (cseg & 1) * 32
+      const int i = cseg >> 1;
+      if (i < n_t && q * 32 < rows_of(i)) {
+        uint32_t v[32];
+        float f[32];
+        tc_fence_after();
+        tmem_ld32(tlane + FB_DQ_COL + (uint32_t)(i * 64 + (cseg & 1) * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+        stage_store(f, 0, cseg & 1, i * 128 + q * 32);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FB_CWARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int fa_encode(CUtensorMap* map, const void* base, int is_f16, long long inner, long long rows, long long images,
+                     int box_rows, int box_cols = 64) {
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)images};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 2, (cuuint64_t)(inner * rows) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) return MFV_ERR_ALIGN;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MFV_ERR_INIT;
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MFV_OK : MFV_ERR_ARG;
+}
+
+// Host entry used by mfv_attn_fwd (attn.cu) for D == 64 and S <= 256.
+int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
+                long long S, long long H, float scale, cudaStream_t st) {
+  if (o_is_f16 != qkv_is_f16) return MFV_ERR_ARG;  // P / O follow the operand format
+  const int NK = ((int)S + 15) & ~15;
+  CUtensorMap tmQ, tmKV, tmO, tmO2;
+  int rc;
+  if ((rc = fa_encode(&tmQ, qkv, qkv_is_f16, 3 * H * 64, S, NB, 128))) return rc;
+  if ((rc = fa_encode(&tmKV, qkv, qkv_is_f16, 3 * H * 64, S, NB, NK))) return rc;
+  if ((rc = fa_encode(&tmO, o, o_is_f16, H * 64, S, NB, 32))) return rc;
+  tmO2 = tmO;
+  if (o_bf16_copy && (rc = fa_encode(&tmO2, o_bf16_copy, 0, H * 64, S, NB, 32))) return rc;
+  const size_t smem = 1024 + 32768 + 2 * (size_t)NK * 128 + 16384 + 64;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(NB * H));
+  cfg.blockDim = dim3(FA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const float sl2 = scale * FA_LOG2E;
+  const int has_o2 = o_bf16_copy != nullptr;
+  if (qkv_is_f16) {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<true>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, NK, sl2,
+                                      has_o2));
+  } else {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<false>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, NK, sl2,
+                                      has_o2));
+  }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+// Host entry used by mfv_attn_bwd (attn.cu) for D == 64 and S <= 224.  o and d_o are bf16.
+int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, void* dqkv,
+                long long NB, long long S, long long H, float scale, cudaStream_t st) {
+  const int NK = ((int)S + 15) & ~15;
+  CUtensorMap tmQKV, tmDO, tmG;
+  int rc;
+  if ((rc = fa_encode(&tmQKV, qkv, qkv_is_f16, 3 * H * 64, S, NB, NK))) return rc;
+  if ((rc = fa_encode(&tmDO, d_o, 0, H * 64, S, NB, NK))) return rc;
+  if ((rc = fa_encode(&tmG, dqkv, 0, 3 * H * 64, S, NB, 32, 32))) return rc;
+  const size_t smem = 1024 + 4 * (size_t)NK * 128 + 65536 + FB_CWARPS * 2048 + 2048 + 128;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(NB * H));
+  cfg.blockDim = dim3(FB_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const __nv_bfloat16* op = reinterpret_cast<const __nv_bfloat16*>(o);
+  if (qkv_is_f16) {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<true>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale));
+  } else {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<false>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale));
+  }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+}  // namespace mfv

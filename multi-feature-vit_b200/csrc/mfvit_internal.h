@@ -10,7 +10,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
-bool pdl_enabled();  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
+bool pdl_enabled();
+bool legacy_attention();  // MFVIT_ATTN=legacy forces the mma.sync attention kernels (A/B measurements)
+// tcgen05 attention (attn_tc.cu); head_dim 64, S <= 256
+int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
+                long long S, long long H, float scale, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, void* dqkv,
+                long long NB, long long S, long long H, float scale, cudaStream_t st);  // S <= 224  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
 
 // Optional per-kernel-class device timing of the encoder executor (CUDA events on the launching stream).
 enum ProfLabel {

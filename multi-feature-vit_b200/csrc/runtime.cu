@@ -38,6 +38,14 @@ static int g_device = -1;
 
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+bool legacy_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFVIT_ATTN");
+    v = (e && e[0] == 'l') ? 1 : 0;
+  }
+  return v == 1;
+}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

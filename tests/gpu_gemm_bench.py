@@ -18,12 +18,15 @@ def timeit(fn, reps=20):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(reps): fn()
-    g.replay(); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    g.replay()
-    b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
+    g.replay(); g.replay(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):  # min of 5 graph replays: the box-to-box / clock-ramp noise is +-30 % on single replays
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) / reps)
+    return best
 
 
 def fwd(G, M, N, K, bn=0, epi=EPI_BF16, cg=0, tag="fwd "):
