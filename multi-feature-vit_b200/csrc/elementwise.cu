@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int C,
                    long long out_gstride) {
   __shared__ float red[8][256 + 8];
+  griddep_wait();    // PDL launch: the producer of x may still be draining
+  griddep_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   const long long g = blockIdx.z;
@@ -374,8 +376,9 @@ extern "C" int mfv_colsum_bf16(const void* x, float* out, int64_t G, int64_t row
   long long gy = (2LL * num_sms()) / (gx * G);
   if (gy < 1) gy = 1;
   if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
-  colsum_bf16_kernel<<<dim3(gx, (unsigned)gy, (unsigned)G), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), out, rows, (int)C, out_gstride);
+  MFV_CUDA_CHECK(launch_pdl(colsum_bf16_kernel, dim3(gx, (unsigned)gy, (unsigned)G), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(x), out, (long long)rows, (int)C,
+                            (long long)out_gstride));
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }

@@ -14,6 +14,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
               float* __restrict__ y32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows_per_group, long long total_rows, long long gb_gstride, float eps) {
   constexpr int C = NV * 128;
+  griddep_wait();    // PDL launch: the producer of x may still be draining
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= total_rows) return;
@@ -70,6 +72,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
               long long rows_per_group, long long gb_gstride) {
   constexpr int C = NV * 128;
   __shared__ float red[LN_WARPS][C + 4];
+  griddep_wait();    // PDL launch: the producers of dy / dres may still be draining
+  griddep_launch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long g = blockIdx.y;
   const float4* gm = reinterpret_cast<const float4*>(gamma + g * gb_gstride);
@@ -156,9 +160,9 @@ extern "C" int mfv_layernorm_fwd(const float* x, const float* gamma, const float
   __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16v);
   __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y_bf16_copy);
   switch (C) {
-    case 256: ln_fwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
-    case 384: ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
-    case 768: ln_fwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps); break;
+    case 256: MFV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps)); break;
+    case 384: MFV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps)); break;
+    case 768: MFV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<6>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, gamma, beta, y16, y16_is_f16, y16b, y_f32, mean, rstd, rows, total, gb_gstride, eps)); break;
     default: return MFV_ERR_SHAPE;
   }
   MFV_LAUNCH_CHECK();
@@ -180,9 +184,9 @@ extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
   const __nv_bfloat16* dy16 = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   switch (C) {
-    case 256: ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
-    case 384: ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
-    case 768: ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride); break;
+    case 256: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<2>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+    case 384: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+    case 768: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<6>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
     default: return MFV_ERR_SHAPE;
   }
   MFV_LAUNCH_CHECK();

@@ -18,6 +18,24 @@ int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_
 int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, void* dqkv,
                 long long NB, long long S, long long H, float scale, cudaStream_t st);  // S <= 224  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
 
+// Launch with programmatic dependent launch (PDL) enabled: the kernel may start while its predecessor in the stream is
+// still draining, and MUST call griddep_wait() (common.cuh) before its first global memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Optional per-kernel-class device timing of the encoder executor (CUDA events on the launching stream).
 enum ProfLabel {
   PROF_PATCHIFY = 0, PROF_GEMM_FWD, PROF_LN_FWD, PROF_ATTN_FWD, PROF_EMBED, PROF_GEMM_DGRAD, PROF_GEMM_WGRAD,
