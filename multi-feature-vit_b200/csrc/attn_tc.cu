@@ -152,46 +152,78 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t ph = (uint32_t)(mt & 1);
       mbar_wait(bar_s, ph);
       tc_fence_after();
+      // Both passes stream the row out of TMEM in 32-column chunks with the next chunk's tcgen05.ld already in flight
+      // (two register buffers), so the TMEM read latency is paid once per pass instead of once per chunk.
+      const int nch = (NK + 31) >> 5;
+      auto ld_chunk = [&](int c, uint32_t (&v)[32]) {
+        if (c * 32 + 32 <= NK) tmem_ld32(trow + (uint32_t)(c * 32), v); else tmem_ld16(trow + (uint32_t)(c * 32), v);
+      };
       // ---- pass 1: row maximum (columns >= S are padding)
       float mx = -INFINITY;
-      for (int c0 = 0; c0 < NK; c0 += 32) {
-        uint32_t v[32];
-        const bool full = c0 + 32 <= NK;
-        if (full) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 <= S) {
+      {
+        uint32_t va[32], vb[32];
+        ld_chunk(0, va);
+        auto red = [&](int c, const uint32_t (&v)[32]) {
+          const int c0 = c * 32;
+          if (c0 + 32 <= S) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
-        } else {
+            for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+          } else {
+            const bool full = c0 + 32 <= NK;
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c0 + k < S && (full || k < 16)) mx = fmaxf(mx, __uint_as_float(v[k]));
+            for (int k = 0; k < 32; ++k)
+              if (c0 + k < S && (full || k < 16)) mx = fmaxf(mx, __uint_as_float(v[k]));
+          }
+        };
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) ld_chunk(c + 1, vb);
+          red(c, va);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) ld_chunk(c + 2, va);
+            red(c + 1, vb);
+          }
         }
       }
       const float mc = mx * scale_log2;
       // ---- pass 2: p = exp2(s * c - max * c), row sum, packed 16-bit P written back over S
       float sum = 0.f;
-      for (int c0 = 0; c0 < NK; c0 += 32) {
-        uint32_t v[32];
-        const bool full = c0 + 32 <= NK;
-        if (full) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
-        tmem_ld_wait();
-        float pr[32];
-        if (c0 + 32 <= S) {
+      {
+        uint32_t va[32], vb[32];
+        ld_chunk(0, va);
+        auto proc = [&](int c, const uint32_t (&v)[32]) {
+          const int c0 = c * 32;
+          const bool full = c0 + 32 <= NK;
+          float pr[32];
+          if (c0 + 32 <= S) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) pr[k] = fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc));
-        } else {
+            for (int k = 0; k < 32; ++k) pr[k] = fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc));
+          } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            pr[k] = (c0 + k < S && (full || k < 16)) ? fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc)) : 0.f;
+            for (int k = 0; k < 32; ++k)
+              pr[k] = (c0 + k < S && (full || k < 16)) ? fast_exp2(fmaf(__uint_as_float(v[k]), scale_log2, -mc)) : 0.f;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            sum += pr[2 * k] + pr[2 * k + 1];
+            pk[k] = F16 ? pack_f16(pr[2 * k], pr[2 * k + 1]) : pack_bf16(pr[2 * k], pr[2 * k + 1]);
+          }
+          // P chunk c lands in columns [16c, 16c+16): always below the S columns still to be read (>= 32(c+1)), and the
+          // chunk c+1 load in flight reads [32(c+1), 32(c+2)) - no overlap either
+          if (full) tmem_st16(trow + (uint32_t)(c0 >> 1), pk); else tmem_st8(trow + (uint32_t)(c0 >> 1), pk);
+        };
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) ld_chunk(c + 1, vb);
+          proc(c, va);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) ld_chunk(c + 2, va);
+            proc(c + 1, vb);
+          }
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          sum += pr[2 * k] + pr[2 * k + 1];
-          pk[k] = F16 ? pack_f16(pr[2 * k], pr[2 * k + 1]) : pack_bf16(pr[2 * k], pr[2 * k + 1]);
-        }
-        if (full) tmem_st16(trow + (uint32_t)(c0 >> 1), pk); else tmem_st8(trow + (uint32_t)(c0 >> 1), pk);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -397,6 +429,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const int tid = threadIdx.x;  // 0..511
     const int q = warp & 3;       // TMEM lane quarter
     const int cseg = warp >> 2;   // 32-column segment
+    // the O row of the delta prologue comes straight from global: issue those loads before waiting for the TMA tiles
+    const int drow = tid >> 1, dhalf = tid & 1;
+    uint4 ovec[4] = {};
+    float lse_row = INFINITY;
+    if (drow < S) {
+      const uint4* og = reinterpret_cast<const uint4*>(o + (((long long)b * S + drow) * H + h) * 64 + dhalf * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ovec[c] = __ldg(og + c);
+      lse_row = lse[(long long)bh * S + drow] * FA_LOG2E;
+    }
     mbar_wait(&bar_ld[0], 0);
     mbar_wait(&bar_ld[1], 0);
     if (QKV_F16) {  // fp16 -> bf16 in place (element-wise, so the swizzle is irrelevant); Q, K, V tiles
@@ -416,15 +458,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
     }
     {  // delta = rowsum(dO * O), lse in the log2 domain (+inf for padded rows -> P = dS = 0 there)
-      const int row = tid >> 1, half = tid & 1;
+      const int row = drow, half = dhalf;
       float acc = 0.f;
       if (row < S) {
-        const uint4* og = reinterpret_cast<const uint4*>(o + (((long long)b * S + row) * H + h) * 64 + half * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 ov = __ldg(og + c);
           const uint4 dv = *reinterpret_cast<const uint4*>(sdO + row * 128 + (((half * 4 + c) ^ (row & 7)) << 4));
-          const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ov);
+          const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ovec[c]);
           const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -437,7 +477,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       if (half == 0) {
         sDelta[row] = acc;
-        sLse[row] = (row < S) ? lse[(long long)bh * S + row] * FA_LOG2E : INFINITY;
+        sLse[row] = lse_row;
       }
     }
     fence_proxy_async_smem();  // converted operands -> visible to the tensor core (async proxy)

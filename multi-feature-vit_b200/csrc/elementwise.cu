@@ -95,12 +95,20 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < C) {
     const __nv_bfloat16* base = x + (g * rows) * C + col;
-    for (long long r = r0 + warp; r < r1; r += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(base + r * C);
+    auto add = [&](const uint4& v) {
       const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
       acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    };
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight per lane (the loop is latency-bound)
+      const uint4 v0 = *reinterpret_cast<const uint4*>(base + r * C);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(base + (r + 8) * C);
+      const uint4 v2 = *reinterpret_cast<const uint4*>(base + (r + 16) * C);
+      const uint4 v3 = *reinterpret_cast<const uint4*>(base + (r + 24) * C);
+      add(v0); add(v1); add(v2); add(v3);
     }
+    for (; r < r1; r += 8) add(*reinterpret_cast<const uint4*>(base + r * C));
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
@@ -373,7 +381,7 @@ extern "C" int mfv_colsum_bf16(const void* x, float* out, int64_t G, int64_t row
                                void* stream) {
   if (G <= 0 || rows <= 0 || C <= 0 || C % 8) return MFV_ERR_SHAPE;
   const unsigned gx = (unsigned)((C + 255) / 256);
-  long long gy = (2LL * num_sms()) / (gx * G);
+  long long gy = (4LL * num_sms()) / (gx * G);
   if (gy < 1) gy = 1;
   if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
   MFV_CUDA_CHECK(launch_pdl(colsum_bf16_kernel, dim3(gx, (unsigned)gy, (unsigned)G), dim3(256), 0, STREAM(stream),

@@ -11,6 +11,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
 bool pdl_enabled();
+// Side stream of mfv_vit_backward: weight-gradient GEMMs and bias column sums are off the critical path (nothing in
+// the backward consumes them), so they run beside the dgrad / attention / LayerNorm chain and fill the SMs those
+// kernels leave idle (dgrad grids are 100 CTAs on 148 SMs at 32 pairs).  MFVIT_SIDE_STREAM=0 serialises everything.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork[2];  // main -> side: inputs of the MLP-half / attention-half weight gradients are ready
+  cudaEvent_t done[2];  // side -> main: those weight gradients have finished reading the reusable buffers
+};
+SideStream* side_stream();  // nullptr when disabled or creation failed
 bool legacy_attention();  // MFVIT_ATTN=legacy forces the mma.sync attention kernels (A/B measurements)
 // tcgen05 attention (attn_tc.cu); head_dim 64, S <= 256
 int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,

@@ -38,6 +38,23 @@ static int g_device = -1;
 
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+SideStream* side_stream() {
+  static SideStream ss;
+  static int state = 0;  // 0 = untried, 1 = ready, -1 = off
+  if (state == 0) {
+    const char* e = getenv("MFVIT_SIDE_STREAM");
+    state = -1;
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess) {
+      bool ok = true;
+      for (int i = 0; i < 2; ++i) {
+        ok = ok && cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) == cudaSuccess;
+      }
+      if (ok) state = 1;
+    }
+  }
+  return state == 1 ? &ss : nullptr;
+}
 bool legacy_attention() {
   static int v = -1;
   if (v < 0) {

@@ -225,6 +225,30 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
   const long long D = C / p->H;
   const float scale = 1.0f / sqrtf((float)D);
   const int last = 2 * (int)p->depth;
+  // Two lanes: `st` carries the chain every later kernel depends on (LayerNorm backward, dgrads, attention backward);
+  // `sw` carries the weight-gradient GEMMs + bias column sums, which only feed the optimizer.  fork[h] marks their
+  // inputs ready, done[h] marks the reusable buffers they read (dhid, gact_bf, dqkv, dx16) free again.
+  SideStream* ss = side_stream();
+  cudaStream_t sw = ss ? ss->stream : st;
+  bool pending[2] = {false, false};  // done[h] recorded and not yet waited on by the main lane
+  auto fork = [&](int h) -> int {
+    if (!ss) return MFV_OK;
+    MFV_CUDA_CHECK(cudaEventRecord(ss->fork[h], st));
+    MFV_CUDA_CHECK(cudaStreamWaitEvent(sw, ss->fork[h], 0));
+    return MFV_OK;
+  };
+  auto side_done = [&](int h) -> int {
+    if (!ss) return MFV_OK;
+    MFV_CUDA_CHECK(cudaEventRecord(ss->done[h], sw));
+    pending[h] = true;
+    return MFV_OK;
+  };
+  auto join = [&](int h) -> int {
+    if (!ss || !pending[h]) return MFV_OK;
+    MFV_CUDA_CHECK(cudaStreamWaitEvent(st, ss->done[h], 0));
+    pending[h] = false;
+    return MFV_OK;
+  };
   int cur = 0;  // dx[cur] holds the gradient of the residual stream
   // final norm
   // each LN backward also emits colsum(dx) = bias gradient of the Linear feeding that residual add (fc2 / proj)
@@ -233,27 +257,36 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
                        v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
   for (int l = (int)p->depth - 1; l >= 0; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+    RC(join(0));  // the previous block's MLP-half weight gradients still read dhid / gact_bf
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid,
                     p->fwd_f16 ? v.g_b(l) : nullptr, v.u(l), Hd, st));
-    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), -1, st));  // bias: LN backward above
-    RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), st));
+    RC(fork(0));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), -1, sw));  // bias: LN backward above
+    RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), sw));
+    RC(side_done(0));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
+    RC(join(1));  // the previous block's attention-half weight gradients still read dx16[cur ^ 1]
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
                          v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
                          v.gr(v.boff(l, p->r_ln2_b)), v.gr(v.boff(l, p->r_proj_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
-    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, st));  // bias: LN2 backward above
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, nullptr, 0, st));
     RCP(PROF_ATTN_BWD, mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
-    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), st));
+    RC(fork(1));
+    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, sw));  // bias: LN2 backward above
+    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), sw));
+    RC(side_done(1));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
+    RC(join(0));  // fc2's weight gradient of this block reads dx16[cur ^ 1], which the LayerNorm backward below rewrites
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
                          v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
                          v.gr(v.boff(l, p->r_ln1_b)), l > 0 ? v.gr(v.boff(l - 1, p->r_fc2_b)) : nullptr, G, M, C, p->P,
                          st));
     cur ^= 1;
   }
+  RC(join(0));
+  RC(join(1));
   // ---- embedding: cls gradient, conv bias / weight gradient (pos_embed is a fixed table)
   const long long rows_pe = p->B * p->np;
   RCP(PROF_EMBED_BWD, mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,

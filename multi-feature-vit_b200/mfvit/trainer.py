@@ -134,10 +134,15 @@ class MFViTCATrainer:
         ws = torch.distributed.get_world_size(self.pg)
         if ws == 1:
             return
-        # mean over ranks (DDP semantics): pre-divide on device, then sum
+        # mean over ranks (DDP semantics).  NCCL averages inside the collective (no extra pass over the 173 MB flat
+        # gradient buffer); gloo (CPU tests) has no AVG, so pre-divide there.
+        avg = torch.distributed.get_backend(self.pg) == "nccl"
         for t in (grad, self._small.grad):
-            t.div_(ws)
-            torch.distributed.all_reduce(t, group=self.pg)
+            if avg:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            else:
+                t.div_(ws)
+                torch.distributed.all_reduce(t, group=self.pg)
 
     def optimizer_step(self, grad):
         eng = self.engine
