@@ -322,6 +322,66 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return dg;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two elements per issue slot.  The GEMM epilogues
+// are instruction-issue bound, so the GELU polynomials run on pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+// Phi(x) for a pair (same polynomial as normal_cdf_fast): 7 packed instructions + 4 MUFU per pair
+__device__ __forceinline__ f32x2 normal_cdf_fast2(f32x2 x, f32x2 x2) {
+  f32x2 q = fma2(splat2(-3.2289765385939972e-06f), x2, splat2(8.82378953974694e-05f));
+  q = fma2(q, x2, splat2(0.0003602751239668578f));
+  q = fma2(q, x2, splat2(-0.10522668808698654f));
+  q = fma2(q, x2, splat2(-2.3020453453063965f));
+  float a0, a1;
+  unpack2(mul2(q, x), a0, a1);
+  float t0, t1, r0, r1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  unpack2(add2(pack2(t0, t1), splat2(1.0f)), t0, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  return pack2(r0, r1);
+}
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+  const f32x2 x = pack2(a, b);
+  unpack2(mul2(x, normal_cdf_fast2(x, mul2(x, x))), a, b);
+}
+// gelu and gelu' of a pair
+__device__ __forceinline__ void gelu_erf_both2(float xa, float xb, f32x2& g, f32x2& dg) {
+  const f32x2 x = pack2(xa, xb);
+  const f32x2 x2 = mul2(x, x);
+  const f32x2 cdf = normal_cdf_fast2(x, x2);
+  float e0, e1;
+  unpack2(mul2(x2, splat2(-0.72134752044448170368f)), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
+  g = mul2(x, cdf);
+  dg = fma2(mul2(x, splat2(0.39894228040143267794f)), pack2(e0, e1), cdf);
+}
+
 // same, with independent A / B element formats (0 = fp16, 1 = bf16): kind::f16 accepts mixed 16-bit operands
 __host__ __device__ constexpr uint32_t make_idesc2(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N,
                                                    uint32_t a_mn_major, uint32_t b_mn_major) {

@@ -391,7 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
             publish(&tmC, st0, n0, row0, g, false);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = gelu_erf(f[k]);
+            for (int k = 0; k < 32; k += 2) gelu_erf2(f[k], f[k + 1]);
             uint8_t* st1 = slot_ptr(use);
             acquire_slot();
 #pragma unroll
@@ -434,10 +434,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 u2 = unpack_bf16(uw[k]);
+                f32x2 gg, dd;
+                gelu_erf_both2(u2.x, u2.y, gg, dd);
                 float g0, g1, d0, d1;
-                gelu_erf_both(u2.x, g0, d0);
-                gelu_erf_both(u2.y, g1, d1);
-                o[k] = pack_bf16(f[8 * j + 2 * k] * d0, f[8 * j + 2 * k + 1] * d1);
+                unpack2(gg, g0, g1);
+                unpack2(mul2(pack2(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]), dd), d0, d1);
+                o[k] = pack_bf16(d0, d1);
                 gk[4 * j + k] = pack_bf16(g0, g1);
               }
               *pp = make_uint4(o[0], o[1], o[2], o[3]);
