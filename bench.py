@@ -335,18 +335,27 @@ def main():
         e2e_value = pairs * e_steps / (e2e_ms * 1e-3)
         gf = gemm_class_flops(img, B)
         roof = None
+        # DRAM bytes per launch of each kernel class from the committed ncu capture of the same step (cold-cache,
+        # serialised launches; profiles/r01_kernel_traffic.json) - only meaningful for the configuration it was taken on
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+        if os.path.exists(tpath) and B == 32 and img == 224:
+            with open(tpath) as f:
+                traffic = {k: v.get("dram_bytes_per_launch") for k, v in json.load(f).get("classes", {}).items()}
         if dominant in gf:
             d = breakdown[dominant]
             ach = gf[dominant] / (d["ms_per_step"] * 1e-3) / 1e12
             roof = {"kernel": "gemm_bf16_kernel (%s launches of the step)" % dominant, "bound": "tensor",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "frac": ach / peaks["bf16_sustained"], "traffic": traffic.get(dominant),
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                      "profiles/r01_kernel_traffic.json" if traffic.get(dominant) else None,
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                     "launches_per_step": d["launches_per_step"], "ms_per_step": d["ms_per_step"]}
         elif dominant is not None:
             d = breakdown[dominant]
             roof = {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": None, "traffic": None, "ms_per_step": d["ms_per_step"]}
+                    "frac": None, "traffic": traffic.get(dominant), "ms_per_step": d["ms_per_step"]}
         step_tf = value * pair_flops(img) / 1e12
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         line = {

@@ -75,6 +75,10 @@ typedef struct {
   int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere) */
   int32_t cta_group;   /* 0 = auto, 1 = 128-row tiles, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) */
   int32_t reserved;
+  /* MFV_EPI_ATOMIC_F32 with 384-wide pair tiles (N == 384) only: f32 [G][M] (group stride bias_gstride), += the row
+   * sums of A over the reduction dimension, i.e. the bias gradient of a weight-gradient GEMM (A = dY read MN-major),
+   * computed by one extra N=16 UMMA per k-step against a tile of ones.  NULL = off.                                */
+  float* row_sum;
 } mfv_gemm_args;
 int mfv_gemm(const mfv_gemm_args* args, void* stream);
 

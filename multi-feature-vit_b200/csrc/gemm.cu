@@ -37,6 +37,7 @@ struct GemmParams {
   int epi;
   int has_c2, has_c3;
   int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
+  float* row_sum;         // BN == 384, fp32 reduce-add epilogue: += row sums of A (bias gradient of a wgrad GEMM)
   long long bias_gstride;
   const float* bias;
 };
@@ -57,7 +58,8 @@ struct GemmSmem {
   static constexpr int STAGES = (STAGE_BYTES > 40960) ? 2 : (STAGE_BYTES > 32768) ? 3 : (STAGE_BYTES > 24576 ? 4 : (STAGE_BYTES > 16384 ? 5 : 6));
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;  // TMEM accumulators: double-buffered when two fit in 512 columns
   static constexpr int BAR_BYTES = 512;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int ONES_BYTES = (BN == 384) ? 2048 : 0;  // [16 k][64 n] tile of 1.0 for the row-sum UMMA
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + 1024;  // +1024: alignment
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -106,6 +108,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
+  uint8_t* ones_tile = bar_base + S::BAR_BYTES;  // BN == 384 only
   uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + AUX_BARS);
 
@@ -133,6 +136,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) {
     if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  if (BN == 384 && warp == 2 && p.row_sum) {  // bf16 1.0 everywhere: the swizzle is irrelevant for a constant tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<uint4*>(ones_tile)[lane + 32 * i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // barriers of both CTAs initialised before any remote signal
@@ -199,6 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                          (uint32_t)p.a_mn, (uint32_t)p.b_mn);
       const uint32_t idesc2 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, 128, (uint32_t)p.a_mn,
                                           (uint32_t)p.b_mn);  // second UMMA of a 384-wide tile
+      const uint32_t idesc3 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, 16, (uint32_t)p.a_mn, 1u);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kadv = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
       const uint32_t b_kadv = p.b_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
@@ -229,6 +239,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (BN == 384) {
               const uint64_t db2 = make_smem_desc_sw128(sb + 16384u + k * b_kadv, b_lbo, 1024u);
               umma_bf16_cg2(tmem_d + 256u, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (p.row_sum)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
+                umma_bf16_cg2(tmem_d + 384u, da, make_smem_desc_sw128(smem_u32(ones_tile), 8192u, 1024u), idesc3,
+                              (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
@@ -336,6 +349,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         continue;
+      }
+      if (BN == 384 && epi == MFV_EPI_F32 && p.row_sum && h == 0 && n_tile == 0) {
+        uint32_t rs;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(trow + 384u) : "memory");
+        tmem_ld_wait();
+        if (row0 + lane < p.M) atomicAdd(p.row_sum + (long long)g * p.bias_gstride + row0 + lane, __uint_as_float(rs));
       }
 #pragma unroll 1
       for (int i = 0; i < n_my; ++i) {
@@ -550,6 +569,11 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 3;  // bit0: skip everything, bit1: skip the bulk stores
   p.bias_gstride = a->bias_gstride;
   p.bias = (const float*)a->bias;
+  p.row_sum = nullptr;
+  if (a->row_sum) {
+    if (BN != 384 || a->epilogue != MFV_EPI_ATOMIC_F32 || a->N != 384) return MFV_ERR_ARG;
+    p.row_sum = a->row_sum;
+  }
 
   CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
   int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);

@@ -118,13 +118,20 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
     if (waves <= 3 && eff > best) { best = eff; splits = sp; }
   }
   a.splits = (int)splits;
+  // bias gradient: folded into the 384-wide pair tile as one extra N=16 UMMA against a tile of ones (no extra pass
+  // over dY); other tilings fall back to the column-sum kernel
+  const bool fold_bias = b_off >= 0 && bn == 384 && bm == 256;
+  if (fold_bias) {
+    a.row_sum = v.gr(b_off);
+    a.bias_gstride = v.p->P;
+  }
   int rc;
   {
     ProfScope ps(PROF_GEMM_WGRAD, st);
     rc = mfv_gemm(&a, st);
   }
   if (rc) return rc;
-  if (b_off >= 0) {
+  if (b_off >= 0 && !fold_bias) {
     ProfScope ps(PROF_COLSUM, st);
     rc = mfv_colsum_bf16(dY, v.gr(b_off), v.p->G, rows, N, v.p->P, st);
   }

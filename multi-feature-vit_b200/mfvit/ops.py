@@ -25,7 +25,7 @@ def _stream():
 
 def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c_gstride=0, bias=None,
          bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, C3=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
-         splits=1, block_n=0, dtype_flags=0, cta_group=0):
+         splits=1, block_n=0, dtype_flags=0, cta_group=0, row_sum=None):
     lib = _lib_for(A)
     a = GemmArgs()
     a.A, a.B, a.C, a.C2, a.bias, a.aux = (A.data_ptr(), B.data_ptr(), Cout.data_ptr(),
@@ -40,6 +40,7 @@ def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c
     a.a_mn_major, a.b_mn_major, a.epilogue, a.splits, a.block_n = int(a_mn), int(b_mn), epilogue, splits, block_n
     a.dtype_flags = dtype_flags
     a.cta_group = cta_group
+    a.row_sum = row_sum.data_ptr() if row_sum is not None else None
     check(lib.mfv_gemm(C.byref(a), _stream()), "mfv_gemm")
     return Cout
 
@@ -68,13 +69,13 @@ def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, ct
                 cta_group=cta_group, C2=out2)
 
 
-def linear_wgrad(dy16, x16, dw, splits=8, block_n=0, cta_group=0):
-    """dw [G,N,K] f32 += dy16[G,M,N]^T x16[G,M,K]."""
+def linear_wgrad(dy16, x16, dw, splits=8, block_n=0, cta_group=0, db=None):
+    """dw [G,N,K] f32 += dy16[G,M,N]^T x16[G,M,K]; db [G,N] f32 += colsum(dy16) (384-wide pair tiles only)."""
     G, M, N = dy16.shape
     K = x16.shape[2]
     return gemm(dy16, x16, dw, M=N, N=K, K=M, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=M * K,
                 c_gstride=N * K, a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, splits=splits, block_n=block_n,
-                cta_group=cta_group)
+                cta_group=cta_group, row_sum=db, bias_gstride=N if db is not None else 0)
 
 
 def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False, f16=False, bf16_copy=False):

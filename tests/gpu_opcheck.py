@@ -107,8 +107,12 @@ def t_gemm_wgrad(G, M, N, K, splits):
         x = bf(torch.randn(G, M, K, device=dev))
         ref = torch.einsum("gmn,gmk->gnk", dy.float(), x.float())
         dw = torch.zeros(G, N, K, device=dev)
-        ops.linear_wgrad(dy, x, dw, splits=splits)
+        fold = K == 384 and N > 128  # 384-wide pair tile: the bias gradient rides along as an extra UMMA
+        db = torch.zeros(G, N, device=dev) if fold else None
+        ops.linear_wgrad(dy, x, dw, splits=splits, db=db)
         report("gemm wgrad G%d M%d N%d K%d s%d" % (G, M, N, K, splits), dw, ref, 1e-4, rel=True)
+        if fold:
+            report("gemm wgrad folded bias grad G%d M%d N%d" % (G, M, N), db, dy.float().sum(1), 1e-4, rel=True)
     return f
 
 
