@@ -305,7 +305,8 @@ def main():
     e2e_ms = e_start.elapsed_time(e_end)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps
+    # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps; the library serialises the
+    # weight-gradient side stream while profiling so that every class time is that class alone
     breakdown, dominant = {}, None
     if rank == 0:
         import ctypes as C

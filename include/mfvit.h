@@ -33,6 +33,9 @@ int mfv_init(int device);
 const char* mfv_strerror(int code);
 /* "file:line: expression" of the last CUDA runtime failure returned to this thread ("" if none); debugging aid. */
 const char* mfv_last_error_where(void);
+/* Runtime switches (A/B measurements, tests): key in {"pdl", "side_stream", "legacy_attention"}; the defaults come
+ * from the environment (MFVIT_PDL=0, MFVIT_SIDE_STREAM=0, MFVIT_ATTN=legacy).                                       */
+int mfv_set_option(const char* key, int value);
 int mfv_num_sms(void);
 /* Number of kernels this library has launched so far in the process (bench.py reports the per-step delta). */
 uint64_t mfv_launch_count(void);

@@ -3,6 +3,7 @@
 #include "mfvit_internal.h"
 
 #include <stdlib.h>
+#include <string>
 #include <vector>
 
 namespace mfv {
@@ -38,13 +39,21 @@ static int g_device = -1;
 
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+// Runtime switches (defaults from the environment, overridable through mfv_set_option): -1 = not read yet
+static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1;
+static int env_flag(const char* name, int dflt, char off_char) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] == off_char ? !dflt : dflt;
+}
 SideStream* side_stream() {
   static SideStream ss;
-  static int state = 0;  // 0 = untried, 1 = ready, -1 = off
+  static int state = 0;  // 0 = untried, 1 = ready, -1 = creation failed
+  if (g_opt_side < 0) g_opt_side = env_flag("MFVIT_SIDE_STREAM", 1, '0');
+  if (!g_opt_side || prof_enabled()) return nullptr;  // per-class timings want serialised launches
   if (state == 0) {
-    const char* e = getenv("MFVIT_SIDE_STREAM");
     state = -1;
-    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess) {
       bool ok = true;
       for (int i = 0; i < 2; ++i) {
         ok = ok && cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
@@ -56,25 +65,30 @@ SideStream* side_stream() {
   return state == 1 ? &ss : nullptr;
 }
 bool legacy_attention() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MFVIT_ATTN");
-    v = (e && e[0] == 'l') ? 1 : 0;
-  }
-  return v == 1;
+  if (g_opt_legacy_attn < 0) g_opt_legacy_attn = env_flag("MFVIT_ATTN", 0, 'l');
+  return g_opt_legacy_attn == 1;
 }
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MFVIT_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
+  if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
+  return g_opt_pdl == 1;
 }
 }  // namespace mfv
 
 // Source location and expression of the last CUDA runtime failure seen by this thread ("" if none).
 extern "C" const char* mfv_last_error_where(void) { return mfv::g_err_where; }
+
+// Runtime switches for A/B measurements and tests: "pdl" (programmatic dependent launch, default 1), "side_stream"
+// (weight gradients on a second stream, default 1), "legacy_attention" (mma.sync attention kernels, default 0).
+extern "C" int mfv_set_option(const char* key, int value) {
+  using namespace mfv;
+  if (!key) return MFV_ERR_ARG;
+  const std::string k(key);
+  if (k == "pdl") g_opt_pdl = value ? 1 : 0;
+  else if (k == "side_stream") g_opt_side = value ? 1 : 0;
+  else if (k == "legacy_attention") g_opt_legacy_attn = value ? 1 : 0;
+  else return MFV_ERR_ARG;
+  return MFV_OK;
+}
 
 extern "C" int mfv_abi_version(void) { return MFV_ABI_VERSION; }
 

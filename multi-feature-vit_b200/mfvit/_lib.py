@@ -71,6 +71,7 @@ SIGNATURES = {
     "mfv_init": (C.c_int, [C.c_int]),
     "mfv_strerror": (C.c_char_p, [C.c_int]),
     "mfv_last_error_where": (C.c_char_p, []),
+    "mfv_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mfv_num_sms": (C.c_int, []),
     "mfv_launch_count": (C.c_uint64, []),
     "mfv_prof_enable": (C.c_int, [C.c_int]),

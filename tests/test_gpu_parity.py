@@ -202,3 +202,64 @@ def test_ema_bit_exact_full_model_and_moco_step():
     assert mn >= GRAD_COS_TOL, "MoCo query-path gradient cosine %.5f at %s" % (mn, worst)
     mn, worst, _ = E.grad_report(pred_ref.named_parameters(), model.predictor.named_parameters())
     assert mn >= GRAD_COS_TOL, "MoCo predictor gradient cosine %.5f at %s" % (mn, worst)
+
+
+def _set_option(key, value):
+    from mfvit import _lib
+    lib = _lib.load()
+    assert lib.mfv_set_option(key.encode(), int(value)) == 0
+
+
+@pytest.mark.parametrize("f16", [False, True])
+def test_tcgen05_attention_matches_mma_sync_kernels(f16):
+    """The tcgen05/TMEM attention (attn_tc.cu) and the mma.sync kernels (attn.cu) implement the same op: same inputs,
+    both paths through the C ABI, outputs equal to 16-bit rounding (and each is checked against PyTorch in opcheck)."""
+    from mfvit import ops
+    torch.manual_seed(11)
+    NB, S, H, D = 8, 197, 6, 64
+    qkv = torch.randn(NB, S, 3, H, D, device="cuda")
+    qkv = qkv.half() if f16 else qkv.bfloat16()
+    do = torch.randn(NB, S, H, D, device="cuda").bfloat16()
+    res = {}
+    try:
+        for legacy in (0, 1):
+            _set_option("legacy_attention", legacy)
+            r = ops.attn_fwd(qkv, H, f16=f16, bf16_copy=f16)
+            o, lse = (r[2], r[1]) if f16 else r
+            res[legacy] = (o.float(), lse.clone(), ops.attn_bwd(qkv, o, do, lse).float())
+    finally:
+        _set_option("legacy_attention", 0)
+    o0, l0, g0 = res[0]
+    o1, l1, g1 = res[1]
+    assert (o0 - o1).abs().max().item() <= 2e-2 * o1.abs().max().item()
+    assert (l0 - l1).abs().max().item() <= 1e-3
+    assert E.cos(g0, g1) > 0.9999 and (g0 - g1).abs().max().item() <= 3e-2 * g1.abs().max().item()
+
+
+def test_side_stream_and_pdl_do_not_change_the_step():
+    """Scheduling switches are value-neutral: weight gradients on the side stream / programmatic dependent launch on or
+    off give the same gradients up to the order of the fp32 reduce-adds."""
+    _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=3)
+    img_c, img_e, tgt = E.synthetic_pair(8, 224, device="cuda")
+
+    def grads():
+        for m in (o_f, o_c, o_e):
+            m.zero_grad(set_to_none=True)
+        fused, x_c, x_e = o_f(o_c, o_e, img_c, img_e)
+        F.cross_entropy(fused + x_c + x_e, tgt).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in list(o_c.named_parameters()) + list(o_e.named_parameters())
+                if p.grad is not None}
+
+    try:
+        base = grads()
+        for key in ("side_stream", "pdl"):
+            _set_option(key, 0)
+            other = grads()
+            _set_option(key, 1)
+            for n in base:
+                assert E.cos(other[n], base[n]) > 0.99999, (key, n)
+                assert (other[n] - base[n]).abs().max().item() <= 1e-3 * base[n].abs().max().item() + 1e-7, (key, n)
+    finally:
+        _set_option("side_stream", 1)
+        _set_option("pdl", 1)
