@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--cpu-sample-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the "
+                                                            "CUDA graph of the step (single-GPU runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "mfvit":
         args.warmup = 3
@@ -254,12 +256,18 @@ def main():
     for i in range(args.warmup):
         trainer.step(*dev_batches[i % nb])
     barrier()
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:  # the whole step (fwd, loss, bwd, optimizer) as one CUDA graph; data-parallel runs stay eager
+        trainer.capture_graph(*dev_batches[0])
+        for i in range(2):
+            trainer.step(*dev_batches[i % nb])
+        barrier()
 
     # ---- timed: device-resident inputs
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.mfv_launch_count()
+    launches0 = lib.mfv_launch_count() + trainer.graph_replays * trainer.graph_launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
@@ -268,7 +276,9 @@ def main():
     end.record()
     barrier()
     elapsed_ms = start.elapsed_time(end)
-    launches = (lib.mfv_launch_count() - launches0) / args.steps
+    # kernels of libmfvit.so per step: eager launches are counted by the library, graph replays re-issue the launches
+    # counted while the step was captured
+    launches = (lib.mfv_launch_count() + trainer.graph_replays * trainer.graph_launches - launches0) / args.steps
     loss_val = float(loss)
 
     # ---- timed: end to end (pinned host -> device copies in, loss read back, every step)
@@ -369,6 +379,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / e_steps},
             "gpu_launches": launches,
+            "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches
+                           if use_graph else "eager stream launches",
             "roofline": roof,
             "step_tflops": step_tf,
             "step_frac_of_bf16_peak": {"measured_sustained": step_tf / peaks["bf16_sustained"] / world,

@@ -56,6 +56,9 @@ class MFViTCATrainer:
         self.steps = 0
         self._mom_engine = None
         self._mom_small = None
+        self._graph = None          # CUDA graph of one whole step (capture_graph)
+        self.graph_launches = 0     # kernels of libmfvit.so inside the captured step
+        self.graph_replays = 0
 
     # -- lazily bind to the device of the first batch
     def _prepare(self, device):
@@ -162,11 +165,61 @@ class MFViTCATrainer:
         ops.sgd_step_(self._small.master, self._small.grad, self._mom_small, None, self.lr, self.momentum, self.wd, first)
         self.steps += 1
 
-    def step(self, img_cxr, img_enh, target):
+    def _step_eager(self, img_cxr, img_enh, target):
         loss, grad = self.forward_backward(img_cxr, img_enh, target)
         self.all_reduce(grad)
         self.optimizer_step(grad)
         return loss
+
+    def step(self, img_cxr, img_enh, target):
+        if self._graph is not None and tuple(img_cxr.shape) == tuple(self._g_inputs[0].shape):
+            for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+            self.steps += 1
+            self.graph_replays += 1
+            return self._g_loss
+        return self._step_eager(img_cxr, img_enh, target)
+
+    def capture_graph(self, img_cxr, img_enh, target):
+        """Capture one whole step (forward, loss, backward incl. the side-stream weight gradients, optimizer) into a
+        CUDA graph replayed by step(): ~240 kernel launches become one graph launch, so a per-step host read of the loss
+        (MAIN_CA:884) no longer starves the GPU.  Parameters and optimizer state are left exactly as they were: the
+        two eager warm-up steps CUDA graph capture needs are undone from a snapshot.  Single-process only."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size(self.pg) > 1:
+            raise MfvError("capture_graph: data-parallel steps run eagerly (the NCCL all-reduce is not captured)")
+        from . import _lib
+        device = img_cxr.device
+        self._prepare(device)
+        lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        eng = self.engine
+        snap = [t.clone() for t in (eng.master, self._mom_engine, self._small.master, self._mom_small)]
+        steps0, fresh0 = self.steps, eng.shadow_fresh
+        self._g_inputs = [torch.empty_like(t) for t in (img_cxr, img_enh, target)]
+        for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
+            dst.copy_(src)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # allocations, cudaFuncSetAttribute, side-stream / event creation happen here
+                self._step_eager(*self._g_inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.mfv_launch_count()
+        with torch.cuda.graph(graph):
+            self._g_loss = self._step_eager(*self._g_inputs)
+        self.graph_launches = int(lib.mfv_launch_count() - n0)
+        # undo the warm-up steps (capture itself executes nothing); the 16-bit GEMM shadows are rebuilt from the master
+        for dst, src in zip((eng.master, self._mom_engine, self._small.master, self._mom_small), snap):
+            dst.copy_(src)
+        ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1), eng.shadow16.view(-1) if eng.fwd_f16 else None)
+        self.steps = max(steps0, 1)  # the captured step is a steady-state one (momentum buffers exist)
+        eng.shadow_fresh = True
+        self._graph = graph
+        return self
 
     def logits(self):
         """(fused, x_cxr, x_enh) of the most recent step."""

@@ -263,3 +263,29 @@ def test_side_stream_and_pdl_do_not_change_the_step():
     finally:
         _set_option("side_stream", 1)
         _set_option("pdl", 1)
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """MFViTCATrainer.capture_graph replays exactly the eager step: same losses and same weights after a few steps on
+    the same batch sequence (up to the order of fp32 reduce-adds), and capture leaves the parameters untouched."""
+    from mfvit.trainer import MFViTCATrainer
+    batches = [E.synthetic_pair(8, 224, device="cuda", rank=i) for i in range(3)]
+    runs = []
+    for use_graph in (False, True):
+        _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=9)
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9)
+        if use_graph:
+            before = None
+            tr._prepare(batches[0][0].device)
+            before = tr.engine.master.clone()
+            tr.capture_graph(*batches[0])
+            assert torch.equal(before, tr.engine.master), "capture_graph must not change the parameters"
+        losses = [float(tr.step(*batches[i % 3])) for i in range(5)]
+        torch.cuda.synchronize()
+        runs.append((losses, tr.engine.master.clone(), tr._small.master.clone()))
+        assert (tr.graph_replays == 5) == use_graph
+    (l0, m0, s0), (l1, m1, s1) = runs
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (l0, l1)
+    assert E.cos(m0, m1) > 0.999999 and (m0 - m1).abs().max().item() <= 1e-3
+    assert E.cos(s0, s1) > 0.99999
