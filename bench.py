@@ -256,7 +256,7 @@ def main():
     for i in range(args.warmup):
         trainer.step(*dev_batches[i % nb])
     barrier()
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("MFVIT_GRAPH_DDP", "1") == "1")
     if use_graph:  # the whole step (fwd, loss, bwd, optimizer) as one CUDA graph; data-parallel runs stay eager
         trainer.capture_graph(*dev_batches[0])
         for i in range(2):
@@ -397,8 +397,14 @@ def main():
                           "passes), oracle port, fp32" % args.cpu_sample_pairs}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: drop the captured graph (it references NCCL kernels) before the communicator goes away, and leave
+        # through os._exit so that a slow NCCL destructor can never hold the launcher after the result line is out.
+        trainer._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

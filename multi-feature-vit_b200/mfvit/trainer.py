@@ -186,10 +186,8 @@ class MFViTCATrainer:
         """Capture one whole step (forward, loss, backward incl. the side-stream weight gradients, optimizer) into a
         CUDA graph replayed by step(): ~240 kernel launches become one graph launch, so a per-step host read of the loss
         (MAIN_CA:884) no longer starves the GPU.  Parameters and optimizer state are left exactly as they were: the
-        two eager warm-up steps CUDA graph capture needs are undone from a snapshot.  Single-process only."""
-        if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size(self.pg) > 1:
-            raise MfvError("capture_graph: data-parallel steps run eagerly (the NCCL all-reduce is not captured)")
+        two eager warm-up steps CUDA graph capture needs are undone from a snapshot."""
+        # Data parallel: the NCCL all-reduce is captured with the step (every rank must capture and replay in lock step).
         from . import _lib
         device = img_cxr.device
         self._prepare(device)
