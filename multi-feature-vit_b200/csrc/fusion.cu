@@ -77,11 +77,23 @@ template <int CPL>
 __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, const float* vec, const float* bias,
                                             float* out, int warp, int lane) {
   constexpr int C = CPL * 32;
-  for (int i = warp; i < C; i += FUS_WARPS) {
-    float w[CPL];
-    load_row<CPL>(w, W + (size_t)i * C, lane);
-    const float s = dot_row<CPL>(w, vec, lane);
-    if (lane == 0) out[i] = s + (bias ? bias[i] : 0.f);
+  // four weight rows per iteration: their loads are all in flight before the first reduction (one CTA streams six
+  // 590 KB matrices out of L2 per sample, so the loop is load-latency bound)
+  for (int i0 = warp; i0 < C; i0 += 4 * FUS_WARPS) {
+    float w[4][CPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) load_row<CPL>(w[r], W + (size_t)i * C, lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) {
+        const float s = dot_row<CPL>(w[r], vec, lane);
+        if (lane == 0) out[i] = s + (bias ? bias[i] : 0.f);
+      }
+    }
   }
 }
 
@@ -160,7 +172,7 @@ __device__ void fusion_forward_core(const FusSmem& sm, const FusPtrs& P, const f
     for (int h = 0; h < heads; ++h) {
       float acc = 0.f;
       const float* wk = P.wk + (size_t)(h * hd) * C + c;
-#pragma unroll 4
+#pragma unroll 16
       for (int i = 0; i < hd; ++i) acc += __ldg(wk + (size_t)i * C) * sm.q[h * hd + i];
       sm.t[h * C + c] = acc;
     }
@@ -175,9 +187,13 @@ __device__ void fusion_forward_core(const FusSmem& sm, const FusPtrs& P, const f
 #pragma unroll
       for (int i = 0; i < CPL; ++i) uacc[h][i] = 0.f;
     }
+    float vn[CPL];  // next row of this warp, requested one iteration ahead (the pass is load-latency bound)
+    if (warp < S) load_row<CPL>(vn, warp == 0 ? sm.f0 : other_rows + (size_t)warp * C, lane);
     for (int j = warp; j < S; j += FUS_WARPS) {
       float v[CPL], xh[CPL];
-      load_row<CPL>(v, j == 0 ? sm.f0 : other_rows + (size_t)j * C, lane);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = vn[i];
+      if (j + FUS_WARPS < S) load_row<CPL>(vn, other_rows + (size_t)(j + FUS_WARPS) * C, lane);
       float rstd;
       ln_stats<CPL>(v, xh, 1e-5f, rstd);
 #pragma unroll
@@ -230,11 +246,21 @@ __device__ void fusion_forward_core(const FusSmem& sm, const FusPtrs& P, const f
   }
   __syncthreads();
   // o[i] = Wv[i] . u_{head(i)}
-  for (int i = warp; i < C; i += FUS_WARPS) {
-    float w[CPL];
-    load_row<CPL>(w, P.wv + (size_t)i * C, lane);
-    const float s = dot_row<CPL>(w, sm.u + (i / hd) * C, lane);
-    if (lane == 0) sm.o[i] = s;
+  for (int i0 = warp; i0 < C; i0 += 4 * FUS_WARPS) {
+    float w[4][CPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) load_row<CPL>(w[r], P.wv + (size_t)i * C, lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) {
+        const float s = dot_row<CPL>(w[r], sm.u + (i / hd) * C, lane);
+        if (lane == 0) sm.o[i] = s;
+      }
+    }
   }
   __syncthreads();
   matvec_rows<CPL>(P.proj_w, sm.o, P.proj_b, sm.c, warp, lane);  // y = Wp o + bp (into c)
@@ -379,7 +405,7 @@ fusion_bwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, co
   // do = Wp^T dy   (thread per column k: sum_i Wp[i][k] dy[i])
   for (int k = tid; k < C; k += FUS_THREADS) {
     float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 16
     for (int i = 0; i < C; ++i) acc += __ldg(P.proj_w + (size_t)i * C + k) * s_dy[i];
     s_do[k] = acc;
   }
@@ -389,7 +415,7 @@ fusion_bwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, co
     for (int h = 0; h < heads; ++h) {
       float acc = 0.f;
       const float* wv = P.wv + (size_t)(h * hd) * C + c;
-#pragma unroll 4
+#pragma unroll 16
       for (int i = 0; i < hd; ++i) acc += __ldg(wv + (size_t)i * C) * s_do[h * hd + i];
       s_du[h * C + c] = acc;
     }
@@ -413,9 +439,13 @@ fusion_bwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, co
 #pragma unroll
       for (int i = 0; i < CPL; ++i) dtacc[h][i] = 0.f;
     float* drows = dtok + ((size_t)o * B + b) * S * C;
+    float vn[CPL];  // next row, requested one iteration ahead
+    if (warp < S) load_row<CPL>(vn, warp == 0 ? sm.f0 : other + (size_t)warp * C, lane);
     for (int j = warp; j < S; j += FUS_WARPS) {
       float v[CPL], n[CPL], xh[CPL], dxh[CPL];
-      load_row<CPL>(v, j == 0 ? sm.f0 : other + (size_t)j * C, lane);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = vn[i];
+      if (j + FUS_WARPS < S) load_row<CPL>(vn, other + (size_t)(j + FUS_WARPS) * C, lane);
       float rstd;
       ln_stats<CPL>(v, n, 1e-5f, rstd);
 #pragma unroll
@@ -476,17 +506,27 @@ fusion_bwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, co
   }
   __syncthreads();
   // dq[i] = Wk[i] . dt_{head(i)}
-  for (int i = warp; i < C; i += FUS_WARPS) {
-    float w[CPL];
-    load_row<CPL>(w, P.wk + (size_t)i * C, lane);
-    const float s = dot_row<CPL>(w, s_dt + (i / hd) * C, lane);
-    if (lane == 0) s_dq[i] = s;
+  for (int i0 = warp; i0 < C; i0 += 4 * FUS_WARPS) {
+    float w[4][CPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) load_row<CPL>(w[r], P.wk + (size_t)i * C, lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r * FUS_WARPS;
+      if (i < C) {
+        const float s = dot_row<CPL>(w[r], s_dt + (i / hd) * C, lane);
+        if (lane == 0) s_dq[i] = s;
+      }
+    }
   }
   __syncthreads();
   // dxh0 += Wq^T dq
   for (int c = tid; c < C; c += FUS_THREADS) {
     float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 16
     for (int i = 0; i < C; ++i) acc += __ldg(P.wq + (size_t)i * C + c) * s_dq[i];
     s_dxh0[c] += acc;
   }
@@ -557,6 +597,7 @@ fusion_wgrad_kernel(const float* __restrict__ scratch, const float* __restrict__
     const int i0 = blockIdx.x * 4;
     for (int c = threadIdx.x; c < C; c += FUS_THREADS) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
       for (int b = 0; b < B; ++b) {
         const float* rb = base + (size_t)b * bs;
 #pragma unroll
