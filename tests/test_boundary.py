@@ -141,3 +141,35 @@ def test_layout_is_aligned_and_complete():
     # blocks are equally strided (the native runtime addresses block l at off_block0 + l*block_stride)
     for i in range(12):
         assert lay.offset["blocks.%d.norm1.weight" % i] == lay.off_block0 + i * lay.block_stride
+
+
+def test_checkpoint_flow_pretrain_to_probe_to_fusion(tmp_path):
+    """The reference hands weights from script to script through state dicts: MoCo pretraining -> `module.base_encoder.`
+    prefix stripped, head dropped (MAIN_LPFT:327-337, missing keys must be exactly head.weight/head.bias) -> fine-tuned
+    `model_best.pth.tar` -> strict load into both MF-ViT CA branches (MAIN_CA:357,385).  The drop-in keeps every key."""
+    import vits
+    bm = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss")
+    moco = bm.MoCo_ViT(partial(vits.vit_small, stop_grad_conv1=True), SimpleNamespace(arch="vit_small"), 256, 4096, 0.2)
+    ckpt = {"state_dict": {"module." + k: v for k, v in moco.state_dict().items()}}  # DDP-wrapped, as MAIN_PRE saves it
+    path = os.path.join(tmp_path, "checkpoint_smallest_loss.pth.tar")
+    torch.save(ckpt, path)
+    # linear-probe script: rename, drop the projector head, non-strict load
+    linear_keyword = "head"
+    sd = torch.load(path, map_location="cpu")["state_dict"]
+    for k in list(sd.keys()):
+        if k.startswith("module.base_encoder") and not k.startswith("module.base_encoder.%s" % linear_keyword):
+            sd[k[len("module.base_encoder."):]] = sd[k]
+        del sd[k]
+    probe = vits.vit_small(num_classes=3)
+    msg = probe.load_state_dict(sd, strict=False)
+    assert set(msg.missing_keys) == {"head.weight", "head.bias"} and not msg.unexpected_keys
+    for n, p in probe.named_parameters():
+        if not n.startswith("head."):
+            assert torch.equal(p, moco.base_encoder.state_dict()[n]), n
+    # fusion script: strict load of the fine-tuned single-branch checkpoint into a fresh branch with a 3-class head
+    best = os.path.join(tmp_path, "model_best.pth.tar")
+    torch.save({"state_dict": probe.state_dict()}, best)
+    branch = vits.vit_small()
+    branch.head = nn.Linear(branch.head.in_features, 3)  # MAIN_CA:309
+    branch.load_state_dict(torch.load(best, map_location="cpu")["state_dict"])  # strict, MAIN_CA:357
+    assert torch.equal(branch.head.weight, probe.head.weight)
