@@ -203,6 +203,26 @@ int mfv_infonce_fwd(const float* q_raw, const float* k_raw, const float* queue, 
 int mfv_infonce_bwd(const float* q_raw, const float* qn, const float* kn, const float* queue, const float* logits,
                     const float* lse, const float* dlogits_ext, const float* queue_override, int64_t ov_start,
                     int64_t ov_n, float gscale, float* dq_raw, int64_t N, int64_t D, int64_t K, float T, void* stream);
+/* Tensor-core InfoNCE (same reference lines): l_neg = (qn / T) @ queue on the tcgen05 GEMM with fp16 operands (qn / T
+ * and an fp16 shadow of the queue; entries in [-1, 1], logits within ~5e-4 of the fp32 kernels at T = 0.2) and fp32
+ * accumulation, written straight into `logits`.  Buffers (caller-owned):
+ *   queue16 fp16 [D][K]: shadow of queue, kept current with mfv_queue16_update (whole queue once, then the enqueued columns)
+ *   logits  f32 [N][ld], ld = K + 8 (16-byte aligned l_neg block): column 7 = l_pos/T, columns 8.. = l_neg/T; the
+ *           tensor given to the loss is the strided view logits[:, 7:]
+ *   qs16    fp16 [N][D] scratch;  lse f32 [N * (1 + 2 * K / 1024)] (lse first, then per-chunk partials);  loss f32 [1]
+ * Backward: dl16 fp16 [N][K] scratch (scaled gradient operand of the split-K GEMM dqn = dlogits @ queue^T), scal f32 [4]
+ * scratch; queue_override / ov_start / ov_n as in mfv_infonce_bwd (pre-enqueue columns, exact fp32 contribution).
+ * D == 256, K % 1024 == 0.                                                                                               */
+int mfv_infonce_tc_fwd(const float* q_raw, const float* k_raw, const void* queue16, float* qn, float* kn, void* qs16,
+                       float* logits, int64_t ld_logits, float* lse, float* loss, int64_t N, int64_t D, int64_t K,
+                       float T, void* stream);
+int mfv_infonce_tc_bwd(const float* q_raw, const float* qn, const float* kn, const void* queue16, const float* logits,
+                       int64_t ld_logits, const float* lse, const float* dlogits_ext, const float* queue_override,
+                       int64_t ov_start, int64_t ov_n, float gscale, void* dl16, float* scal, float* dq_raw, int64_t N,
+                       int64_t D, int64_t K, float T, void* stream);
+/* queue16[:, col0:col0+ncols] = fp16(queue[:, col0:col0+ncols])                                                         */
+int mfv_queue16_update(const float* queue, void* queue16, int64_t D, int64_t K, int64_t col0, int64_t ncols,
+                       void* stream);
 /* queue[:, ptr:ptr+n] = keys^T  (BLD:102); keys f32 [n][D] (already all-gathered, rank-major).                        */
 int mfv_enqueue_keys(const float* keys, float* queue, int64_t n, int64_t D, int64_t K, int64_t ptr, void* stream);
 

@@ -4,7 +4,9 @@
 Same class / attribute / buffer names and forward signature as the reference (BLD:11-226); the hot ops are kernels:
   * both ViT-S/16 encoders            -> mfvit.engine (mfv_vit_forward / mfv_vit_backward)
   * _momentum_update_key_encoder      -> mfv_ema_update, one multi-tensor launch, bit-exact with BLD:88
-  * normalize + l_pos + l_neg + cat/T -> mfv_infonce_fwd / mfv_infonce_bwd (no queue.clone(), BLD:185)
+  * normalize + l_pos + l_neg + cat/T -> mfv_infonce_tc_fwd / _bwd: l_neg on the tcgen05 GEMM against an fp16 shadow of
+                                         the queue (no queue.clone(), BLD:185); MFVIT_INFONCE=fp32 selects the exact
+                                         fp32 FMA kernels mfv_infonce_fwd / _bwd
   * _dequeue_and_enqueue              -> one NCCL all_gather_into_tensor + mfv_enqueue_keys (transposed write)
 The projector / predictor MLPs (Linear-BN-ReLU, 0.4 % of the step FLOPs) remain torch.nn modules so that
 SyncBatchNorm conversion and DDP wrapping (MAIN_PRE:297,312) keep working unchanged.
@@ -17,7 +19,7 @@ import _path  # noqa: E402,F401
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 from mfvit import ops  # noqa: E402
-from mfvit.functions import InfoNCEFn  # noqa: E402
+from mfvit.functions import InfoNCEFn, InfoNCETensorCoreFn  # noqa: E402
 
 
 def _dist_on():
@@ -44,6 +46,10 @@ class MoCo(nn.Module):
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
         self._ema_cache = None
         self._ptr_host = None
+        # fp16 shadow of the queue for the tensor-core InfoNCE (not a buffer: it never reaches a state dict)
+        self._queue16 = None
+        self._queue16_sig = None
+        self.infonce_precision = os.environ.get("MFVIT_INFONCE", "tc")
         # True: reproduce BLD:107-152 (all-gather the key images, global shuffle) even when it cannot change the result
         self.force_batch_shuffle = False
 
@@ -98,13 +104,29 @@ class MoCo(nn.Module):
             holder["start"] = ptr
             holder["old"] = self.queue[:, ptr:ptr + batch_size].clone()
         ops.enqueue_keys_(keys.float().contiguous(), self.queue, ptr)
+        if self._queue16 is not None and self._queue16_sig == self._queue_sig():
+            ops.queue16_update_(self.queue, self._queue16, ptr, batch_size)  # keep the fp16 shadow current
         ptr = (ptr + batch_size) % self.K
         self._ptr_host = ptr
         self.queue_ptr.fill_(ptr)
 
     def _load_from_state_dict(self, *a, **k):
         self._ptr_host = None
+        self._queue16_sig = None
         return super()._load_from_state_dict(*a, **k)
+
+    def _queue_sig(self):
+        # in-place edits through torch bump _version; .to()/.cuda() change the storage; our own enqueue does neither
+        return (self.queue.data_ptr(), self.queue._version, str(self.queue.device))
+
+    def _queue16_current(self):
+        """fp16 shadow of `queue`, rebuilt in one pass whenever the fp32 queue was replaced or edited behind our back."""
+        sig = self._queue_sig()
+        if self._queue16 is None or self._queue16_sig != sig or self._queue16.device != self.queue.device:
+            self._queue16 = torch.empty(self.queue.shape, device=self.queue.device, dtype=torch.float16)
+            ops.queue16_update_(self.queue, self._queue16)
+            self._queue16_sig = sig
+        return self._queue16
 
     # ------------------------------------------------------------------------------------------------ shuffle (BLD:107-152)
     @torch.no_grad()
@@ -154,7 +176,10 @@ class MoCo(nn.Module):
                 k = self.predictor(self.momentum_encoder(im_k))
                 k = self._batch_unshuffle_ddp(k, idx_unshuffle)
         holder = {}
-        logits, kn, _ = InfoNCEFn.apply(q, k, self.queue, self.T, holder)
+        if self.infonce_precision == "fp32":
+            logits, kn, _ = InfoNCEFn.apply(q, k, self.queue, self.T, holder)
+        else:
+            logits, kn, _ = InfoNCETensorCoreFn.apply(q, k, self._queue16_current(), self.T, holder)
         labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)
         self._dequeue_and_enqueue(kn, holder)
         return logits, labels

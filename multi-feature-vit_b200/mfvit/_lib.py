@@ -97,6 +97,10 @@ SIGNATURES = {
     "mfv_ema_update": (C.c_int, [c_vp, i64, i64, f32, f32, c_vp]),
     "mfv_infonce_fwd": (C.c_int, [c_vp] * 8 + [i64, i64, i64, f32, c_vp]),
     "mfv_infonce_bwd": (C.c_int, [c_vp] * 8 + [i64, i64, f32, c_vp, i64, i64, i64, f32, c_vp]),
+    "mfv_infonce_tc_fwd": (C.c_int, [c_vp] * 7 + [i64, c_vp, c_vp, i64, i64, i64, f32, c_vp]),
+    "mfv_infonce_tc_bwd": (C.c_int, [c_vp] * 5 + [i64, c_vp, c_vp, c_vp, i64, i64, f32, c_vp, c_vp, c_vp, i64, i64, i64,
+                                     f32, c_vp]),
+    "mfv_queue16_update": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
     "mfv_enqueue_keys": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
     "mfv_vit_forward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
     "mfv_vit_backward": (C.c_int, [C.POINTER(VitPlan), c_vp]),

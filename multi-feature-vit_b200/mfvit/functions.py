@@ -104,3 +104,34 @@ class InfoNCEFn(torch.autograd.Function):
         else:
             dq = ops.infonce_bwd(q_raw, qn, kn, ctx.queue, logits, lse, ctx.T, override=ov, ov_start=start) * dloss
         return dq, None, None, None, None
+
+
+class InfoNCETensorCoreFn(torch.autograd.Function):
+    """Same op as InfoNCEFn on the tcgen05 GEMM: fp16 operands (qn / T, fp16 shadow of the queue), fp32 accumulation.
+    The returned logits are a strided view [N, 1+K] of an [N, K+8] buffer (16-byte aligned l_neg block)."""
+
+    @staticmethod
+    def forward(ctx, q_raw, k_raw, queue16, T, holder):
+        q_raw = q_raw.float().contiguous()
+        k_raw = k_raw.float().contiguous()
+        qn, kn, buf, lse, loss = ops.infonce_tc_fwd(q_raw, k_raw, queue16, T)
+        ctx.save_for_backward(q_raw, qn, kn, buf, lse)
+        ctx.queue16, ctx.T, ctx.holder = queue16, T, holder
+        ctx.mark_non_differentiable(kn)
+        return buf[:, 7:], kn, loss
+
+    @staticmethod
+    def backward(ctx, dlogits, _dkn, dloss):
+        q_raw, qn, kn, buf, lse = ctx.saved_tensors
+        h = ctx.holder or {}
+        ov, start = h.get("old"), h.get("start", 0)
+        dq = None
+        if dlogits is not None:
+            dbuf = torch.empty_like(buf)
+            dbuf[:, 7:].copy_(dlogits)
+            dq = ops.infonce_tc_bwd(q_raw, qn, kn, ctx.queue16, buf, lse, ctx.T, dlogits_buf=dbuf, override=ov,
+                                    ov_start=start)
+        if dloss is not None:
+            d2 = ops.infonce_tc_bwd(q_raw, qn, kn, ctx.queue16, buf, lse, ctx.T, override=ov, ov_start=start) * dloss
+            dq = d2 if dq is None else dq + d2
+        return dq, None, None, None, None

@@ -260,6 +260,46 @@ def infonce_bwd(q_raw, qn, kn, queue, logits, lse, T, dlogits=None, gscale=1.0, 
     return dq
 
 
+def queue16_update_(queue, queue16, col0=0, ncols=None):
+    """queue16[:, col0:col0+ncols] = fp16(queue[...]): the fp16 shadow the tensor-core InfoNCE reads."""
+    D, K = queue.shape
+    ncols = K - col0 if ncols is None else ncols
+    check(_lib_for(queue).mfv_queue16_update(_p(queue), _p(queue16), D, K, int(col0), int(ncols), _stream()),
+          "mfv_queue16_update")
+    return queue16
+
+
+def infonce_tc_fwd(q_raw, k_raw, queue16, T):
+    """Tensor-core InfoNCE forward.  Returns (qn, kn, logits_buf [N, K+8], lse, loss); logits = logits_buf[:, 7:]."""
+    N, D = q_raw.shape
+    K = queue16.shape[1]
+    dev = q_raw.device
+    qn, kn = torch.empty_like(q_raw), torch.empty_like(k_raw)
+    qs16 = torch.empty(N, D, device=dev, dtype=torch.float16)
+    buf = torch.empty(N, K + 8, device=dev, dtype=torch.float32)
+    lse = torch.empty(N * (1 + 2 * (K // 1024)), device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    check(_lib_for(q_raw).mfv_infonce_tc_fwd(_p(q_raw), _p(k_raw), _p(queue16), _p(qn), _p(kn), _p(qs16), _p(buf), K + 8,
+                                             _p(lse), _p(loss), N, D, K, float(T), _stream()), "mfv_infonce_tc_fwd")
+    return qn, kn, buf, lse, loss
+
+
+def infonce_tc_bwd(q_raw, qn, kn, queue16, buf, lse, T, dlogits_buf=None, gscale=1.0, override=None, ov_start=0):
+    """dq_raw of the tensor-core path; dlogits_buf (optional) has the [N, K+8] layout of the logits buffer."""
+    N, D = q_raw.shape
+    K = queue16.shape[1]
+    dev = q_raw.device
+    dq = torch.empty_like(q_raw)
+    dl16 = torch.empty(N, K, device=dev, dtype=torch.float16)
+    scal = torch.empty(4, device=dev, dtype=torch.float32)
+    ov_n = 0 if override is None else override.shape[1]
+    check(_lib_for(q_raw).mfv_infonce_tc_bwd(_p(q_raw), _p(qn), _p(kn), _p(queue16), _p(buf), K + 8, _p(lse),
+                                             _p(dlogits_buf), _p(override), int(ov_start), int(ov_n), float(gscale),
+                                             _p(dl16), _p(scal), _p(dq), N, D, K, float(T), _stream()),
+          "mfv_infonce_tc_bwd")
+    return dq
+
+
 def enqueue_keys_(keys, queue, ptr):
     n, D = keys.shape
     K = queue.shape[1]

@@ -73,6 +73,12 @@ queues = [torch.nn.functional.normalize(torch.randn(D, K, device=dev), dim=0) fo
 outs = [ops.infonce_fwd(qr, kr, qu, 0.2) for qu in queues]
 ms = timeit([lambda qu=qu: ops.infonce_fwd(qr, kr, qu, 0.2) for qu in queues], reps=5)
 report("InfoNCE fwd (queue 64 MiB read, logits 32 MiB written)", D * K * 4 + N * (K + 1) * 4, ms)
+q16s = [ops.queue16_update_(qu, torch.empty(D, K, device=dev, dtype=torch.float16)) for qu in queues]
+ms = timeit([lambda q16=q16: ops.infonce_tc_fwd(qr, kr, q16, 0.2) for q16 in q16s], reps=5)
+report("InfoNCE tc fwd (fp16 queue 32 MiB rd, logits 32 MiB wr + rd)", D * K * 2 + 2 * N * K * 4, ms)
+tq = ops.infonce_tc_fwd(qr, kr, q16s[0], 0.2)
+ms = timeit([lambda q16=q16: ops.infonce_tc_bwd(qr, tq[0], tq[1], q16, tq[2], tq[3], 0.2) for q16 in q16s], reps=5)
+report("InfoNCE tc bwd (logits rd, fp16 grad 16 MiB wr + rd, queue rd)", D * K * 2 + N * K * 4 + 2 * N * K * 2, ms)
 try:
     qn, kn, logits, lse, loss = outs[0]
     ms = timeit([lambda qu=qu: ops.infonce_bwd(qr, qn, kn, qu, logits, lse, 0.2) for qu in queues], reps=5)

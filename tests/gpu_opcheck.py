@@ -265,6 +265,26 @@ def t_infonce():
     (l2 * dl).sum().backward()
     dq2 = ops.infonce_bwd(q.detach(), qn, kn, queue, logits, lse, T, dlogits=dl)
     report("infonce dq (external dlogits)", dq2, q2.grad, 2e-3, rel=True)
+    # ---- tensor-core path (fp16 operands, fp32 accumulation): north_star bound on logits 2e-3 abs
+    q16 = ops.queue16_update_(queue, torch.empty(D, K, device=dev, dtype=torch.float16))
+    report("queue fp16 shadow", q16.float(), queue, 2.5e-4)
+    qn_t, kn_t, buf, lse_t, loss_t = ops.infonce_tc_fwd(q.detach(), k, q16, T)
+    report("infonce tc qn", qn_t, qn_ref, 1e-6)
+    report("infonce tc logits", buf[:, 7:], logits_ref, 2e-3)
+    report("infonce tc lse", lse_t[:N], torch.logsumexp(logits_ref, 1), 1e-3)
+    report("infonce tc loss", loss_t, loss_ref.reshape(1), 1e-3)
+    dq_t = ops.infonce_tc_bwd(q.detach(), qn_t, kn_t, q16, buf, lse_t, T)
+    report("infonce tc dq (fused CE)", dq_t, q.grad, 5e-3, rel=True)
+    dbuf = torch.zeros_like(buf)
+    dbuf[:, 7:] = dl
+    dq2_t = ops.infonce_tc_bwd(q.detach(), qn_t, kn_t, q16, buf, lse_t, T, dlogits_buf=dbuf)
+    report("infonce tc dq (external dlogits)", dq2_t, q2.grad, 5e-3, rel=True)
+    # backward after an enqueue overwrote 256 columns: the saved fp32 columns must restore the forward's queue
+    old = queue[:, 4096:4096 + 256].clone()
+    q16b = q16.clone()
+    q16b[:, 4096:4096 + 256] = 0
+    dq3_t = ops.infonce_tc_bwd(q.detach(), qn_t, kn_t, q16b, buf, lse_t, T, override=old, ov_start=4096)
+    report("infonce tc dq with overwritten columns", dq3_t, q.grad, 5e-3, rel=True)
     keys = torch.randn(256, D, device=dev)
     qq = queue.clone()
     ops.enqueue_keys_(keys, qq, 1024)
