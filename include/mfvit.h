@@ -275,6 +275,14 @@ typedef struct {
 } mfv_vit_plan;
 int mfv_vit_forward(const mfv_vit_plan* plan, void* stream);
 int mfv_vit_backward(const mfv_vit_plan* plan, void* stream);
+/* The backward in segments: blocks block_hi .. block_lo (inclusive, descending).  MFV_BWD_HEAD adds the final-norm
+ * backward in front (first segment), MFV_BWD_TAIL the embedding part behind (last segment).  When a call returns, the
+ * gradients of its blocks are complete in stream order, so a data-parallel caller can start the all-reduce of that
+ * slice of the flat gradient buffer while the next segment runs.  (The fc2 bias gradient of block l-1 is produced by
+ * block l's LayerNorm backward, i.e. earlier than its own segment - never later.)                                    */
+#define MFV_BWD_HEAD 1
+#define MFV_BWD_TAIL 2
+int mfv_vit_backward_range(const mfv_vit_plan* plan, void* stream, int block_hi, int block_lo, int flags);
 
 /* ---- elementwise / optimiser ------------------------------------------------------------------------------------------
  * f32 master -> 16-bit shadow weights for the GEMM operands: bf16 (backward) and/or fp16 (forward); either may be NULL. */

@@ -223,9 +223,15 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
 }
 
 extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
+  if (!p) return MFV_ERR_ARG;
+  return mfv_vit_backward_range(p, stream, (int)p->depth - 1, 0, MFV_BWD_HEAD | MFV_BWD_TAIL);
+}
+
+extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int block_hi, int block_lo, int flags) {
   using namespace mfv;
   RC(check_plan(p));
   if (!p->save_for_backward || !p->grad || !p->dtokens) return MFV_ERR_ARG;
+  if (block_lo < 0 || block_hi >= p->depth || block_lo > block_hi) return MFV_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const PlanView v(p);
   const long long G = p->G, C = p->C, Hd = p->hidden, M = v.M;
@@ -256,13 +262,14 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
     pending[h] = false;
     return MFV_OK;
   };
-  int cur = 0;  // dx[cur] holds the gradient of the residual stream
+  int cur = 0;  // dx[cur] holds the gradient of the residual stream (always 0 at a block boundary: two flips per block)
   // final norm
   // each LN backward also emits colsum(dx) = bias gradient of the Linear feeding that residual add (fc2 / proj)
-  RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
-                       p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
-                       v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
-  for (int l = (int)p->depth - 1; l >= 0; --l) {
+  if (flags & MFV_BWD_HEAD)
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
+                         p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
+                         v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
+  for (int l = block_hi; l >= block_lo; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
     RC(join(0));  // the previous block's MLP-half weight gradients still read dhid / gact_bf
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid,
@@ -293,7 +300,8 @@ extern "C" int mfv_vit_backward(const mfv_vit_plan* p, void* stream) {
     cur ^= 1;
   }
   RC(join(0));
-  RC(join(1));
+  RC(join(1));  // every gradient of blocks block_hi..block_lo is complete in stream order when this call returns
+  if (!(flags & MFV_BWD_TAIL)) return MFV_OK;
   // ---- embedding: cls gradient, conv bias / weight gradient (pos_embed is a fixed table)
   const long long rows_pe = p->B * p->np;
   RCP(PROF_EMBED_BWD, mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,

@@ -104,6 +104,7 @@ SIGNATURES = {
     "mfv_enqueue_keys": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
     "mfv_vit_forward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
     "mfv_vit_backward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
+    "mfv_vit_backward_range": (C.c_int, [C.POINTER(VitPlan), c_vp, C.c_int, C.c_int, C.c_int]),
     "mfv_cast_shadow": (C.c_int, [c_vp, c_vp, c_vp, i64, c_vp]),
     "mfv_fill_f32": (C.c_int, [c_vp, f32, i64, c_vp]),
     "mfv_sgd_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, i64, f32, f32, f32, C.c_int, c_vp]),

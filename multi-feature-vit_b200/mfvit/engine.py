@@ -309,7 +309,10 @@ class ViTEngine:
         self.grad_idx = nxt
         return self.grads[nxt]
 
-    def backward(self, lease, dtokens, zero=True):
+    def backward(self, lease, dtokens, zero=True, segments=None, on_segment=None):
+        """Encoder backward.  `segments` (optional): list of (block_hi, block_lo) covering depth-1 .. 0 in descending
+        order; `on_segment(grad, lo_elem, hi_elem)` is called after each one with the element range of every group's flat
+        gradient buffer that is now final (data-parallel callers start that slice's all-reduce there)."""
         if lease is None or lease.ws is None:
             raise MfvError("backward called without saved activations (forward ran with save=False?)")
         ws = lease.ws
@@ -320,8 +323,20 @@ class ViTEngine:
         dtokens = dtokens.contiguous()
         stop = not self._params[0][2][1].requires_grad  # patch_embed.proj.weight frozen (stop_grad_conv1)
         plan = self._plan(ws, None, None, dtokens=dtokens, grad=grad, stop_grad_conv1=stop)
-        check(lib.mfv_vit_backward(C.byref(plan), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-              "mfv_vit_backward")
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if not segments:
+            check(lib.mfv_vit_backward(C.byref(plan), stream), "mfv_vit_backward")
+        else:
+            lay = self.layout
+            upper = lay.P
+            for i, (hi, lo) in enumerate(segments):
+                flags = (1 if i == 0 else 0) | (2 if i == len(segments) - 1 else 0)
+                check(lib.mfv_vit_backward_range(C.byref(plan), stream, int(hi), int(lo), flags),
+                      "mfv_vit_backward_range")
+                lower = 0 if i == len(segments) - 1 else lay.off_block0 + lo * lay.block_stride
+                if on_segment is not None:
+                    on_segment(grad, lower, upper)
+                upper = lower
         lease.release()
         return grad
 

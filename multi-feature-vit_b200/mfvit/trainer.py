@@ -9,6 +9,8 @@ cross-entropy on fused + x_cxr + x_enh (mfv_ce_small) -> fusion backward -> enco
 GEMM shadows (mfv_sgd_step).  No autograd graph, no per-parameter Python loop; parameters stay ordinary nn.Parameters
 (views into flat buffers), so state_dict()/checkpoints are unchanged.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -56,6 +58,8 @@ class MFViTCATrainer:
         self.steps = 0
         self._mom_engine = None
         self._mom_small = None
+        self.overlap_allreduce = os.environ.get("MFVIT_OVERLAP_ALLREDUCE", "1") != "0"
+        self._pending = []
         self._graph = None          # CUDA graph of one whole step (capture_graph)
         self.graph_launches = 0     # kernels of libmfvit.so inside the captured step
         self.graph_replays = 0
@@ -108,8 +112,10 @@ class MFViTCATrainer:
             self._shadow_complete = False
         return self._ranges
 
-    def forward_backward(self, img_cxr, img_enh, target):
-        """Forward + backward; gradients land in engine.grads[engine.grad_idx] and self._small.grad."""
+    def forward_backward(self, img_cxr, img_enh, target, reduce_async=False):
+        """Forward + backward; gradients land in engine.grads[engine.grad_idx] and self._small.grad.  reduce_async
+        (set by step() in data-parallel runs) starts the gradient all-reduce slice by slice during the backward; a
+        direct call never issues a collective."""
         device = img_cxr.device
         self._prepare(device)
         eng = self.engine
@@ -127,11 +133,38 @@ class MFViTCATrainer:
         d_x[0].copy_(dlogits)
         d_x[1].copy_(dlogits)
         ops.fusion_bwd(tok, self._pstruct, self._gstruct, dlogits, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok)
-        grad = eng.backward(lease, dtok)
+        self._pending = []
+        if reduce_async and self._overlap_allreduce():
+            # Data parallel: the encoder backward runs in three block segments; the slice of the flat gradient buffer a
+            # segment finished is all-reduced (NCCL, asynchronously on its own stream) while the next segment computes.
+            # Blocks are contiguous in the flat layout, so a slice is one contiguous range per branch.
+            dist = torch.distributed
+            self._pending.append(dist.all_reduce(self._small.grad, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            d = lay.depth
+            cuts = sorted({d, (2 * d) // 3, d // 3, 0}, reverse=True)
+            segments = [(cuts[i] - 1, cuts[i + 1]) for i in range(len(cuts) - 1)]
+
+            def reduce_slice(grad, lo, hi):
+                for g in range(eng.G):
+                    self._pending.append(dist.all_reduce(grad[g, lo:hi], op=dist.ReduceOp.AVG, group=self.pg,
+                                                         async_op=True))
+            grad = eng.backward(lease, dtok, segments=segments, on_segment=reduce_slice)
+        else:
+            grad = eng.backward(lease, dtok)
         self._last = (fused, x)
         return loss, grad
 
+    def _overlap_allreduce(self):
+        dist = torch.distributed
+        return (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+                and dist.get_backend(self.pg) == "nccl" and self.overlap_allreduce)
+
     def all_reduce(self, grad):
+        if getattr(self, "_pending", None):
+            for w in self._pending:  # stream-level waits: the optimizer step is ordered after the NCCL kernels
+                w.wait()
+            self._pending = []
+            return
         if self.pg is None and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
             return
         ws = torch.distributed.get_world_size(self.pg)
@@ -166,7 +199,7 @@ class MFViTCATrainer:
         self.steps += 1
 
     def _step_eager(self, img_cxr, img_enh, target):
-        loss, grad = self.forward_backward(img_cxr, img_enh, target)
+        loss, grad = self.forward_backward(img_cxr, img_enh, target, reduce_async=True)
         self.all_reduce(grad)
         self.optimizer_step(grad)
         return loss

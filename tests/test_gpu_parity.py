@@ -289,3 +289,27 @@ def test_cuda_graph_step_equals_eager_step():
         assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (l0, l1)
     assert E.cos(m0, m1) > 0.999999 and (m0 - m1).abs().max().item() <= 1e-3
     assert E.cos(s0, s1) > 0.99999
+
+
+def test_segmented_backward_equals_whole_backward():
+    """mfv_vit_backward_range over (11..8), (7..4), (3..0) produces the gradients of mfv_vit_backward, and reports
+    final slices in descending order that tile the flat buffer exactly (what the overlapped all-reduce relies on)."""
+    from mfvit.engine import engine_for
+    _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=13)
+    eng = engine_for(o_c, o_e)
+    img_c, img_e, _ = E.synthetic_pair(4, 224, device="cuda")
+    eng.adopt(img_c.device)
+    torch.manual_seed(1)
+    dtok = torch.randn(2, 4, 197, 384, device="cuda") * 1e-2
+    tok, lease = eng.forward([img_c, img_e], save=True)
+    g_whole = eng.backward(lease, dtok).clone()
+    tok2, lease2 = eng.forward([img_c, img_e], save=True)
+    slices = []
+    g_seg = eng.backward(lease2, dtok, segments=[(11, 8), (7, 4), (3, 0)],
+                         on_segment=lambda g, lo, hi: slices.append((lo, hi))).clone()
+    assert torch.equal(tok, tok2)
+    P = eng.layout.P
+    assert slices[0][1] == P and slices[-1][0] == 0
+    assert all(slices[i][0] == slices[i + 1][1] for i in range(len(slices) - 1))
+    assert E.cos(g_seg, g_whole) > 0.999999
+    assert (g_seg - g_whole).abs().max().item() <= 1e-4 * g_whole.abs().max().item()
