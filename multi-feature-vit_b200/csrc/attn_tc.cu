@@ -326,13 +326,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   float* sLse = sDelta + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLse + 256);
   uint64_t* bar_ld = bars;             // [2]: Q,K | V,dO landed
-  uint64_t* bar_conv = bars + 2;       // operands converted / ready (16 warp arrivals)
+  uint64_t* bar_conv = bars + 2;       // fp16 mode: Q, K converted to bf16 (16 warp arrivals)
   uint64_t* bar_sdp = bars + 3;        // S, dP accumulators complete
   uint64_t* bar_sdp_free = bars + 4;   // S, dP read out of TMEM (16)
   uint64_t* bar_pds = bars + 5;        // P, dS tiles written (16)
   uint64_t* bar_mma = bars + 6;        // dV, dK, dQ MMAs of the step complete (P / dS tiles free, accumulators valid)
   uint64_t* bar_acc_free = bars + 7;   // dK_j, dV_j read out (16)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_conv2 = bars + 8;      // fp16 mode: V converted to bf16 (16 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
@@ -348,7 +349,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tma_prefetch_desc(&tmDO);
       tma_prefetch_desc(&tmG);
       mbar_init(&bar_ld[0], 1); mbar_init(&bar_ld[1], 1);
-      mbar_init(bar_conv, FB_CWARPS); mbar_init(bar_sdp, 1); mbar_init(bar_sdp_free, FB_CWARPS);
+      mbar_init(bar_conv, FB_CWARPS); mbar_init(bar_conv2, FB_CWARPS); mbar_init(bar_sdp, 1);
+      mbar_init(bar_sdp_free, FB_CWARPS);
       mbar_init(bar_pds, FB_CWARPS); mbar_init(bar_mma, 1); mbar_init(bar_acc_free, FB_CWARPS);
       fence_mbar_init();
     }
@@ -371,24 +373,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(2 * TILE));
       tma_load_3d(sV, &tmQKV, &bar_ld[1], (2 * H + h) * 64, 0, b);
       tma_load_3d(sdO, &tmDO, &bar_ld[1], h * 64, 0, b);
-      mbar_wait(bar_conv, 0);
-      tc_fence_after();
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
-      auto issue_sdp = [&](int n) {
+      auto issue_s = [&](int n) {
         const int j = n / n_t, i = n % n_t;
         const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base + FB_S_COL, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 0u, 1024u),
                     make_smem_desc_sw128(aK + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+      };
+      auto issue_dp = [&](int n) {
+        const int j = n / n_t, i = n % n_t;
+        const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base + FB_DP_COL, make_smem_desc_sw128(adO + i * 16384 + k * 32, 0u, 1024u),
                     make_smem_desc_sw128(aV + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
         umma_commit(bar_sdp);
       };
-      issue_sdp(0);
+      auto issue_sdp = [&](int n) { issue_s(n); issue_dp(n); };
+      // the first S = Q K^T starts as soon as Q and K are in shared memory (and converted, in fp16 mode) - it does not
+      // wait for V, dO or the delta prologue of the compute warps
+      mbar_wait(&bar_ld[0], 0);
+      if (QKV_F16) mbar_wait(bar_conv, 0);
+      tc_fence_after();
+      issue_s(0);
+      mbar_wait(&bar_ld[1], 0);
+      if (QKV_F16) mbar_wait(bar_conv2, 0);
+      tc_fence_after();
+      issue_dp(0);
       const uint32_t idesc_t = make_idesc2(1u, 1u, 128, 64, 1, 1);  // A = P / dS read MN-major (transposed use)
       const uint32_t idesc_q = make_idesc2(1u, 1u, 128, 64, 0, 1);  // A = dS K-major
       for (int n = 0; n < n_steps; ++n) {
@@ -439,23 +453,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       for (int c = 0; c < 4; ++c) ovec[c] = __ldg(og + c);
       lse_row = lse[(long long)bh * S + drow] * FA_LOG2E;
     }
-    mbar_wait(&bar_ld[0], 0);
-    mbar_wait(&bar_ld[1], 0);
-    if (QKV_F16) {  // fp16 -> bf16 in place (element-wise, so the swizzle is irrelevant); Q, K, V tiles
-      for (int t = 0; t < 3; ++t) {
-        uint8_t* base = (t == 0) ? sQ : (t == 1 ? sK : sV);
-        for (int c = tid; c < TILE / 16; c += FB_CWARPS * 32) {
-          uint4* pp = reinterpret_cast<uint4*>(base + c * 16);
-          uint4 w = *pp;
-          uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+    auto to_bf16 = [&](uint8_t* base) {  // fp16 -> bf16 in place (element-wise, so the swizzle is irrelevant)
+      for (int c = tid; c < TILE / 16; c += FB_CWARPS * 32) {
+        uint4* pp = reinterpret_cast<uint4*>(base + c * 16);
+        uint4 w = *pp;
+        uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f2 = unpack_f16(ww[e]);
-            ww[e] = pack_bf16(f2.x, f2.y);
-          }
-          *pp = w;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f2 = unpack_f16(ww[e]);
+          ww[e] = pack_bf16(f2.x, f2.y);
         }
+        *pp = w;
       }
+    };
+    mbar_wait(&bar_ld[0], 0);
+    if (QKV_F16) {
+      to_bf16(sQ);
+      to_bf16(sK);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_conv);  // S = Q K^T may start
+    }
+    mbar_wait(&bar_ld[1], 0);
+    if (QKV_F16) {
+      to_bf16(sV);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_conv2);  // dP = dO V^T may start
     }
     {  // delta = rowsum(dO * O), lse in the log2 domain (+inf for padded rows -> P = dS = 0 there)
       const int row = drow, half = dhalf;
@@ -480,9 +504,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         sLse[row] = lse_row;
       }
     }
-    fence_proxy_async_smem();  // converted operands -> visible to the tensor core (async proxy)
-    asm volatile("bar.sync 1, %0;" ::"n"(FB_CWARPS * 32) : "memory");
-    if (lane == 0) mbar_arrive(bar_conv);
+    asm volatile("bar.sync 1, %0;" ::"n"(FB_CWARPS * 32) : "memory");  // sDelta / sLse visible to every compute warp
 
     const float scale_log2 = scale * FA_LOG2E;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
