@@ -112,6 +112,13 @@ int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o
  * kept qkv in fp16 (qkv_is_f16) the tiles are converted to bf16 in shared memory: the backward always runs in bf16.                                        */
 int mfv_attn_bwd(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, float* delta,
                  void* dqkv, int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream);
+/* Same, with a workspace: f32 [NB][S][H*D] (mfv_attn_bwd_workspace_bytes).  With it, sequences longer than 224 tokens
+ * (D == 64) also run on tcgen05: one CTA per (image, head, 128-key block), dK / dV accumulated in TMEM over the query
+ * tiles, the key blocks' shares of dQ summed in the workspace by fp32 TMA reduce-adds and converted at the end.      */
+size_t mfv_attn_bwd_workspace_bytes(int64_t NB, int64_t S, int64_t H, int64_t D);
+int mfv_attn_bwd_ws(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, float* delta,
+                    void* dqkv, float* workspace, int64_t NB, int64_t S, int64_t H, int64_t D, float scale,
+                    void* stream);
 
 /* ---- patch embedding -----------------------------------------------------------------------------------------------
  * Replaces timm PatchEmbed Conv2d(3,C,k=16,s=16)+flatten+transpose, cls-token concat and pos-embed add
@@ -272,6 +279,7 @@ typedef struct {
   void* dqkv;             /* bf16 [G][M][3C] */
   float* delta;           /* f32 [G*B][H][S] */
   void* dacc;             /* bf16 [G][B*np][C] */
+  float* attn_ws;         /* f32 [G*B][S][C] (or NULL): fp32 dQ accumulator of the long-sequence attention backward */
 } mfv_vit_plan;
 int mfv_vit_forward(const mfv_vit_plan* plan, void* stream);
 int mfv_vit_backward(const mfv_vit_plan* plan, void* stream);

@@ -489,6 +489,21 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
   return MFV_OK;
 }
 
+extern "C" size_t mfv_attn_bwd_workspace_bytes(int64_t NB, int64_t S, int64_t H, int64_t D) {
+  return (D == 64 && S > 224) ? (size_t)(NB * S * H * D) * sizeof(float) : 0;
+}
+
+extern "C" int mfv_attn_bwd_ws(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse,
+                               float* delta, void* dqkv, float* workspace, int64_t NB, int64_t S, int64_t H, int64_t D,
+                               float scale, void* stream) {
+  using namespace mfv;
+  if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
+  if (workspace && D == 64 && S > 224 && !legacy_attention())
+    return attn_bwd_tc_mb(qkv, qkv_is_f16, o, d_o, lse, delta, workspace, dqkv, NB, S, H, scale,
+                          reinterpret_cast<cudaStream_t>(stream));
+  return mfv_attn_bwd(qkv, qkv_is_f16, o, d_o, lse, delta, dqkv, NB, S, H, D, scale, stream);
+}
+
 extern "C" int mfv_attn_bwd(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse,
                             float* delta, void* dqkv, int64_t NB, int64_t S, int64_t H, int64_t D, float scale,
                             void* stream) {

@@ -612,6 +612,348 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
+
+// =====================================================================================================================
+// Backward for long sequences (S > 224, e.g. 577 tokens at 384^2).  One CTA = one (image, head, key block j of 128 keys);
+// it walks the query tiles i, with K_j / V_j resident and Q_i / dO_i streamed through a two-slot TMA ring:
+//   S = Q_i K_j^T, dP = dO_i V_j^T -> P, dS (as above) -> dV_j += P^T dO_i, dK_j += dS^T Q_i (accumulated over i in TMEM)
+//   dQ_i (this key block's share) = dS K_j -> fp32 TMA reduce-add into dq_ws [NB][S][H*64]; a small kernel turns the
+//   summed dQ into bf16 afterwards.  delta = rowsum(dO * O) comes from attn_delta_kernel.
+// TMEM: S | dP | dQ | dK | dV = 128 + 128 + 64 + 64 + 64 columns.  Warps 0..15 compute, 16 = MMA issue, 17 = TMA producer.
+constexpr int FM_THREADS = 32 * (FB_CWARPS + 2);
+constexpr uint32_t FM_S_COL = 0, FM_DP_COL = 128, FM_DQ_COL = 256, FM_DK_COL = 320, FM_DV_COL = 384;
+
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                  long long rows /* NB*S */, int S, int H) {
+  // one thread per (row, head): 64 bf16 of O and dO
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * H) return;
+  const long long row = t / H;
+  const int h = (int)(t % H);
+  const uint4* a = reinterpret_cast<const uint4*>(o + (row * H + h) * 64);
+  const uint4* b = reinterpret_cast<const uint4*>(d_o + (row * H + h) * 64);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 x = __ldg(a + c), y = __ldg(b + c);
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&x);
+    const uint32_t* yw = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 p = unpack_bf16(xw[e]), q = unpack_bf16(yw[e]);
+      acc = fmaf(p.x, q.x, acc);
+      acc = fmaf(p.y, q.y, acc);
+    }
+  }
+  const long long nb = row / S;
+  const int srow = (int)(row % S);
+  delta[(nb * H + h) * S + srow] = acc;  // [NB][H][S], the layout of lse
+}
+
+// dqkv[nb][s][0][h][:] = bf16(dq_ws[nb][s][h][:])
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, long long rows, int H) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 elements
+  const long long per_row = (long long)H * 8;
+  if (t >= rows * per_row) return;
+  const long long row = t / per_row;
+  const int c8 = (int)(t % per_row);
+  const float4 a = reinterpret_cast<const float4*>(dq_ws + row * H * 64)[c8 * 2];
+  const float4 b = reinterpret_cast<const float4*>(dq_ws + row * H * 64)[c8 * 2 + 1];
+  reinterpret_cast<uint4*>(dqkv + row * 3 * H * 64)[c8] =
+      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+}
+
+template <bool QKV_F16>
+__global__ void __launch_bounds__(FM_THREADS, 1)
+attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmDQ,
+                      const float* __restrict__ lse, const float* __restrict__ delta, int S, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                  // [128][64] bf16, 128B-swizzled (keys j*128 ..)
+  uint8_t* sV = sK + 16384;
+  uint8_t* sQ = sV + 16384;            // 2 slots x [128][64]
+  uint8_t* sdO = sQ + 2 * 16384;       // 2 slots
+  uint8_t* sP = sdO + 2 * 16384;       // [2 key halves of 64][128 q][128 B]
+  uint8_t* sdS = sP + 32768;
+  uint8_t* sStage = sdS + 32768;       // 16 warps x 2 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + FB_CWARPS * 2048);
+  uint64_t* bar_kv = bars;             // K_j, V_j landed
+  uint64_t* bar_q = bars + 1;          // [2] Q_i, dO_i landed in slot
+  uint64_t* bar_qfree = bars + 3;      // [2] slot consumed by the MMAs of its step
+  uint64_t* bar_kvconv = bars + 5;     // fp16 mode: K, V converted (16)
+  uint64_t* bar_qconv = bars + 6;      // [2] fp16 mode: Q_i converted (16)
+  uint64_t* bar_sdp = bars + 8;        // S, dP complete
+  uint64_t* bar_sdp_free = bars + 9;   // S, dP read out (16)
+  uint64_t* bar_pds = bars + 10;       // P, dS written (16)
+  uint64_t* bar_mma = bars + 11;       // dV, dK, dQ MMAs of the step complete
+  uint64_t* bar_dq_free = bars + 12;   // dQ read out of TMEM (16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, j = blockIdx.y;
+  const int b = bh / H, h = bh % H;
+  const int n_t = (S + 127) >> 7;
+  auto rows_of = [&](int t) { return min(128, S - 128 * t); };
+  auto r16 = [](int x) { return (x + 15) & ~15; };
+  const int nk = r16(rows_of(j));      // keys of this block, padded to the UMMA N / K granularity
+
+  if (warp == FB_CWARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmDQ);
+      mbar_init(bar_kv, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&bar_q[s], 1); mbar_init(&bar_qfree[s], 1); mbar_init(&bar_qconv[s], FB_CWARPS); }
+      mbar_init(bar_kvconv, FB_CWARPS); mbar_init(bar_sdp, 1); mbar_init(bar_sdp_free, FB_CWARPS);
+      mbar_init(bar_pds, FB_CWARPS); mbar_init(bar_mma, 1); mbar_init(bar_dq_free, FB_CWARPS);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+
+  if (warp == FB_CWARPS + 1) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      griddep_wait();
+      mbar_arrive_expect_tx(bar_kv, 2 * 16384);
+      tma_load_3d(sK, &tmQKV, bar_kv, (H + h) * 64, j * 128, b);
+      tma_load_3d(sV, &tmQKV, bar_kv, (2 * H + h) * 64, j * 128, b);
+      for (int i = 0; i < n_t; ++i) {
+        const int s = i & 1;
+        if (i >= 2) mbar_wait(&bar_qfree[s], (uint32_t)(((i >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(&bar_q[s], 2 * 16384);
+        tma_load_3d(sQ + s * 16384, &tmQKV, &bar_q[s], h * 64, i * 128, b);
+        tma_load_3d(sdO + s * 16384, &tmDO, &bar_q[s], h * 64, i * 128, b);
+      }
+    }
+  } else if (warp == FB_CWARPS) {
+    // ------------------------------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+      const uint32_t idesc_s = make_idesc2(1u, 1u, 128, (uint32_t)nk, 0, 0);
+      const uint32_t idesc_t = make_idesc2(1u, 1u, 128, 64, 1, 1);  // A = P / dS read MN-major
+      const uint32_t idesc_q = make_idesc2(1u, 1u, 128, 64, 0, 1);  // A = dS K-major
+      auto wait_q = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(&bar_q[s], (uint32_t)((i >> 1) & 1));
+        if (QKV_F16) mbar_wait(&bar_qconv[s], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+      };
+      auto issue_sdp = [&](int i) {
+        const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FM_S_COL, make_smem_desc_sw128(q + k * 32, 0u, 1024u),
+                    make_smem_desc_sw128(aK + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + FM_DP_COL, make_smem_desc_sw128(d + k * 32, 0u, 1024u),
+                    make_smem_desc_sw128(aV + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
+      };
+      mbar_wait(bar_kv, 0);
+      if (QKV_F16) mbar_wait(bar_kvconv, 0);
+      wait_q(0);
+      issue_sdp(0);
+      for (int i = 0; i < n_t; ++i) {
+        if (i + 1 < n_t) {
+          mbar_wait(bar_sdp_free, (uint32_t)(i & 1));
+          wait_q(i + 1);
+          issue_sdp(i + 1);
+        }
+        mbar_wait(bar_pds, (uint32_t)(i & 1));
+        if (i > 0) mbar_wait(bar_dq_free, (uint32_t)((i - 1) & 1));  // dQ of the previous tile has been read out
+        tc_fence_after();
+        const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
+        const int kq = r16(rows_of(i)) / 16;
+        for (int k = 0; k < kq; ++k) {
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          umma_bf16(tmem_base + FM_DV_COL, make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u),
+                    make_smem_desc_sw128(d + k * 2048, 8192u, 1024u), idesc_t, acc);
+          umma_bf16(tmem_base + FM_DK_COL, make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u),
+                    make_smem_desc_sw128(q + k * 2048, 8192u, 1024u), idesc_t, acc);
+        }
+        for (int k = 0; k < nk / 16; ++k)
+          umma_bf16(tmem_base + FM_DQ_COL, make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u),
+                    make_smem_desc_sw128(aK + k * 2048, 8192u, 1024u), idesc_q, k > 0 ? 1u : 0u);
+        umma_commit(&bar_qfree[i & 1]);  // the slot's Q / dO tiles are no longer needed
+        umma_commit(bar_mma);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ compute warps
+    griddep_wait();
+    const int tid = threadIdx.x;  // 0..511
+    const int q = warp & 3, cseg = warp >> 2;
+    auto to_bf16 = [&](uint8_t* base) {
+      for (int c = tid; c < 16384 / 16; c += FB_CWARPS * 32) {
+        uint4* pp = reinterpret_cast<uint4*>(base + c * 16);
+        uint4 w = *pp;
+        uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f2 = unpack_f16(ww[e]);
+          ww[e] = pack_bf16(f2.x, f2.y);
+        }
+        *pp = w;
+      }
+    };
+    if (QKV_F16) {
+      mbar_wait(bar_kv, 0);
+      to_bf16(sK);
+      to_bf16(sV);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_kvconv);
+    }
+    const float scale_log2 = scale * FA_LOG2E;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* stg = sStage + warp * 2048;
+    const bool col_active = cseg * 32 < nk;
+    float dqv[16];            // this warp's 16 dQ columns of the previous tile, waiting for their reduce-add
+    int dq_row0 = -1;
+    auto flush_dq = [&]() {   // fp32 tile 32 rows x 16 columns -> staging -> TMA reduce-add into dq_ws
+      if (dq_row0 < 0) return;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+            make_float4(dqv[4 * c], dqv[4 * c + 1], dqv[4 * c + 2], dqv[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmDQ)),
+                     "r"(smem_u32(stg)), "r"(h * 64 + cseg * 16), "r"(dq_row0), "r"(b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      dq_row0 = -1;
+    };
+    auto read_dq = [&](int i) {  // after bar_mma(i): this warp's columns [cseg*16, +16) of dQ_i, rows q*32 ..
+      tc_fence_after();
+      const bool ok = q * 32 < rows_of(i);
+      if (ok) {
+        uint32_t v[16];
+        fb_tmem_ld16(tlane + FM_DQ_COL + (uint32_t)(cseg * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dqv[e] = __uint_as_float(v[e]);
+        dq_row0 = i * 128 + q * 32;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dq_free);
+    };
+    for (int i = 0; i < n_t; ++i) {
+      const int s = i & 1;
+      const int qrows = rows_of(i);
+      const bool active = (q * 32 < qrows) && col_active;
+      const int r = q * 32 + lane;
+      if (QKV_F16) {  // this step's Q tile to bf16 (dO is bf16 already)
+        mbar_wait(&bar_q[s], (uint32_t)((i >> 1) & 1));
+        to_bf16(sQ + s * 16384);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_qconv[s]);
+      }
+      float l2 = INFINITY, dl = 0.f;
+      if (i * 128 + r < S) {
+        l2 = lse[(long long)bh * S + i * 128 + r] * FA_LOG2E;
+        dl = delta[(long long)bh * S + i * 128 + r];
+      }
+      mbar_wait(bar_sdp, (uint32_t)(i & 1));
+      tc_fence_after();
+      uint32_t pk[16], dk[16];
+      if (active) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t sv[16], dv[16];
+          fb_tmem_ld16(tlane + FM_S_COL + (uint32_t)(cseg * 32 + hh * 16), sv);
+          fb_tmem_ld16(tlane + FM_DP_COL + (uint32_t)(cseg * 32 + hh * 16), dv);
+          tmem_ld_wait();
+          const int key0 = j * 128 + cseg * 32 + hh * 16;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * e]), scale_log2, -l2));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * e + 1]), scale_log2, -l2));
+            if (key0 + 2 * e >= S) p0 = 0.f;
+            if (key0 + 2 * e + 1 >= S) p1 = 0.f;
+            const float d0 = p0 * (__uint_as_float(dv[2 * e]) - dl) * scale;
+            const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dl) * scale;
+            pk[hh * 8 + e] = pack_bf16(p0, p1);
+            dk[hh * 8 + e] = pack_bf16(d0, d1);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sdp_free);
+      if (i > 0) {  // the previous step's MMAs: P / dS tiles free again, dQ_{i-1} complete
+        mbar_wait(bar_mma, (uint32_t)((i - 1) & 1));
+        read_dq(i - 1);
+      }
+      if (active) {
+        const uint32_t off = (uint32_t)((cseg >> 1) * 16384 + r * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t sw = off + ((((cseg & 1) * 4 + c) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          *reinterpret_cast<uint4*>(sdS + sw) = make_uint4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pds);
+      flush_dq();  // dQ_{i-1}: off the critical path (the MMAs of step i are already unblocked)
+    }
+    // ---- tail: last tile's dQ, then dK_j / dV_j (lanes = keys of this block)
+    mbar_wait(bar_mma, (uint32_t)((n_t - 1) & 1));
+    read_dq(n_t - 1);
+    flush_dq();
+    {
+      tc_fence_after();
+      if (q * 32 < rows_of(j)) {
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(tlane + (cseg < 2 ? FM_DK_COL : FM_DV_COL) + (uint32_t)((cseg & 1) * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(f[8 * c], f[8 * c + 1]), pack_bf16(f[8 * c + 2], f[8 * c + 3]),
+                         pack_bf16(f[8 * c + 4], f[8 * c + 5]), pack_bf16(f[8 * c + 6], f[8 * c + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          fa_tma_store_3d(&tmG, stg, ((cseg < 2 ? 1 : 2) * H + h) * 64 + (cseg & 1) * 32, j * 128 + q * 32, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FB_CWARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int fa_encode(CUtensorMap* map, const void* base, int is_f16, long long inner, long long rows, long long images,
                      int box_rows, int box_cols = 64) {
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)images};
@@ -718,6 +1060,71 @@ int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o,
     }
     MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<false>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale));
   }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+// Long sequences (S > 224): key-block CTAs, dQ summed in fp32 through dq_ws (f32 [NB][S][H*64], zeroed here) and
+// converted afterwards; delta is the caller's f32 [NB][H][S] scratch.
+int attn_bwd_tc_mb(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, float* delta,
+                   float* dq_ws, void* dqkv, long long NB, long long S, long long H, float scale, cudaStream_t st) {
+  CUtensorMap tmQKV, tmDO, tmG, tmDQ;
+  int rc;
+  if ((rc = fa_encode(&tmQKV, qkv, qkv_is_f16, 3 * H * 64, S, NB, 128))) return rc;
+  if ((rc = fa_encode(&tmDO, d_o, 0, H * 64, S, NB, 128))) return rc;
+  if ((rc = fa_encode(&tmG, dqkv, 0, 3 * H * 64, S, NB, 32, 32))) return rc;
+  {  // fp32 [NB][S][H*64], box 16 columns (64 B) x 32 rows, 64B swizzle
+    cuuint64_t dims[3] = {(cuuint64_t)(H * 64), (cuuint64_t)S, (cuuint64_t)NB};
+    cuuint64_t strides[2] = {(cuuint64_t)(H * 64) * 4, (cuuint64_t)(H * 64 * S) * 4};
+    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (reinterpret_cast<uintptr_t>(dq_ws) & 15) return MFV_ERR_ALIGN;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return MFV_ERR_INIT;
+    if (enc(&tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dq_ws, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MFV_ERR_ARG;
+  }
+  const long long rows = NB * S;
+  if ((rc = mfv_fill_f32(dq_ws, 0.f, rows * H * 64, st))) return rc;
+  attn_delta_kernel<<<(unsigned)((rows * H + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta, rows, (int)S, (int)H);
+  MFV_LAUNCH_CHECK();
+  const size_t smem = 1024 + 6 * 16384 + 65536 + FB_CWARPS * 2048 + 256;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(NB * H), (unsigned)((S + 127) / 128));
+  cfg.blockDim = dim3(FM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (qkv_is_f16) {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_mb_kernel<true>, tmQKV, tmDO, tmG, tmDQ, lse, (const float*)delta,
+                                      (int)S, (int)H, scale));
+  } else {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_mb_kernel<false>, tmQKV, tmDO, tmG, tmDQ, lse, (const float*)delta,
+                                      (int)S, (int)H, scale));
+  }
+  MFV_LAUNCH_CHECK();
+  attn_dq_convert_kernel<<<(unsigned)((rows * H * 8 + 255) / 256), 256, 0, st>>>(
+      dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), rows, (int)H);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }

@@ -25,7 +25,9 @@ bool legacy_attention();  // MFVIT_ATTN=legacy forces the mma.sync attention ker
 int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
                 long long S, long long H, float scale, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, void* dqkv,
-                long long NB, long long S, long long H, float scale, cudaStream_t st);  // S <= 224  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
+                long long NB, long long S, long long H, float scale, cudaStream_t st);  // S <= 224
+int attn_bwd_tc_mb(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, float* delta,
+                   float* dq_ws, void* dqkv, long long NB, long long S, long long H, float scale, cudaStream_t st);  // MFVIT_PDL=0 disables programmatic dependent launch (default on)
 
 // Launch with programmatic dependent launch (PDL) enabled: the kernel may start while its predecessor in the stream is
 // still draining, and MUST call griddep_wait() (common.cuh) before its first global memory access.

@@ -286,7 +286,8 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_proj_w), C, MFV_EPI_BF16, p->d_o, nullptr, nullptr, 0, st));
-    RCP(PROF_ATTN_BWD, mfv_attn_bwd(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, G * p->B, p->S, p->H, D, scale, st));
+    RCP(PROF_ATTN_BWD, mfv_attn_bwd_ws(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, p->attn_ws,
+                                       G * p->B, p->S, p->H, D, scale, st));
     RC(fork(1));
     RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, sw));  // bias: LN2 backward above
     RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), sw));

@@ -59,7 +59,7 @@ class VitPlan(C.Structure):
         + [("save_for_backward", i32), ("stop_grad_conv1", i32), ("fwd_f16", i32), ("reserved", i32)]
         + [(n, c_vp) for n in ["patches_bf", "xn_bf", "attn_o_bf", "gact_bf"]]
         + [("dtokens", c_vp), ("dx", c_vp * 2), ("dx16", c_vp * 2)]
-        + [(n, c_vp) for n in ["dhid", "dxn", "d_o", "dqkv", "delta", "dacc"]]
+        + [(n, c_vp) for n in ["dhid", "dxn", "d_o", "dqkv", "delta", "dacc", "attn_ws"]]
     )
 
 
@@ -83,6 +83,8 @@ SIGNATURES = {
     "mfv_layernorm_bwd": (C.c_int, [c_vp] * 12 + [i64, i64, i64, i64, c_vp]),
     "mfv_attn_fwd": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_attn_bwd": (C.c_int, [c_vp, C.c_int] + [c_vp] * 5 + [i64, i64, i64, i64, f32, c_vp]),
+    "mfv_attn_bwd_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),
+    "mfv_attn_bwd_ws": (C.c_int, [c_vp, C.c_int] + [c_vp] * 6 + [i64, i64, i64, i64, f32, c_vp]),
     "mfv_patchify": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, i64, i64, c_vp]),
     "mfv_embed_finish": (C.c_int, [c_vp] * 5 + [i64] * 5 + [c_vp]),
     "mfv_embed_finish_bwd": (C.c_int, [c_vp] * 4 + [i64] * 5 + [c_vp]),

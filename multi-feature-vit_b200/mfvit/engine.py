@@ -128,6 +128,9 @@ class _Workspace:
                 dqkv=torch.empty(G * M * 3 * lay.C, device=device, dtype=bf),
                 delta=torch.empty(G * B * lay.H * lay.S, device=device, dtype=f32),
                 dacc=torch.empty(G * B * lay.np * lay.C, device=device, dtype=bf),
+                # fp32 dQ accumulator of the long-sequence (S > 224) tcgen05 attention backward
+                attn_ws=(torch.empty(G * M * lay.C, device=device, dtype=f32)
+                         if (lay.S > 224 and lay.C // lay.H == 64) else None),
             )
         return self.bwd
 
@@ -265,6 +268,7 @@ class ViTEngine:
             p.dx16[0], p.dx16[1] = b["dx16_0"].data_ptr(), b["dx16_1"].data_ptr()
             for f in ("dhid", "dxn", "d_o", "dqkv", "delta", "dacc"):
                 setattr(p, f, b[f].data_ptr())
+            p.attn_ws = b["attn_ws"].data_ptr() if b["attn_ws"] is not None else None
         return p
 
     # ------------------------------------------------------------------------------------------ forward / backward

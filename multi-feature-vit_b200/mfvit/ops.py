@@ -128,8 +128,10 @@ def attn_bwd(qkv, o, d_o, lse):
     lib = _lib_for(qkv)
     dqkv = torch.empty_like(qkv, dtype=torch.bfloat16)
     delta = torch.empty_like(lse)
-    check(lib.mfv_attn_bwd(_p(qkv), int(qkv.dtype == torch.float16), _p(o), _p(d_o), _p(lse), _p(delta), _p(dqkv), NB, S, H, D, float(D) ** -0.5,
-                           _stream()), "mfv_attn_bwd")
+    nws = lib.mfv_attn_bwd_workspace_bytes(NB, S, H, D)
+    ws = torch.empty(nws // 4, device=qkv.device, dtype=torch.float32) if nws else None
+    check(lib.mfv_attn_bwd_ws(_p(qkv), int(qkv.dtype == torch.float16), _p(o), _p(d_o), _p(lse), _p(delta), _p(dqkv),
+                              _p(ws), NB, S, H, D, float(D) ** -0.5, _stream()), "mfv_attn_bwd_ws")
     return dqkv
 
 

@@ -39,8 +39,8 @@ def test_ctypes_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 13 * 8 + 8 * 4 + 8
     assert ctypes.sizeof(_lib.FusionParams) == 13 * 2 * 8
     assert ctypes.sizeof(_lib.EmaChunk) == 24
-    # mfv_vit_plan: 10 i64 + 4 ptr + 20 i64 + 2 ptr + 11 ptr + 4 i32 + 4 ptr + (1 + 2 + 2 + 6) ptr
-    assert ctypes.sizeof(_lib.VitPlan) == (10 + 4 + 20 + 2 + 11) * 8 + 16 + 4 * 8 + (1 + 2 + 2 + 6) * 8
+    # mfv_vit_plan: 10 i64 + 4 ptr + 20 i64 + 2 ptr + 11 ptr + 4 i32 + 4 ptr + (1 + 2 + 2 + 7) ptr
+    assert ctypes.sizeof(_lib.VitPlan) == (10 + 4 + 20 + 2 + 11) * 8 + 16 + 4 * 8 + (1 + 2 + 2 + 7) * 8
 
 
 def test_cpu_forward_fails_loudly():
