@@ -855,17 +855,18 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       if (lane == 0) mbar_arrive(bar_dq_free);
     };
     for (int i = 0; i < n_t; ++i) {
-      const int s = i & 1;
       const int qrows = rows_of(i);
       const bool active = (q * 32 < qrows) && col_active;
       const int r = q * 32 + lane;
-      if (QKV_F16) {  // this step's Q tile to bf16 (dO is bf16 already)
-        mbar_wait(&bar_q[s], (uint32_t)((i >> 1) & 1));
-        to_bf16(sQ + s * 16384);
+      auto convert_q = [&](int t) {  // fp16 mode: Q tile of step t to bf16 in place (dO is bf16 already)
+        const int ss = t & 1;
+        mbar_wait(&bar_q[ss], (uint32_t)((t >> 1) & 1));
+        to_bf16(sQ + ss * 16384);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_qconv[s]);
-      }
+        if (lane == 0) mbar_arrive(&bar_qconv[ss]);
+      };
+      if (QKV_F16 && i == 0) convert_q(0);
       float l2 = INFINITY, dl = 0.f;
       if (i * 128 + r < S) {
         l2 = lse[(long long)bh * S + i * 128 + r] * FA_LOG2E;
@@ -898,6 +899,9 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sdp_free);
+      // the next tile's Q is converted now, one step ahead, so the MMA warp can issue S / dP of step i+1 while this
+      // step's P / dS are still being written (its slot was released by the MMAs of step i-1)
+      if (QKV_F16 && i + 1 < n_t) convert_q(i + 1);
       if (i > 0) {  // the previous step's MMAs: P / dS tiles free again, dQ_{i-1} complete
         mbar_wait(bar_mma, (uint32_t)((i - 1) & 1));
         read_dq(i - 1);

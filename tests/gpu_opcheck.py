@@ -373,6 +373,8 @@ def main():
     run("attn 50/64", t_attn(3, 50, 2, 64), flt)
     run("attn 197/64 f16", t_attn(4, 197, 6, 64, True), flt)
     run("attn 577/32 f16", t_attn(1, 577, 12, 32, True), flt)
+    run("attn 577/64 f16", t_attn(2, 577, 6, 64, True), flt)
+    run("attn 300/64", t_attn(2, 300, 3, 64), flt)
     run("fusion", t_fusion, flt)
     run("ema", t_ema, flt)
     run("infonce", t_infonce, flt)
