@@ -461,9 +461,13 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
                             int64_t NB, int64_t S, int64_t H, int64_t D, float scale, void* stream) {
   using namespace mfv;
   if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
-  if (D == 64 && S <= 256 && (o_is_f16 != 0) == (qkv_is_f16 != 0) && !legacy_attention())
-    return attn_fwd_tc(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
-                       reinterpret_cast<cudaStream_t>(stream));
+  if (D == 64 && (o_is_f16 != 0) == (qkv_is_f16 != 0) && !legacy_attention()) {
+    if (S <= 256)
+      return attn_fwd_tc(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
+                         reinterpret_cast<cudaStream_t>(stream));
+    return attn_fwd_tc_mb(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
+                          reinterpret_cast<cudaStream_t>(stream));
+  }
   if (NB * H > 65535) return MFV_ERR_SHAPE;
   const int Spad = ((int)S + 63) & ~63;
   // whole query range in one CTA when K, V and Q of a head fit twice per SM (S=197: 96 KB); else 128-row chunks

@@ -958,6 +958,247 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   }
 }
 
+
+// =====================================================================================================================
+// Forward for long sequences (S > 256, e.g. 577 tokens at 384^2): flash-style.  One CTA = one (image, head, 128-query
+// tile); K / V stream through a 4-slot TMA ring in blocks of 64 keys; S is double-buffered in TMEM (2 x 64 columns) so the
+// Q K^T of block kb+1 runs under the softmax of block kb; the running row maximum m and sum l live in registers (thread =
+// query row) and O in TMEM is rescaled only when a row's maximum moved (tcgen05.ld / st, warp-uniform skip otherwise).
+// Warps 0..3 softmax + epilogue, 4 MMA issue, 5 TMA producer.  256 TMEM columns, ~97 KB smem: two CTAs per SM.
+constexpr int FL_THREADS = 192;
+constexpr int FL_RING = 4;
+constexpr uint32_t FL_O_COL = 128;  // S buffers at columns 0 and 64 (P aliases the first 32 columns of each), O at 128..191
+
+template <bool F16>
+__global__ void __launch_bounds__(FL_THREADS, 2)
+attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                      float* __restrict__ lse, int S, int H, float scale_log2, int has_o2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                        // [128][64], reused as O staging
+  uint8_t* sRing = sQ + 16384;               // FL_RING x (K block [64][64] 8 KB | V block 8 KB)
+  uint8_t* sO2 = sRing + FL_RING * 16384;    // 16 KB staging of the optional bf16 copy of O
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO2 + 16384);
+  uint64_t* bar_q = bars;                    // Q landed
+  uint64_t* ring_full = bars + 1;            // [FL_RING]
+  uint64_t* ring_free = bars + 1 + FL_RING;  // [FL_RING]
+  uint64_t* bar_s = bars + 1 + 2 * FL_RING;  // [2] S buffer complete
+  uint64_t* bar_p = bar_s + 2;               // P written / O rescaled (4 warp arrivals)
+  uint64_t* bar_o = bar_p + 1;               // P.V of the block complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, mt = blockIdx.y;
+  const int b = bh / H, h = bh % H;
+  const int n_kb = (S + 63) >> 6;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmO);
+      mbar_init(bar_q, 1);
+      for (int i = 0; i < FL_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_free[i], 1); }
+      mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+
+  if (warp == 5) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      griddep_wait();
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_3d(sQ, &tmQ, bar_q, h * 64, mt * 128, b);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int sl = kb % FL_RING;
+        if (kb >= FL_RING) mbar_wait(&ring_free[sl], (uint32_t)(((kb / FL_RING) - 1) & 1));
+        mbar_arrive_expect_tx(&ring_full[sl], 16384);
+        tma_load_3d(sRing + sl * 16384, &tmKV, &ring_full[sl], (H + h) * 64, kb * 64, b);
+        tma_load_3d(sRing + sl * 16384 + 8192, &tmKV, &ring_full[sl], (2 * H + h) * 64, kb * 64, b);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const uint32_t fmt = F16 ? 0u : 1u;
+      const uint32_t qa = smem_u32(sQ);
+      auto keys_of = [&](int kb) { return min(64, S - 64 * kb); };
+      auto issue_s = [&](int kb) {
+        const int sl = kb % FL_RING;
+        mbar_wait(&ring_full[sl], (uint32_t)((kb / FL_RING) & 1));
+        tc_fence_after();
+        const uint32_t ka = smem_u32(sRing + sl * 16384);
+        const uint32_t idesc = make_idesc2(fmt, fmt, 128, (uint32_t)((keys_of(kb) + 15) & ~15), 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + (uint32_t)((kb & 1) * 64), make_smem_desc_sw128(qa + k * 32, 0u, 1024u),
+                    make_smem_desc_sw128(ka + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+        umma_commit(&bar_s[kb & 1]);
+      };
+      const uint32_t idesc_o = make_idesc2(fmt, fmt, 128, 64, 0, 1);
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      if (n_kb > 1) issue_s(1);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(bar_p, (uint32_t)(kb & 1));
+        tc_fence_after();
+        const uint32_t va = smem_u32(sRing + (kb % FL_RING) * 16384 + 8192);
+        const int ksteps = ((keys_of(kb) + 15) & ~15) / 16;
+        for (int k = 0; k < ksteps; ++k)
+          umma_f16_ts(tmem_base + FL_O_COL, tmem_base + (uint32_t)((kb & 1) * 64 + k * 8),
+                      make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&ring_free[kb % FL_RING]);  // K (used by S) and V of this block are spent
+        umma_commit(bar_o);
+        if (kb + 2 < n_kb) issue_s(kb + 2);     // reuses S buffer kb & 1: ordered behind the P.V just issued
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax warps
+    griddep_wait();
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f;  // running maximum (raw score units) and sum for this thread's query row
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int keys = min(64, S - 64 * kb);
+      const int nk = (keys + 15) & ~15;
+      const uint32_t sbuf = trow + (uint32_t)((kb & 1) * 64);
+      mbar_wait(&bar_s[kb & 1], (uint32_t)((kb >> 1) & 1));
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(sbuf, v0);
+      if (nk > 32) tmem_ld32(sbuf + 32u, v1);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < keys) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(v0[k]));
+      if (nk > 32) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (32 + k < keys) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(v1[k]));
+      }
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      const float mc = m_new * scale_log2;
+      const float alpha = fast_exp2(m_run * scale_log2 - mc);  // 0 on the first block (m_run = -inf)
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float p0 = (2 * k < keys) ? fast_exp2(fmaf(__uint_as_float(v0[2 * k]), scale_log2, -mc)) : 0.f;
+        const float p1 = (2 * k + 1 < keys) ? fast_exp2(fmaf(__uint_as_float(v0[2 * k + 1]), scale_log2, -mc)) : 0.f;
+        s4[k & 3] += p0 + p1;
+        pk[k] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
+      }
+      if (nk > 32) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = (32 + 2 * k < keys) ? fast_exp2(fmaf(__uint_as_float(v1[2 * k]), scale_log2, -mc)) : 0.f;
+          const float p1 = (33 + 2 * k < keys) ? fast_exp2(fmaf(__uint_as_float(v1[2 * k + 1]), scale_log2, -mc)) : 0.f;
+          s4[k & 3] += p0 + p1;
+          pk[16 + k] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int k = 16; k < 32; ++k) pk[k] = 0u;
+      }
+      l_run = l_run * alpha + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      m_run = m_new;
+      // P (packed 16-bit) over the first 32 columns of this S buffer
+      {
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo[k] = pk[k]; hi[k] = pk[16 + k]; }
+        tmem_st16(sbuf, lo);
+        if (nk > 32) tmem_st16(sbuf + 16u, hi);
+      }
+      if (kb > 0) {
+        // O so far belongs to the old maximum: wait for the previous P.V, rescale rows whose maximum moved
+        mbar_wait(bar_o, (uint32_t)((kb - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha < 1.0f)) {
+          uint32_t o0[32], o1[32];
+          tmem_ld32(trow + FL_O_COL, o0);
+          tmem_ld32(trow + FL_O_COL + 32u, o1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            o0[k] = __float_as_uint(__uint_as_float(o0[k]) * alpha);
+            o1[k] = __float_as_uint(__uint_as_float(o1[k]) * alpha);
+          }
+          uint32_t t[16];
+#pragma unroll
+          for (int part = 0; part < 4; ++part) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) t[k] = part < 2 ? o0[(part & 1) * 16 + k] : o1[(part & 1) * 16 + k];
+            tmem_st16(trow + FL_O_COL + (uint32_t)(part * 16), t);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    // ---- epilogue
+    const int row = mt * 128 + warp * 32 + lane;
+    if (row < S) lse[(long long)bh * S + row] = (m_run * scale_log2 + log2f(l_run)) * FA_LN2;
+    const float inv = 1.f / l_run;
+    mbar_wait(bar_o, (uint32_t)((n_kb - 1) & 1));
+    tc_fence_after();
+    float o[64];
+    {
+      uint32_t v0[32], v1[32];
+      tmem_ld32(trow + FL_O_COL, v0);
+      tmem_ld32(trow + FL_O_COL + 32u, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { o[k] = __uint_as_float(v0[k]) * inv; o[32 + k] = __uint_as_float(v1[k]) * inv; }
+    }
+    if (mt * 128 + warp * 32 < S) {
+      uint8_t* st = sQ + warp * 4096;  // Q is spent: every S MMA has completed (the last bar_o follows them)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 w;
+        if (F16)
+          w = make_uint4(pack_f16(o[8 * j], o[8 * j + 1]), pack_f16(o[8 * j + 2], o[8 * j + 3]),
+                         pack_f16(o[8 * j + 4], o[8 * j + 5]), pack_f16(o[8 * j + 6], o[8 * j + 7]));
+        else
+          w = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                         pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+        *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = w;
+      }
+      uint8_t* st2 = sO2 + warp * 4096;
+      if (has_o2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(st2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                         pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        fa_tma_store_3d(&tmO, st, h * 64, mt * 128 + warp * 32, b);
+        if (has_o2) fa_tma_store_3d(&tmO2, st2, h * 64, mt * 128 + warp * 32, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 static int fa_encode(CUtensorMap* map, const void* base, int is_f16, long long inner, long long rows, long long images,
                      int box_rows, int box_cols = 64) {
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)images};
@@ -1129,6 +1370,53 @@ int attn_bwd_tc_mb(const void* qkv, int qkv_is_f16, const void* o, const void* d
   MFV_LAUNCH_CHECK();
   attn_dq_convert_kernel<<<(unsigned)((rows * H * 8 + 255) / 256), 256, 0, st>>>(
       dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), rows, (int)H);
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+// Long sequences (S > 256): flash-style kernel, one CTA per (image, head, 128-query tile).
+int attn_fwd_tc_mb(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
+                   long long S, long long H, float scale, cudaStream_t st) {
+  if (o_is_f16 != qkv_is_f16) return MFV_ERR_ARG;
+  CUtensorMap tmQ, tmKV, tmO, tmO2;
+  int rc;
+  if ((rc = fa_encode(&tmQ, qkv, qkv_is_f16, 3 * H * 64, S, NB, 128))) return rc;
+  if ((rc = fa_encode(&tmKV, qkv, qkv_is_f16, 3 * H * 64, S, NB, 64))) return rc;
+  if ((rc = fa_encode(&tmO, o, o_is_f16, H * 64, S, NB, 32))) return rc;
+  tmO2 = tmO;
+  if (o_bf16_copy && (rc = fa_encode(&tmO2, o_bf16_copy, 0, H * 64, S, NB, 32))) return rc;
+  const size_t smem = 1024 + 16384 + FL_RING * 16384 + 16384 + 256;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(NB * H), (unsigned)((S + 127) / 128));
+  cfg.blockDim = dim3(FL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const float sl2 = scale * FA_LOG2E;
+  const int has_o2 = o_bf16_copy != nullptr;
+  if (qkv_is_f16) {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_mb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_mb_kernel<true>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, sl2, has_o2));
+  } else {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_mb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_mb_kernel<false>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, sl2, has_o2));
+  }
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
