@@ -4,6 +4,7 @@
 // softmax, quad shuffles only).  Scores never touch HBM; the backward recomputes them from the saved log-sum-exp.
 // Tensor-core path: mma.sync.m16n8k16 bf16 with ldmatrix from XOR-swizzled smem (the attention FLOPs are <8 % of the
 // step; the dense contractions live in gemm.cu on tcgen05).
+#include <stdlib.h>
 #include "common.cuh"
 #include "mfvit_internal.h"
 
@@ -462,7 +463,14 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
   using namespace mfv;
   if (NB <= 0 || S <= 0 || H <= 0 || (D != 64 && D != 32)) return MFV_ERR_SHAPE;
   if (D == 64 && (o_is_f16 != 0) == (qkv_is_f16 != 0) && !legacy_attention()) {
-    if (S <= 256)
+    // The flash-style kernel (64-key blocks, S double-buffered in TMEM, one TMEM read per score) is also the faster
+    // one at S = 197 (23.5 vs 28.7 us in fp16 mode); MFVIT_ATTN_FLASH=0 selects the single-shot kernel for S <= 256.
+    static int flash_all = -1;
+    if (flash_all < 0) {
+      const char* e = getenv("MFVIT_ATTN_FLASH");
+      flash_all = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (S <= 256 && !flash_all)
       return attn_fwd_tc(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
                          reinterpret_cast<cudaStream_t>(stream));
     return attn_fwd_tc_mb(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
