@@ -382,6 +382,33 @@ __device__ __forceinline__ void gelu_erf_both2(float xa, float xb, f32x2& g, f32
   dg = fma2(mul2(x, splat2(0.39894228040143267794f)), pack2(e0, e1), cdf);
 }
 
+// Backward-only variant with ONE MUFU per element: Phi(x) = 1/2 + 1/2 tanh(x H(x^2)) (the same logistic polynomial, halved)
+// and phi(x) = Phi'(x) = 1/2 (1 - t^2) d/dx[x H(x^2)] evaluated as a second polynomial - no ex2 / rcp.  The GELU' epilogue
+// is bound by the XU pipe (MUFU and F2FP share it at 8 cycles per warp instruction: 3 MUFU + 1 F2FP-equivalent per
+// element = 21 us for the fc2 dgrad); this form needs 1 MUFU.  tanh.approx has 2^-11 relative error: |dg| error <= 3e-3
+// and |g| error <= 2.4e-4 |x|, both below the bf16 rounding of the stored values - not used in the forward.
+__device__ __forceinline__ void gelu_tanh_both2(float xa, float xb, f32x2& g, f32x2& dg) {
+  const f32x2 x = pack2(xa, xb);
+  const f32x2 x2 = mul2(x, x);
+  f32x2 hh = fma2(splat2(1.1190779787284555e-06f), x2, splat2(-3.058092624996789e-05f));
+  hh = fma2(hh, x2, splat2(-0.00012486183550208807f));
+  hh = fma2(hh, x2, splat2(0.03646879270672798f));
+  hh = fma2(hh, x2, splat2(0.7978281378746033f));
+  float a0, a1, t0, t1;
+  unpack2(mul2(hh, x), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  const f32x2 t = pack2(t0, t1);
+  f32x2 dd = fma2(splat2(5.035850790591212e-06f), x2, splat2(-0.0001070332364179194f));
+  dd = fma2(dd, x2, splat2(-0.00031215461785905063f));
+  dd = fma2(dd, x2, splat2(0.05470318719744682f));
+  dd = fma2(dd, x2, splat2(0.39891406893730164f));
+  const f32x2 sig = fma2(splat2(0.5f), t, splat2(0.5f));
+  const f32x2 om = fma2(mul2(t, splat2(-1.0f)), t, splat2(1.0f));  // 1 - t^2
+  g = mul2(x, sig);
+  dg = fma2(mul2(x, om), dd, sig);
+}
+
 // same, with independent A / B element formats (0 = fp16, 1 = bf16): kind::f16 accepts mixed 16-bit operands
 __host__ __device__ constexpr uint32_t make_idesc2(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N,
                                                    uint32_t a_mn_major, uint32_t b_mn_major) {

@@ -454,7 +454,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int k = 0; k < 4; ++k) {
                 const float2 u2 = unpack_bf16(uw[k]);
                 f32x2 gg, dd;
-                gelu_erf_both2(u2.x, u2.y, gg, dd);
+                gelu_tanh_both2(u2.x, u2.y, gg, dd);
                 float g0, g1, d0, d1;
                 unpack2(gg, g0, g1);
                 unpack2(mul2(pack2(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]), dd), d0, d1);
