@@ -315,6 +315,39 @@ def main():
     e2e_ms = e_start.elapsed_time(e_end)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- timed: the same loop fed by the paired uint8 input pipeline (mfvit.data): pinned uint8
+    # store -> host gather -> H2D of uint8 -> flip / rotate / crop / normalise kernel -> step -> loss read back
+    from mfvit.data import PairedDeviceLoader, PairedU8Store
+    gu = torch.Generator().manual_seed(4096 + rank)
+    n_store = (8 if img <= 224 else 3) * B
+    store = PairedU8Store(torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
+                          torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
+                          torch.randint(0, 3, (n_store,), generator=gu))
+    loader = PairedDeviceLoader(store, B, crop=img, degrees=True, training=True, device=device, seed=rank, drop_last=True)
+
+    def loader_batches(n):
+        done, epoch = 0, 0
+        while done < n:
+            loader.set_epoch(epoch)
+            for batch in loader:
+                yield batch
+                done += 1
+                if done == n:
+                    return
+            epoch += 1
+
+    for xc, xe, y in loader_batches(2):
+        trainer.step(xc, xe, y)
+    barrier()
+    u_start, u_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u_start.record()
+    for xc, xe, y in loader_batches(e_steps):
+        loss_u = trainer.step(xc, xe, y)
+        loss_host = float(loss_u)
+    u_end.record()
+    barrier()
+    u8_ms = u_start.elapsed_time(u_end)
+
     # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps; the library serialises the
     # weight-gradient side stream while profiling so that every class time is that class alone
     breakdown, dominant = {}, None
@@ -335,9 +368,9 @@ def main():
                                                                   "launches_per_step": cnt[i] / psteps}
         dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else None
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([elapsed_ms, e2e_ms, u8_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        elapsed_ms, e2e_ms, u8_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks = measured_peaks()
@@ -378,6 +411,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / e_steps},
+            "e2e_u8_loader": {"value": pairs * e_steps / (u8_ms * 1e-3), "unit": UNIT,
+                              "h2d_bytes_per_step": loader.h2d_bytes_per_batch, "d2h_bytes_per_step": 4,
+                              "ms_per_step": u8_ms / e_steps,
+                              "path": "pinned uint8 store -> gather -> H2D -> mfv_augment_u8 (flip, +-1 deg rotation, "
+                                      "crop, normalise) x 2 -> step; not the headline e2e (that one copies the float32 "
+                                      "tensors the reference's loaders produce)"},
             "gpu_launches": launches,
             "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches
                            if use_graph else "eager stream launches",

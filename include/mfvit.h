@@ -305,6 +305,27 @@ int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, v
                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
                   int64_t step, void* stream);
 
+/* ---- paired input pipeline, device side -----------------------------------------------------------
+ * Replaces the per-sample torchvision transform of the training loaders (image_transform.py:50-84 composed at
+ * MAIN_CA:524-531, applied at loader.py:127-129): RandomHorizontalFlip -> RandomRotation (nearest, Pillow's 16.16
+ * fixed-point inverse map) -> RandomCrop / CenterCrop -> ToTensor -> Normalize, bit-identical to the eager sequence.
+ * src uint8 [B][Hs][Ws][3] (the decoded + resized image), out f32 [B][3][crop][crop]; crop % 4 == 0.
+ * params int32 [B][MFV_AUG_PARAMS] on the device: {flip, rotate, a0, a1, a2, a3, a4, a5, top, left, 0, 0}; with rotate != 0
+ * the source pixel of rotated (x, y) is ((a2 + y*a1 + x*a0) >> 16, (a5 + y*a4 + x*a3) >> 16), outside the image -> 0.
+ * mean3 / std3: f32 [3] on the device.                                                                                */
+#define MFV_AUG_PARAMS 12
+int mfv_augment_u8(const void* src_u8, const int32_t* params, const float* mean3, const float* std3, float* out,
+                   int64_t B, int64_t Hs, int64_t Ws, int64_t crop, void* stream);
+
+/* ---- epoch metrics kept on the device -------------------------------------------------------------
+ * Replaces the per-iteration `.item()` / `.cpu()` reads of MAIN_CA:884-899: logits = a + b + c (b, c optional),
+ * loss_sum f64 [1] += loss[0] * rows, counters i64 [3] = {rows seen, argmax == target, rows dropped for capacity};
+ * row i of this call goes to slot counters[0] + i of vals f32 [capacity][NC], preds / gts i32 [capacity].  The host
+ * reads the buffers once per epoch (ROC AUC needs all scores) and zeroes loss_sum / counters.                          */
+int mfv_epoch_metrics(const float* a, const float* b, const float* c, const int64_t* target, const float* loss,
+                      int64_t rows, int64_t NC, double* loss_sum, int64_t* counters, int64_t capacity, float* vals,
+                      int32_t* preds, int32_t* gts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,8 @@ SIGNATURES = {
     "mfv_linear_small_fwd": (C.c_int, [c_vp, i64, c_vp, c_vp, c_vp, i64, i64, i64, c_vp]),
     "mfv_linear_small_bwd": (C.c_int, [c_vp, i64, c_vp, c_vp, c_vp, i64, c_vp, c_vp, i64, i64, i64, c_vp]),
     "mfv_ce_small": (C.c_int, [c_vp] * 6 + [i64, i64, c_vp]),
+    "mfv_augment_u8": (C.c_int, [c_vp] * 5 + [i64, i64, i64, i64, c_vp]),
+    "mfv_epoch_metrics": (C.c_int, [c_vp] * 5 + [i64, i64, c_vp, c_vp, i64, c_vp, c_vp, c_vp, c_vp]),
     "mfv_ema_update": (C.c_int, [c_vp, i64, i64, f32, f32, c_vp]),
     "mfv_infonce_fwd": (C.c_int, [c_vp] * 8 + [i64, i64, i64, f32, c_vp]),
     "mfv_infonce_bwd": (C.c_int, [c_vp] * 8 + [i64, i64, f32, c_vp, i64, i64, i64, f32, c_vp]),

@@ -237,6 +237,27 @@ def ce_small(a, b, c, target, want_grad=True):
     return loss, dl
 
 
+def augment_u8(src_u8, params, mean3, std3, crop, out=None):
+    """src uint8 [B][Hs][Ws][3], params int32 [B][12] (mfvit.data.pack_params) -> normalised f32 [B][3][crop][crop]."""
+    B, Hs, Ws, ch = src_u8.shape
+    if ch != 3 or src_u8.dtype != torch.uint8 or not src_u8.is_contiguous():
+        raise MfvError("augment_u8 wants a contiguous uint8 [B][H][W][3] batch")
+    if params.dtype != torch.int32 or tuple(params.shape) != (B, 12) or not params.is_contiguous():
+        raise MfvError("augment_u8 wants int32 [B][12] parameters")
+    if out is None:
+        out = torch.empty(B, 3, crop, crop, device=src_u8.device, dtype=torch.float32)
+    check(_lib_for(src_u8).mfv_augment_u8(_p(src_u8), _p(params), _p(mean3), _p(std3), _p(out), B, Hs, Ws, crop,
+                                          _stream()), "mfv_augment_u8")
+    return out
+
+
+def epoch_metrics_(a, b, c, target, loss, loss_sum, counters, vals, preds, gts):
+    rows, NC = a.shape
+    check(_lib_for(a).mfv_epoch_metrics(_p(a), _p(b), _p(c), _p(target), _p(loss), rows, NC, _p(loss_sum),
+                                        _p(counters), vals.shape[0], _p(vals), _p(preds), _p(gts), _stream()),
+          "mfv_epoch_metrics")
+
+
 def infonce_fwd(q_raw, k_raw, queue, T):
     N, D = q_raw.shape
     K = queue.shape[1]

@@ -45,8 +45,9 @@ class FlatParams:
 
 class MFViTCATrainer:
     def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
-                 train_backbones=True):
+                 train_backbones=True, metrics=None):
         self.fusion, self.vits = fusion, (vit_cxr, vit_enh)
+        self.metrics = metrics      # mfvit.data.EpochMetrics: loss / hits / scores accumulated on the device per step
         self.lr, self.momentum, self.wd = lr, momentum, weight_decay
         self.pg = process_group
         self.train_backbones = train_backbones
@@ -200,6 +201,8 @@ class MFViTCATrainer:
 
     def _step_eager(self, img_cxr, img_enh, target):
         loss, grad = self.forward_backward(img_cxr, img_enh, target, reduce_async=True)
+        if self.metrics is not None:  # MAIN_CA:884-899 without the host round trips
+            self.metrics.accumulate(*self.logits(), target, loss)
         self.all_reduce(grad)
         self.optimizer_step(grad)
         return loss
@@ -247,6 +250,8 @@ class MFViTCATrainer:
         for dst, src in zip((eng.master, self._mom_engine, self._small.master, self._mom_small), snap):
             dst.copy_(src)
         ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1), eng.shadow16.view(-1) if eng.fwd_f16 else None)
+        if self.metrics is not None:
+            self.metrics.reset()  # the warm-up steps are not part of the epoch
         self.steps = max(steps0, 1)  # the captured step is a steady-state one (momentum buffers exist)
         eng.shadow_fresh = True
         self._graph = graph

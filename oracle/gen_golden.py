@@ -115,9 +115,41 @@ def gen_moco():
                 "keys": sorted(full.state_dict().keys())}, os.path.join(OUT, "moco_keys.pt"))
 
 
+def gen_augment():
+    """The reference's own transform lists (image_transform.get_transform_type, image_transform.py:50-84) composed as
+    MAIN_CA:524-531 does, run on seeded uint8 images with torch's global RNG seeded per case."""
+    import importlib.util
+
+    import numpy as np
+    import torchvision.transforms as T
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location(
+        "ref_image_transform", "/root/reference/moco_pretraining/moco/aihc_utils/image_transform.py")
+    it = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(it)
+    rng = np.random.default_rng(99)
+    cases = []
+    for i, (h, w, crop, rotate, img_type) in enumerate([
+            (64, 64, 64, False, "data"), (64, 64, 64, True, "Train_Mix"), (72, 80, 64, True, "data"),
+            (80, 72, 48, 5, "Train_Mix"), (64, 64, 48, 30, "CheXpert_Enh"), (96, 96, 64, True, "CheXpert-v1.0-small")]):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        # the stored image is already resized: Resize(shorter side) in front of the list returns it unchanged
+        args = SimpleNamespace(maintain_ratio=True, img_size=min(h, w), rotate=rotate, crop=crop)
+        out = {}
+        for training in (True, False):
+            tf = T.Compose(it.get_transform_type(args, training=training, img_type=img_type))
+            seed = 700 + i
+            torch.manual_seed(seed)
+            out["train" if training else "eval"] = tf(Image.fromarray(img)).clone()
+        cases.append({"img": torch.from_numpy(img), "crop": crop, "rotate": rotate, "img_type": img_type, "seed": seed,
+                      "train": out["train"], "eval": out["eval"]})
+    torch.save(cases, os.path.join(OUT, "augment_ref.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_fusion()
     gen_moco()
+    gen_augment()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
