@@ -237,7 +237,9 @@ def main():
         E.reference_head_init_(v)
     fus = fm.Fus_CrossViT(cxr, enh)
     cxr.to(device), enh.to(device), fus.to(device)
-    trainer = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, weight_decay=0.0)
+    from mfvit.data import EpochMetrics
+    metrics = EpochMetrics(capacity=B * max(args.steps, 1), num_classes=3, device=device)
+    trainer = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, weight_decay=0.0, metrics=metrics)
 
     # synthetic data: 4 rotating batches per rank, pinned host copies for the end-to-end leg
     nb = 4
@@ -324,6 +326,8 @@ def main():
                           torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
                           torch.randint(0, 3, (n_store,), generator=gu))
     loader = PairedDeviceLoader(store, B, crop=img, degrees=True, training=True, device=device, seed=rank, drop_last=True)
+    if trainer.input_buffers() is not None:
+        loader.bind_outputs(*trainer.input_buffers())
 
     def loader_batches(n):
         done, epoch = 0, 0
@@ -347,6 +351,17 @@ def main():
     u_end.record()
     barrier()
     u8_ms = u_start.elapsed_time(u_end)
+    # the same loop the way the pipeline is meant to be driven: loss / hits / scores accumulate on the device
+    # (mfv_epoch_metrics inside the captured step), one device -> host read at the end of the pass
+    metrics.reset()
+    barrier()
+    u_start.record()
+    for xc, xe, y in loader_batches(e_steps):
+        trainer.step(xc, xe, y)
+    ep_loss, ep_auc, ep_acc = metrics.result()
+    u_end.record()
+    barrier()
+    u8_nosync_ms = u_start.elapsed_time(u_end)
 
     # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps; the library serialises the
     # weight-gradient side stream while profiling so that every class time is that class alone
@@ -368,9 +383,9 @@ def main():
                                                                   "launches_per_step": cnt[i] / psteps}
         dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else None
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, u8_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, u8_ms = float(t[0]), float(t[1]), float(t[2])
+        elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms = (float(v) for v in t)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -414,6 +429,9 @@ def main():
             "e2e_u8_loader": {"value": pairs * e_steps / (u8_ms * 1e-3), "unit": UNIT,
                               "h2d_bytes_per_step": loader.h2d_bytes_per_batch, "d2h_bytes_per_step": 4,
                               "ms_per_step": u8_ms / e_steps,
+                              "value_epoch_metrics_on_device": pairs * e_steps / (u8_nosync_ms * 1e-3),
+                              "epoch_metrics": {"loss": ep_loss, "auc": ep_auc, "acc": ep_acc,
+                                                "d2h": "once per pass (loss sum, hit count, scores for the AUC)"},
                               "path": "pinned uint8 store -> gather -> H2D -> mfv_augment_u8 (flip, +-1 deg rotation, "
                                       "crop, normalise) x 2 -> step; not the headline e2e (that one copies the float32 "
                                       "tensors the reference's loaders produce)"},

@@ -90,6 +90,21 @@ def draw_train_params(n, h, w, crop, degrees, generator=None):
     return out
 
 
+def draw_train_params_batch(n, h, w, crop, degrees, generator=None):
+    """The same distributions drawn a batch at a time (flips, then angles, then window rows, then window columns): four
+    generator calls per batch instead of up to four per sample, which is what keeps the loader's worker thread off the
+    GIL.  (A multi-worker DataLoader has no reproducible per-sample stream to follow in the first place.)"""
+    deg = float(degrees)
+    flips = (torch.rand(n, generator=generator) < 0.5).tolist()
+    angles = torch.empty(n, dtype=torch.float32).uniform_(-deg, deg, generator=generator).tolist()
+    if crop == 0 or (h == crop and w == crop):
+        tops = lefts = [0] * n
+    else:
+        tops = torch.randint(0, h - crop + 1, size=(n,), generator=generator).tolist()
+        lefts = torch.randint(0, w - crop + 1, size=(n,), generator=generator).tolist()
+    return list(zip(flips, angles, tops, lefts))
+
+
 def eval_params(n, h, w, crop):
     top, left = (int(round((h - crop) / 2.0)), int(round((w - crop) / 2.0))) if crop else (0, 0)  # CenterCrop
     return [(False, 0.0, top, left)] * n
@@ -146,7 +161,9 @@ class PairedU8Store:
         import cv2
         from PIL import Image
         cxr, enh, labels = [], [], []
-        size = img_size if maintain_ratio else (img_size, img_size)
+        if maintain_ratio:
+            raise MfvError("the uint8 store holds one H x W for every image: resize with maintain_ratio=False")
+        size = (img_size, img_size)
         import torchvision.transforms as T
         resize = T.Resize(size)
         with open(img_csv) as f:
@@ -162,6 +179,16 @@ class PairedU8Store:
                 enh.append(pair[1])
                 labels.append(int(float(fields[-2])))
         return cls(np.stack(cxr), np.stack(enh), np.asarray(labels))
+
+
+def _gather_rows(src, idx, dst):
+    """dst[j] = src[idx[j]] for uint8 image stacks: whole rows moved as 8-byte words (index_select on uint8 goes byte by
+    byte and is ~250x slower)."""
+    row = src[0].numel()
+    if row % 8 == 0:
+        torch.index_select(src.view(len(src), row).view(torch.int64), 0, idx, out=dst.view(len(dst), row).view(torch.int64))
+    else:
+        np.take(src.numpy(), idx.numpy(), axis=0, out=dst.numpy())
 
 
 class _Slot:
@@ -189,6 +216,8 @@ class PairedDeviceLoader:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise MfvError("PairedDeviceLoader runs its transforms on the GPU; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.shuffle, self.seed, self.rank, self.world, self.drop_last = shuffle, seed, rank, world_size, drop_last
         self.epoch = 0
         _, self.H, self.W, _ = store.cxr.shape
@@ -200,6 +229,7 @@ class PairedDeviceLoader:
             self.stats.append((torch.tensor(mean, dtype=torch.float32, device=self.device),
                                torch.tensor(std, dtype=torch.float32, device=self.device)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.into = None
         self.slots = [_Slot(batch_size, self.H, self.W, crop, self.device, True) for _ in range(3)]
         self.h2d_bytes_per_batch = 2 * batch_size * self.H * self.W * 3 + 2 * batch_size * N_PARAMS * 4 + 8 * batch_size
 
@@ -215,11 +245,11 @@ class PairedDeviceLoader:
         n = len(idx)
         if slot.used:
             slot.copied.synchronize()  # the previous H2D out of this staging buffer is done
-        torch.index_select(self.store.cxr, 0, idx, out=slot.h_cxr[:n])
-        torch.index_select(self.store.enh, 0, idx, out=slot.h_enh[:n])
+        _gather_rows(self.store.cxr, idx, slot.h_cxr[:n])
+        _gather_rows(self.store.enh, idx, slot.h_enh[:n])
         slot.h_lab[:n] = self.store.labels[idx]
         for t in range(2):  # each image type draws its own flip / angle / window, as two transform calls would
-            samples = (draw_train_params(n, self.H, self.W, self.crop, self.degrees, gen) if self.training
+            samples = (draw_train_params_batch(n, self.H, self.W, self.crop, self.degrees, gen) if self.training
                        else eval_params(n, self.H, self.W, self.crop))
             pack_params(samples, self.W, self.H, out=slot.h_par[t])
         with torch.cuda.stream(self.copy_stream):
@@ -232,15 +262,23 @@ class PairedDeviceLoader:
             slot.copied.record(self.copy_stream)
         slot.n, slot.used = n, True
 
+    def bind_outputs(self, img_cxr, img_enh, target):
+        """Write every batch straight into these device tensors (e.g. MFViTCATrainer.input_buffers(), the static inputs
+        of the captured step) instead of the loader's own output slots."""
+        self.into = (img_cxr, img_enh, target)
+
     def _finish(self, slot):
         """Device transform on the caller's stream."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(slot.copied)
         n = slot.n
+        outs = self.into if self.into is not None else (slot.out[0], slot.out[1], slot.d_lab)
         for t, (src, (mean, std)) in enumerate(zip((slot.d_cxr, slot.d_enh), self.stats)):
-            ops.augment_u8(src[:n], slot.d_par[t, :n], mean, std, self.crop, out=slot.out[t][:n])
+            ops.augment_u8(src[:n], slot.d_par[t, :n], mean, std, self.crop, out=outs[t][:n])
+        if self.into is not None:
+            outs[2][:n].copy_(slot.d_lab[:n], non_blocking=True)
         slot.consumed.record(cur)
-        return slot.out[0][:n], slot.out[1][:n], slot.d_lab[:n]
+        return outs[0][:n], outs[1][:n], outs[2][:n]
 
     def __iter__(self):
         idx = shard_indices(len(self.store), self.epoch, self.seed, self.shuffle, self.rank, self.world, self.drop_last)

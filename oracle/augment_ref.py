@@ -93,6 +93,18 @@ def draw_train(h, w, crop, degrees):
     return flip, angle, top, left
 
 
+def draw_train_batch(n, h, w, crop, degrees):
+    """The loader's batched draw order (mfvit.data.draw_train_params_batch): same distributions, drawn per batch."""
+    flips = [bool(v) for v in (torch.rand(n) < 0.5)]
+    angles = [float(v) for v in torch.empty(n).uniform_(-float(degrees), float(degrees))]
+    if crop == 0 or (h == crop and w == crop):
+        tops = lefts = [0] * n
+    else:
+        tops = [int(v) for v in torch.randint(0, h - crop + 1, size=(n,))]
+        lefts = [int(v) for v in torch.randint(0, w - crop + 1, size=(n,))]
+    return list(zip(flips, angles, tops, lefts))
+
+
 def center_crop_offsets(h, w, crop):
     return int(round((h - crop) / 2.0)), int(round((w - crop) / 2.0))
 

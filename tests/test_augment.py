@@ -66,6 +66,12 @@ def test_host_draws_and_coefficients_follow_the_oracle():
             assert row[0] == int(flip) and row[8] == top and row[9] == left
             assert row[1] == (0 if fixed is None else 1)
             assert tuple(row[2:8]) == (fixed if fixed is not None else (0,) * 6)
+    gen = torch.Generator()
+    gen.manual_seed(77)
+    ours = data.draw_train_params_batch(33, 72, 80, 64, 5, gen)
+    torch.manual_seed(77)
+    assert ours == A.draw_train_batch(33, 72, 80, 64, 5)
+    assert {f for f, _, _, _ in ours} == {True, False} and all(-5 <= a <= 5 and 0 <= t <= 8 and 0 <= l <= 16 for _, a, t, l in ours)
     assert data.eval_params(2, 256, 240, 224) == [(False, 0.0, *A.center_crop_offsets(256, 240, 224))] * 2
     assert data.STATS == A.STATS
     with pytest.raises(data.MfvError):
@@ -97,6 +103,12 @@ def test_store_validates_and_loader_refuses_cpu():
         data.PairedU8Store(u8.float(), u8, [0, 1, 2, 1], pin=False)
     with pytest.raises(data.MfvError):
         data.PairedDeviceLoader(store, 2, crop=8, device="cpu")
+    for shape in [(40, 24, 24, 3), (10, 5, 7, 3)]:  # row bytes divisible by 8 (word gather) and not (byte gather)
+        st = torch.randint(0, 256, shape, dtype=torch.uint8)
+        idx = torch.randperm(shape[0])[:4]
+        dst = torch.zeros(6, *shape[1:], dtype=torch.uint8)
+        data._gather_rows(st, idx, dst[:4])
+        assert torch.equal(dst[:4], st[idx]) and int(dst[4:].sum()) == 0
 
 
 def test_auc_matches_pairwise_definition_and_sklearn():
@@ -181,17 +193,23 @@ def test_paired_loader_yields_aligned_transformed_pairs():
         xc, xe = xc.cpu(), xe.cpu()
         for src, got, t in ((cxr, xc, "data"), (enh, xe, "Train_Mix")):
             mean, std = A.STATS[t]
+            drawn = A.draw_train_batch(len(ids), H, W, crop, True)
             for j, i in enumerate(ids):
-                flip, angle, top, left = A.draw_train(H, W, crop, True)
+                flip, angle, top, left = drawn[j]
                 want = A.to_tensor_normalize(A.apply_u8(src[i], flip, A.rotation_fixed(angle, W, H), top, left, crop), mean, std)
                 assert torch.equal(got[j], want), (bi, j, t)
         seen += ids
     assert sorted(seen) == list(range(N))  # one pass, every pair once, both types indexed by the same permutation
-    # eval mode: centre crop, no randomness, natural order
+    # eval mode: centre crop, no randomness, natural order; written straight into caller-owned buffers
     ev = data.PairedDeviceLoader(store, B, crop=crop, training=False, shuffle=False)
-    xc, xe, y = next(iter(ev))
+    bufs = (torch.zeros(B, 3, crop, crop, device="cuda"), torch.zeros(B, 3, crop, crop, device="cuda"),
+            torch.zeros(B, dtype=torch.int64, device="cuda"))
+    ev.bind_outputs(*bufs)
+    batches = list(ev)
+    xc, xe, y = batches[-1]  # 23 = 8 + 8 + 7: the ragged last batch
+    assert xc.shape[0] == 7 and xc.data_ptr() == bufs[0].data_ptr() and y.cpu().tolist() == [int(v) for v in labels[16:]]
     mean, std = A.STATS["Train_Mix"]
-    assert torch.equal(xe[3].cpu(), A.transform_eval(enh[3], crop, mean, std))
+    assert torch.equal(xe[3].cpu(), A.transform_eval(enh[19], crop, mean, std))
 
 
 @pytest.mark.gpu
@@ -222,3 +240,59 @@ def test_epoch_metrics_accumulate_on_device():
     small.accumulate(a, None, None, t, loss)
     with pytest.raises(data.MfvError):
         small.result()
+
+
+@pytest.mark.gpu
+def test_loader_feeds_the_captured_step_and_metrics_stay_on_device():
+    """uint8 store -> PairedDeviceLoader (bound to the graph's static inputs) -> MFViTCATrainer.step with EpochMetrics:
+    the same losses as the step fed with the oracle-transformed float32 tensors, and the epoch's loss / accuracy / AUC
+    equal to the per-step host computation of MAIN_CA:884-909."""
+    import e2e_common as E
+    from mfvit import data
+    from mfvit.trainer import MFViTCATrainer
+    rng = np.random.default_rng(31)
+    N, B, crop = 16, 8, 224
+    cxr = rng.integers(0, 256, size=(N, crop, crop, 3), dtype=np.uint8)
+    enh = rng.integers(0, 256, size=(N, crop, crop, 3), dtype=np.uint8)
+    labels = rng.integers(0, 3, size=N)
+    store = data.PairedU8Store(cxr, enh, labels)
+    runs = []
+    for use_loader in (True, False):
+        _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=9)
+        metrics = data.EpochMetrics(capacity=N, num_classes=3)
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics)
+        tr.capture_graph(*E.synthetic_pair(B, crop, device="cuda"))
+        assert int(metrics.counters[0]) == 0  # warm-up steps of the capture are not part of the epoch
+        losses, vals = [], []
+        if use_loader:
+            loader = data.PairedDeviceLoader(store, B, crop=crop, degrees=True, training=True, seed=3)
+            loader.bind_outputs(*tr.input_buffers())
+            for xc, xe, y in loader:
+                losses.append(float(tr.step(xc, xe, y)))
+                f, a, b = tr.logits()
+                vals.append(((f + a) + b).cpu().numpy())
+            assert tr.graph_replays == 2
+        else:
+            idx = data.shard_indices(N, 0, 3, True)
+            torch.manual_seed(3 * 1000003)
+            for bi in range(2):
+                ids = idx[bi * B:(bi + 1) * B].tolist()
+                xs = []
+                for src, t in ((cxr, "data"), (enh, "Train_Mix")):
+                    mean, std = A.STATS[t]
+                    drawn = A.draw_train_batch(B, crop, crop, crop, True)
+                    xs.append(torch.stack([A.to_tensor_normalize(
+                        A.apply_u8(src[i], f, A.rotation_fixed(ang, crop, crop), tp, lf, crop), mean, std)
+                        for i, (f, ang, tp, lf) in zip(ids, drawn)]).cuda())
+                y = torch.from_numpy(labels[ids]).cuda()
+                losses.append(float(tr.step(xs[0], xs[1], y)))
+                f, a, b = tr.logits()
+                vals.append(((f + a) + b).cpu().numpy())
+        ep_loss, ep_auc, ep_acc = metrics.result()
+        idx = data.shard_indices(N, 0, 3, True).numpy()
+        acc, auc = A.epoch_metrics(np.concatenate(vals), labels[idx])
+        assert ep_acc == acc and (abs(ep_auc - auc) < 1e-12 or (np.isnan(auc) and np.isnan(ep_auc)))
+        assert abs(ep_loss - sum(l * B for l in losses) / N) < 1e-6
+        runs.append(losses)
+    for a, b in zip(*runs):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), runs  # identical inputs; fp32 reduce-add order may differ
