@@ -326,8 +326,6 @@ def main():
                           torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
                           torch.randint(0, 3, (n_store,), generator=gu))
     loader = PairedDeviceLoader(store, B, crop=img, degrees=True, training=True, device=device, seed=rank, drop_last=True)
-    if trainer.input_buffers() is not None:
-        loader.bind_outputs(*trainer.input_buffers())
 
     def loader_batches(n):
         done, epoch = 0, 0
@@ -433,7 +431,7 @@ def main():
                               "epoch_metrics": {"loss": ep_loss, "auc": ep_auc, "acc": ep_acc,
                                                 "d2h": "once per pass (loss sum, hit count, scores for the AUC)"},
                               "path": "pinned uint8 store -> gather -> H2D -> mfv_augment_u8 (flip, +-1 deg rotation, "
-                                      "crop, normalise) x 2 -> step; not the headline e2e (that one copies the float32 "
+                                      "crop, normalise) x 2 on the copy stream -> step; not the headline e2e (that one copies the float32 "
                                       "tensors the reference's loaders produce)"},
             "gpu_launches": launches,
             "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches

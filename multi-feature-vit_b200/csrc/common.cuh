@@ -36,7 +36,7 @@ void note_error(const char* file, int line, const char* expr);  // remembered fo
       mfv::note_error(__FILE__, __LINE__, "launch"); \
       return (int)_e;                                \
     }                                                \
-    ++mfv::g_launch_count;                           \
+    __atomic_add_fetch(&mfv::g_launch_count, 1ULL, __ATOMIC_RELAXED); /* the loader launches from its own thread */ \
   } while (0)
 
 namespace mfv {

@@ -200,15 +200,17 @@ class _Slot:
         self.d_par = torch.empty(2, B, N_PARAMS, dtype=torch.int32, device=device)
         self.d_lab = torch.empty(B, dtype=torch.int64, device=device)
         self.out = [torch.empty(B, 3, crop, crop, dtype=torch.float32, device=device) for _ in range(2)]
-        self.copied = torch.cuda.Event()    # H2D of this slot finished (copy stream)
-        self.consumed = torch.cuda.Event()  # augment kernels of this slot finished reading the uint8 buffers
+        self.copied = torch.cuda.Event()    # H2D of this slot finished: the pinned staging may be refilled
+        self.ready = torch.cuda.Event()     # transform finished: the float32 batch may be consumed
+        self.consumed = torch.cuda.Event()  # the consumer's work on this slot's outputs is done
         self.n = 0
         self.used = False
 
 
 class PairedDeviceLoader:
-    """Iterates index-aligned (img_cxr, img_enh, target) device batches; the next batches are gathered and copied while
-    the caller works on the current one.  The yielded tensors are reused three batches later."""
+    """Iterates index-aligned (img_cxr, img_enh, target) device batches; the next batches are gathered, copied and
+    transformed on a copy stream while the caller works on the current one.  The yielded tensors are reused three
+    batches later (after the work the caller enqueued on them has finished)."""
 
     def __init__(self, store, batch_size, crop=224, degrees=0, training=True, img_types=("data", "Train_Mix"),
                  device="cuda", shuffle=True, seed=0, rank=0, world_size=1, drop_last=False):
@@ -229,7 +231,6 @@ class PairedDeviceLoader:
             self.stats.append((torch.tensor(mean, dtype=torch.float32, device=self.device),
                                torch.tensor(std, dtype=torch.float32, device=self.device)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.into = None
         self.slots = [_Slot(batch_size, self.H, self.W, crop, self.device, True) for _ in range(3)]
         self.h2d_bytes_per_batch = 2 * batch_size * self.H * self.W * 3 + 2 * batch_size * N_PARAMS * 4 + 8 * batch_size
 
@@ -240,45 +241,36 @@ class PairedDeviceLoader:
         n = len(shard_indices(len(self.store), 0, 0, False, self.rank, self.world, self.drop_last))
         return n // self.B if self.drop_last else (n + self.B - 1) // self.B
 
-    def _stage(self, slot, idx, gen):
-        """Host gather into pinned staging + async H2D on the copy stream."""
+    def _draw(self, n, gen):
+        """int32 [2][n][12]: each image type draws its own flip / angle / window, as two transform calls would."""
+        par = torch.zeros(2, n, N_PARAMS, dtype=torch.int32)
+        for t in range(2):
+            samples = (draw_train_params_batch(n, self.H, self.W, self.crop, self.degrees, gen) if self.training
+                       else eval_params(n, self.H, self.W, self.crop))
+            pack_params(samples, self.W, self.H, out=par[t])
+        return par
+
+    def _stage(self, slot, idx, par):
+        """Worker thread: host gather into pinned staging, H2D and the device transform, all on the copy stream."""
         n = len(idx)
         if slot.used:
             slot.copied.synchronize()  # the previous H2D out of this staging buffer is done
         _gather_rows(self.store.cxr, idx, slot.h_cxr[:n])
         _gather_rows(self.store.enh, idx, slot.h_enh[:n])
         slot.h_lab[:n] = self.store.labels[idx]
-        for t in range(2):  # each image type draws its own flip / angle / window, as two transform calls would
-            samples = (draw_train_params_batch(n, self.H, self.W, self.crop, self.degrees, gen) if self.training
-                       else eval_params(n, self.H, self.W, self.crop))
-            pack_params(samples, self.W, self.H, out=slot.h_par[t])
+        slot.h_par[:, :n] = par
         with torch.cuda.stream(self.copy_stream):
             if slot.used:
-                self.copy_stream.wait_event(slot.consumed)  # last batch's kernels are done with the device buffers
+                self.copy_stream.wait_event(slot.consumed)  # the consumer's kernels are done with this slot's outputs
             slot.d_cxr[:n].copy_(slot.h_cxr[:n], non_blocking=True)
             slot.d_enh[:n].copy_(slot.h_enh[:n], non_blocking=True)
             slot.d_par.copy_(slot.h_par, non_blocking=True)
             slot.d_lab[:n].copy_(slot.h_lab[:n], non_blocking=True)
             slot.copied.record(self.copy_stream)
+            for t, (src, (mean, std)) in enumerate(zip((slot.d_cxr, slot.d_enh), self.stats)):
+                ops.augment_u8(src[:n], slot.d_par[t, :n], mean, std, self.crop, out=slot.out[t][:n])
+            slot.ready.record(self.copy_stream)
         slot.n, slot.used = n, True
-
-    def bind_outputs(self, img_cxr, img_enh, target):
-        """Write every batch straight into these device tensors (e.g. MFViTCATrainer.input_buffers(), the static inputs
-        of the captured step) instead of the loader's own output slots."""
-        self.into = (img_cxr, img_enh, target)
-
-    def _finish(self, slot):
-        """Device transform on the caller's stream."""
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(slot.copied)
-        n = slot.n
-        outs = self.into if self.into is not None else (slot.out[0], slot.out[1], slot.d_lab)
-        for t, (src, (mean, std)) in enumerate(zip((slot.d_cxr, slot.d_enh), self.stats)):
-            ops.augment_u8(src[:n], slot.d_par[t, :n], mean, std, self.crop, out=outs[t][:n])
-        if self.into is not None:
-            outs[2][:n].copy_(slot.d_lab[:n], non_blocking=True)
-        slot.consumed.record(cur)
-        return outs[0][:n], outs[1][:n], outs[2][:n]
 
     def __iter__(self):
         idx = shard_indices(len(self.store), self.epoch, self.seed, self.shuffle, self.rank, self.world, self.drop_last)
@@ -287,8 +279,9 @@ class PairedDeviceLoader:
         batches = [idx[i:i + self.B] for i in range(0, len(idx), self.B)]
         if self.drop_last and batches and len(batches[-1]) < self.B:
             batches.pop()
-        # A worker thread gathers, draws and copies ahead (index_select and the H2D enqueue release the GIL), so the
-        # host side of batch i+1 overlaps the device side of batch i even when the caller reads the loss every step.
+        # A worker thread gathers, draws, copies and launches the transform ahead of the consumer (index_select and the
+        # CUDA enqueues release the GIL): when the consumer asks for a batch it only waits on an event, so the host and
+        # copy-engine side of batch i+1 overlaps the training step of batch i even if the loss is read every step.
         staged = queue.Queue()
         free = [threading.Semaphore(1) for _ in self.slots]
         stop = threading.Event()
@@ -296,13 +289,19 @@ class PairedDeviceLoader:
         def worker():
             try:
                 torch.cuda.set_device(self.device)
+                # The interpreter-bound part (random draws, fixed-point coefficients) of batch i+1 is done right after
+                # batch i is staged, i.e. while the consumer is busy with an earlier batch - not in the window after a
+                # slot is handed back, where it would compete with the consumer's next launch for the GIL.
+                par = self._draw(len(batches[0]), gen) if batches else None
                 for i, b in enumerate(batches):
                     k = i % len(self.slots)
-                    while not free[k].acquire(timeout=0.1):
-                        if stop.is_set():
-                            return
-                    self._stage(self.slots[k], b, gen)
+                    free[k].acquire()
+                    if stop.is_set():
+                        return
+                    self._stage(self.slots[k], b, par)
                     staged.put(k)
+                    if i + 1 < len(batches):
+                        par = self._draw(len(batches[i + 1]), gen)
                 staged.put(None)
             except BaseException as e:  # noqa: BLE001 - re-raised in the consumer
                 staged.put(e)
@@ -316,11 +315,21 @@ class PairedDeviceLoader:
                     break
                 if isinstance(k, BaseException):
                     raise k
-                out = self._finish(self.slots[k])
-                free[k].release()  # `consumed` is recorded: the copy stream orders the next H2D into this slot after it
-                yield out
+                slot = self.slots[k]
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(slot.ready)
+                yield slot.out[0][:slot.n], slot.out[1][:slot.n], slot.d_lab[:slot.n]
+                # back from the consumer: whatever it enqueued on its stream has to finish before the slot is rewritten
+                slot.consumed.record(torch.cuda.current_stream(self.device))
+                free[k].release()
         finally:
             stop.set()
+            for f in free:
+                f.release()
+            th.join()  # an abandoned pass must not keep staging into the slots the next pass will use
+            cur = torch.cuda.current_stream(self.device)
+            for slot in self.slots:  # an abandoned pass: later passes must still order after the consumer's work
+                slot.consumed.record(cur)
 
 
 def roc_auc_ovr_mean(vals, gts, num_classes):

@@ -257,11 +257,6 @@ class MFViTCATrainer:
         self._graph = graph
         return self
 
-    def input_buffers(self):
-        """(img_cxr, img_enh, target) static inputs of the captured step, or None before capture_graph: a producer that
-        writes into them (PairedDeviceLoader.bind_outputs) saves step() its three device-to-device copies."""
-        return tuple(self._g_inputs) if self._graph is not None else None
-
     def logits(self):
         """(fused, x_cxr, x_enh) of the most recent step."""
         fused, x = self._last
