@@ -28,6 +28,7 @@ def _dist_on():
 
 class MoCo(nn.Module):
     """Build a MoCo model with a base encoder, a momentum encoder, and two MLPs (BLD:11-60)."""
+    predictor_on_keys = True  # False in builder_vit_mocov3structure_mocov2loss_noprediction_q
 
     def __init__(self, base_encoder, args, dim=256, mlp_dim=4096, T=1.0):
         super(MoCo, self).__init__()
@@ -169,11 +170,13 @@ class MoCo(nn.Module):
         q = self.predictor(self.base_encoder(im_q))  # queries: NxC (normalised inside the InfoNCE kernel)
         with torch.no_grad():
             self._momentum_update_key_encoder(m)
+            # BLD:174 runs the keys through the predictor too; the `_noprediction_q` builder (BLD_NOPRED:175) does not
+            key_head = self.predictor if self.predictor_on_keys else (lambda t: t)
             if self._shuffle_is_noop():
-                k = self.predictor(self.momentum_encoder(im_k))
+                k = key_head(self.momentum_encoder(im_k))
             else:
                 im_k, idx_unshuffle = self._batch_shuffle_ddp(im_k)
-                k = self.predictor(self.momentum_encoder(im_k))
+                k = key_head(self.momentum_encoder(im_k))
                 k = self._batch_unshuffle_ddp(k, idx_unshuffle)
         holder = {}
         if self.infonce_precision == "fp32":

@@ -292,3 +292,50 @@ def test_loader_feeds_the_captured_step_and_metrics_stay_on_device():
         runs.append(losses)
     for a, b in zip(*runs):
         assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), runs  # identical inputs; fp32 reduce-add order may differ
+
+
+@pytest.mark.gpu
+def test_run_phase_val_matches_the_oracle_and_train_updates():
+    """mfvit.loops.run_phase: the `val` phase (forward only, MAIN_CA:824-909 with phase == 'val') reproduces the oracle's
+    loss / accuracy / AUC on the centre-cropped images and leaves the parameters alone; the `train` phase steps them."""
+    import torch.nn.functional as F
+    import e2e_common as E
+    from mfvit import data, loops
+    from mfvit.trainer import MFViTCATrainer
+    rng = np.random.default_rng(41)
+    N, B, H, crop = 12, 8, 240, 224
+    cxr = rng.integers(0, 256, size=(N, H, H, 3), dtype=np.uint8)
+    enh = rng.integers(0, 256, size=(N, H, H, 3), dtype=np.uint8)
+    labels = rng.integers(0, 3, size=N)
+    store = data.PairedU8Store(cxr, enh, labels)
+    (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair(seed=17)
+    metrics = data.EpochMetrics(capacity=N, num_classes=3)
+    tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics)
+    val = data.PairedDeviceLoader(store, B, crop=crop, training=False, shuffle=False)
+    v_loss, v_auc, v_acc = loops.run_phase("val", tr, val, metrics, N)
+    master0 = tr.engine.master.clone()
+    # oracle: eval transform + as-written fp32 graph
+    outs, loss_sum = [], 0.0
+    with torch.no_grad():
+        for lo in range(0, N, B):
+            ids = range(lo, min(lo + B, N))
+            xc = torch.stack([A.transform_eval(cxr[i], crop, *A.STATS["data"]) for i in ids]).cuda()
+            xe = torch.stack([A.transform_eval(enh[i], crop, *A.STATS["Train_Mix"]) for i in ids]).cuda()
+            fused, x_c, x_e = r_f(r_c, r_e, xc, xe)
+            out = fused + x_c + x_e
+            t = torch.from_numpy(labels[lo:lo + B]).cuda()
+            loss_sum += float(F.cross_entropy(out, t)) * len(ids)
+            outs.append(out.cpu().numpy())
+    ref_vals = np.concatenate(outs)
+    assert np.abs(metrics.vals[:N].cpu().numpy() - ref_vals).max() <= 3 * 2e-3   # three logit sets, 2e-3 each (north_star)
+    assert abs(v_loss - loss_sum / N) <= 5e-3
+    acc, auc = A.epoch_metrics(metrics.vals[:N].cpu().numpy(), labels)
+    assert v_acc == acc and abs(v_auc - auc) < 1e-12
+    again = loops.run_phase("val", tr, val, metrics, N)
+    assert again == (v_loss, v_auc, v_acc) and torch.equal(tr.engine.master, master0)
+    train = data.PairedDeviceLoader(store, B, crop=crop, degrees=True, training=True, seed=1, drop_last=True)
+    t_loss, _, t_acc = loops.run_phase("train", tr, train, metrics, B)
+    assert np.isfinite(t_loss) and not torch.equal(tr.engine.master, master0)
+    assert int(metrics.counters[0]) == B
+    with pytest.raises(data.MfvError):
+        loops.run_phase("train", MFViTCATrainer(o_f, o_c, o_e), train, metrics)

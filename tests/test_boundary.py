@@ -173,3 +173,47 @@ def test_checkpoint_flow_pretrain_to_probe_to_fusion(tmp_path):
     branch.head = nn.Linear(branch.head.in_features, 3)  # MAIN_CA:309
     branch.load_state_dict(torch.load(best, map_location="cpu")["state_dict"])  # strict, MAIN_CA:357
     assert torch.equal(branch.head.weight, probe.head.weight)
+
+
+def test_checkpoint_helpers_follow_the_reference_hand_offs(tmp_path):
+    """mfvit.checkpoint restates MAIN_LPFT:318-340 (rename + non-strict load), MAIN_CA:343-385 (strict branch load) and
+    MAIN_CA:1002-1011 (file naming) as functions."""
+    import vits
+    from mfvit import checkpoint as ck
+    bm = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss")
+    moco = bm.MoCo_ViT(partial(vits.vit_small, stop_grad_conv1=True), SimpleNamespace(arch="vit_small"), 256, 4096, 0.2)
+    pre = ck.save_checkpoint(str(tmp_path), {"state_dict": {"module." + k: v for k, v in moco.state_dict().items()}},
+                             is_best=False, filename="checkpoint_smallest_loss.pth.tar")
+    assert pre.endswith("checkpoint_smallest_loss.pth.tar")
+    probe = vits.vit_small(num_classes=3)
+    ck.load_pretrained_backbone(probe, pre)
+    assert torch.equal(probe.blocks[3].attn.qkv.weight, moco.base_encoder.blocks[3].attn.qkv.weight)
+    assert ck.sanity_check_frozen(probe.state_dict(), pre)
+    with torch.no_grad():
+        probe.blocks[0].mlp.fc1.bias.add_(1.0)
+    with pytest.raises(AssertionError):
+        ck.sanity_check_frozen(probe.state_dict(), pre)
+    with pytest.raises(RuntimeError):  # a checkpoint of another architecture
+        ck.load_pretrained_backbone(vits.vit_small(num_classes=3), {"state_dict": {"module.base_encoder.cls_token": torch.zeros(1, 1, 384)}})
+    best = ck.save_checkpoint(str(tmp_path), {"state_dict": {"module." + k: v for k, v in probe.state_dict().items()}}, is_best=True)
+    assert os.path.basename(best) == "model_best.pth.tar"
+    branch = vits.vit_small()
+    branch.head = nn.Linear(branch.head.in_features, 3)
+    ck.load_finetuned_branch(branch, best)
+    assert torch.equal(branch.blocks[0].mlp.fc1.bias, probe.blocks[0].mlp.fc1.bias)
+    sd = ck.strip_moco_prefix({"module.base_encoder.head.0.weight": 1, "module.momentum_encoder.x": 2, "module.queue": 3,
+                               "module.base_encoder.norm.weight": 4})
+    assert sd == {"norm.weight": 4}
+
+
+def test_noprediction_builder_surface():
+    """BLD_NOPRED differs from BLD in one line (keys skip the predictor); same classes, keys and buffers."""
+    import vits
+    a = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss")
+    b = importlib.import_module("moco.builder_vit_mocov3structure_mocov2loss_noprediction_q")
+    for n in ("MoCo", "MoCo_ViT", "MoCo_ResNet", "concat_all_gather"):
+        assert hasattr(b, n)
+    mk = lambda mod: mod.MoCo_ViT(partial(vits.vit_small, stop_grad_conv1=True), SimpleNamespace(arch="vit_small"), 256, 4096, 0.2)  # noqa: E731
+    ma, mb = mk(a), mk(b)
+    assert sorted(ma.state_dict().keys()) == sorted(mb.state_dict().keys())
+    assert ma.predictor_on_keys and not mb.predictor_on_keys and isinstance(mb, a.MoCo)
