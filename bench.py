@@ -321,7 +321,9 @@ def main():
     # store -> host gather -> H2D of uint8 -> flip / rotate / crop / normalise kernel -> step -> loss read back
     from mfvit.data import PairedDeviceLoader, PairedU8Store
     gu = torch.Generator().manual_seed(4096 + rank)
-    n_store = (8 if img <= 224 else 3) * B
+    # one pass covers the timed steps when that fits ~0.6 GB of pinned memory per image type (a pass restart costs one
+    # un-prefetched batch; real epochs are hundreds of batches long)
+    n_store = max(3, min(args.steps + 2, int(6e8 // (B * img * img * 3)))) * B
     store = PairedU8Store(torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
                           torch.randint(0, 256, (n_store, img, img, 3), dtype=torch.uint8, generator=gu),
                           torch.randint(0, 3, (n_store,), generator=gu))

@@ -17,7 +17,6 @@ generator, so a run is reproducible and the CPU restatement in oracle/augment_re
 import math
 import queue
 import threading
-import time
 
 import numpy as np
 import torch
@@ -232,7 +231,6 @@ class PairedDeviceLoader:
             self.stats.append((torch.tensor(mean, dtype=torch.float32, device=self.device),
                                torch.tensor(std, dtype=torch.float32, device=self.device)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.handback_grace = 3e-4  # seconds the worker waits after a slot is handed back (see __iter__)
         self.slots = [_Slot(batch_size, self.H, self.W, crop, self.device, True) for _ in range(3)]
         self.h2d_bytes_per_batch = 2 * batch_size * self.H * self.W * 3 + 2 * batch_size * N_PARAMS * 4 + 8 * batch_size
 
@@ -297,12 +295,7 @@ class PairedDeviceLoader:
                 par = self._draw(len(batches[0]), gen) if batches else None
                 for i, b in enumerate(batches):
                     k = i % len(self.slots)
-                    if not free[k].acquire(blocking=False):
-                        free[k].acquire()
-                        # The slot was handed back just now, i.e. the consumer is about to launch its next step: stay off
-                        # the GIL for a moment so that launch is not interleaved with this thread (every CUDA call of the
-                        # consumer releases the GIL, and each hand-over costs a thread wake-up).
-                        time.sleep(self.handback_grace)
+                    free[k].acquire()
                     if stop.is_set():
                         return
                     self._stage(self.slots[k], b, par)

@@ -76,3 +76,39 @@ for nstore, label in ((8, "8 batches / epoch"), (64, "64 batches / epoch")):
     a.record(); run(steps); b.record(); torch.cuda.synchronize()
     print("%-60s %.3f ms/step" % ("D PairedDeviceLoader, " + label, a.elapsed_time(b) / steps), flush=True)
 timed("A again", lambda i: tr.step(*bufs))
+
+# ---- per-step loss reads: where does the turnaround go?
+def sync_loop(name, batches_iter):
+    turn, stept = [], []
+    t_sync = None
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    n = 0
+    for xc, xe, y in batches_iter:
+        t0 = time.perf_counter()
+        if t_sync is not None:
+            turn.append(t0 - t_sync)
+        loss = tr.step(xc, xe, y)
+        t1 = time.perf_counter()
+        float(loss)
+        t_sync = time.perf_counter()
+        stept.append(t1 - t0)
+        n += 1
+    b.record(); torch.cuda.synchronize()
+    import statistics
+    print("%-44s %.3f ms/step; host: hand-back->next batch %.3f ms (median), step() call %.3f ms" %
+          (name, a.elapsed_time(b) / n, statistics.median(turn) * 1e3, statistics.median(stept) * 1e3), flush=True)
+
+sync_loop("S1 resident inputs, loss read every step", ((bufs[0], bufs[1], bufs[2]) for _ in range(steps)))
+other = tuple(t.clone() for t in bufs)
+sync_loop("S2 other device tensors (3 D2D copies)", (other for _ in range(steps)))
+loader = data.PairedDeviceLoader(store, B, crop=img, degrees=True, training=True, device=dev, drop_last=True)
+def gen(n):
+    done = 0
+    for xc, xe, y in loader:
+        yield xc, xe, y
+        done += 1
+        if done == n:
+            return
+sync_loop("S3 PairedDeviceLoader (64 batches / epoch)", gen(steps))
