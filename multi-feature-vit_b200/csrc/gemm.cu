@@ -37,6 +37,7 @@ struct GemmParams {
   int epi;
   int has_c2, has_c3;
   int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
+  int rows_cta;           // rows of the output tile each CTA owns: 128, or 96 (K-major A only; see launch_gemm_epi)
   float* row_sum;         // BN == 384, fp32 reduce-add epilogue: += row sums of A (bias gradient of a wgrad GEMM)
   long long bias_gstride;
   const float* bias;
@@ -169,14 +170,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int g = r / p.tiles_m;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-        const int m0 = m_tile * (BM * CG) + (int)rank * BM;          // this CTA's 128 rows of A
+        const int m0 = (m_tile * CG + (int)rank) * p.rows_cta;       // this CTA's rows of A
         const int n0 = n_tile * BN + (int)rank * (BN / CG);          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           // the leader's barrier collects the bytes of both CTAs' loads
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES * CG);
+          if (rank == 0)
+            mbar_arrive_expect_tx(&full_bar[stage], (S::STAGE_BYTES - S::A_BYTES + p.rows_cta * BK * 2) * CG);
           if (!p.a_mn) {
             load(sa, &tmA, &full_bar[stage], kb * BK, m0, g);
           } else {
@@ -308,12 +310,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int g = r / p.tiles_m;
       const int as = it % NACC;
       const uint32_t aphase = (it / NACC) & 1;
-      const int row0 = m_tile * (BM * CG) + (int)rank * BM + q * 32;   // first row of this warp's 32-row slice
+      const int row0 = (m_tile * CG + (int)rank) * p.rows_cta + q * 32;  // first row of this warp's 32-row slice
       const int ncol0 = n_tile * BN;
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
       // pieces owned by this warp that hold real output (slices past M / N are skipped; TMA clips partial ones)
       int n_my = 0;
-      if (row0 < p.M)
+      if (row0 < p.M && q * 32 < p.rows_cta)  // 96-row CTAs: TMEM lanes 96..127 hold rows the neighbour tile owns
         for (int c = h; c < npieces && ncol0 + c * PW < p.N; c += 4) ++n_my;
       // The aux operand (fp32 residual / bf16 pre-GELU u) of piece i arrives by TMA in the ring slot where the result
       // of piece i is then computed in place.  AUX_AHEAD pieces are in flight: the load of piece i+AUX_AHEAD is issued
@@ -553,8 +555,19 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   }
   GemmParams p;
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.G = (int)a->G;
-  p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
   p.tiles_n = (p.N + BN - 1) / BN;
+  // Rows per CTA.  The N = 384 GEMMs of a 32- or 64-pair step are one or two waves of 256 x 384 pair tiles that leave a
+  // third of the SMs idle (50 tiles on 74 pairs); every byte of such a kernel moves through the per-SM L2 port, so idle
+  // SMs are lost bandwidth.  When 192-row pair tiles need no more waves than 256-row ones, each CTA stages / stores only
+  // 96 rows (TMEM lanes 96..127 of the M = 256 UMMA compute rows of the next tile and are ignored): 66 tiles on 74 pairs.
+  p.rows_cta = BM;
+  if (BN == 384 && CG == 2 && !a->a_mn_major && a->epilogue != MFV_EPI_ATOMIC_F32) {
+    const long long pairs = num_sms() / 2;
+    const long long t128 = ((p.M + 255) / 256) * p.tiles_n * p.G, t96 = ((p.M + 191) / 192) * p.tiles_n * p.G;
+    const bool fits = (t96 + pairs - 1) / pairs <= (t128 + pairs - 1) / pairs;
+    if (a->rows_per_cta == 96 || (a->rows_per_cta == 0 && fits)) p.rows_cta = 96;
+  }
+  p.tiles_m = (p.M + p.rows_cta * CG - 1) / (p.rows_cta * CG);
   p.kb_total = (p.K + BK - 1) / BK;
   int splits = a->splits > 0 ? a->splits : 1;
   if (splits > p.kb_total) splits = p.kb_total;
@@ -576,7 +589,8 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   }
 
   CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
-  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);
+  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G,
+                              a->a_mn_major ? BM : p.rows_cta, p.a_f16);
   if (rc) return rc;
   rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, BN == 384 ? 64 : BN / CG,
                           p.b_f16);

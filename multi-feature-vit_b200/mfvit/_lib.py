@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("a_gstride", i64), ("b_gstride", i64), ("c_gstride", i64),
         ("aux_ld", i64), ("aux_gstride", i64), ("bias_gstride", i64),
         ("a_mn_major", i32), ("b_mn_major", i32), ("epilogue", i32), ("splits", i32), ("block_n", i32),
-        ("dtype_flags", i32), ("cta_group", i32), ("reserved", i32),
+        ("dtype_flags", i32), ("cta_group", i32), ("rows_per_cta", i32),
         ("row_sum", c_vp),
     ]
 

@@ -25,7 +25,7 @@ def _stream():
 
 def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c_gstride=0, bias=None,
          bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, C3=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
-         splits=1, block_n=0, dtype_flags=0, cta_group=0, row_sum=None):
+         splits=1, block_n=0, dtype_flags=0, cta_group=0, row_sum=None, rows_per_cta=0):
     lib = _lib_for(A)
     a = GemmArgs()
     a.A, a.B, a.C, a.C2, a.bias, a.aux = (A.data_ptr(), B.data_ptr(), Cout.data_ptr(),
@@ -40,13 +40,14 @@ def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c
     a.a_mn_major, a.b_mn_major, a.epilogue, a.splits, a.block_n = int(a_mn), int(b_mn), epilogue, splits, block_n
     a.dtype_flags = dtype_flags
     a.cta_group = cta_group
+    a.rows_per_cta = rows_per_cta
     a.row_sum = row_sum.data_ptr() if row_sum is not None else None
     check(lib.mfv_gemm(C.byref(a), _stream()), "mfv_gemm")
     return Cout
 
 
 def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=None, block_n=0, dtype_flags=0,
-               out3=None, cta_group=0):
+               out3=None, cta_group=0, rows_per_cta=0):
     """x16 [G,M,K] bf16, w16 [G,N,K] bf16, bias [G,N] f32."""
     G, M, K = x16.shape
     N = w16.shape[1]
@@ -55,10 +56,10 @@ def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=
                           dtype=torch.float32 if epilogue in (EPI_RESID_F32, EPI_F32) else torch.bfloat16)
     return gemm(x16, w16, out, M=M, N=N, K=K, G=G, lda=K, ldb=K, ldc=N, a_gstride=M * K, b_gstride=N * K,
                 c_gstride=M * N, bias=bias, bias_gstride=N, aux=aux, aux_ld=N, aux_gstride=M * N, C2=out2, C3=out3,
-                epilogue=epilogue, block_n=block_n, dtype_flags=dtype_flags, cta_group=cta_group)
+                epilogue=epilogue, block_n=block_n, dtype_flags=dtype_flags, cta_group=cta_group, rows_per_cta=rows_per_cta)
 
 
-def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, cta_group=0, out2=None):
+def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, cta_group=0, out2=None, rows_per_cta=0):
     """dy16 [G,M,N] bf16, w16 [G,N,K] bf16 -> dx [G,M,K]."""
     G, M, N = dy16.shape
     K = w16.shape[2]
@@ -66,7 +67,7 @@ def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, ct
         out = torch.empty(G, M, K, device=dy16.device, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16)
     return gemm(dy16, w16, out, M=M, N=K, K=N, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=N * K,
                 c_gstride=M * K, aux=aux, aux_ld=K, aux_gstride=M * K, b_mn=True, epilogue=epilogue, block_n=block_n,
-                cta_group=cta_group, C2=out2)
+                cta_group=cta_group, C2=out2, rows_per_cta=rows_per_cta)
 
 
 def linear_wgrad(dy16, x16, dw, splits=8, block_n=0, cta_group=0, db=None):
