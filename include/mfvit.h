@@ -77,8 +77,8 @@ typedef struct {
   int32_t block_n; /* 0 = auto, else 64/128/256 */
   int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere) */
   int32_t cta_group;   /* 0 = auto, 1 = 128-row tiles, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) */
-  int32_t rows_per_cta; /* 384-wide pair tiles with K-major A only: 0 = auto, 128, or 96 (192-row pair tiles, chosen
-                         * automatically when they fill the SMs better without adding a wave)                        */
+  int32_t rows_per_cta; /* 384-wide pair tiles with K-major A only: 0 = default (128), or 96 = 192-row pair tiles
+                         * (more, smaller tiles: fills the SMs better for M ~ 6-12 k; opt-in, see gemm.cu)           */
   /* MFV_EPI_ATOMIC_F32 with 384-wide pair tiles (N == 384) only: f32 [G][M] (group stride bias_gstride), += the row
    * sums of A over the reduction dimension, i.e. the bias gradient of a weight-gradient GEMM (A = dY read MN-major),
    * computed by one extra N=16 UMMA per k-step against a tile of ones.  NULL = off.                                */

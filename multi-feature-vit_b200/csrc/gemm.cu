@@ -557,15 +557,17 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.G = (int)a->G;
   p.tiles_n = (p.N + BN - 1) / BN;
   // Rows per CTA.  The N = 384 GEMMs of a 32- or 64-pair step are one or two waves of 256 x 384 pair tiles that leave a
-  // third of the SMs idle (50 tiles on 74 pairs); every byte of such a kernel moves through the per-SM L2 port, so idle
-  // SMs are lost bandwidth.  When 192-row pair tiles need no more waves than 256-row ones, each CTA stages / stores only
-  // 96 rows (TMEM lanes 96..127 of the M = 256 UMMA compute rows of the next tile and are ignored): 66 tiles on 74 pairs.
+  // third of the SMs idle (50 tiles on 74 pairs).  With 192-row pair tiles each CTA stages / stores only 96 rows (TMEM
+  // lanes 96..127 of the M = 256 UMMA compute rows of the next tile and are ignored): 66 tiles on 74 pairs, and the
+  // isolated GEMMs get 2-9 % faster (tests/gpu_rows96_bench.py).  The step does not: in the backward the idle SMs are
+  // where the side-stream weight-gradient GEMMs run (filling them cost 1.3 % of the step), and in the forward the gain
+  // disappears behind PDL overlap.  So it stays opt-in: rows_per_cta = 96, or MFVIT_ROWS96=1 for the forward GEMMs.
   p.rows_cta = BM;
   if (BN == 384 && CG == 2 && !a->a_mn_major && a->epilogue != MFV_EPI_ATOMIC_F32) {
     const long long pairs = num_sms() / 2;
     const long long t128 = ((p.M + 255) / 256) * p.tiles_n * p.G, t96 = ((p.M + 191) / 192) * p.tiles_n * p.G;
     const bool fits = (t96 + pairs - 1) / pairs <= (t128 + pairs - 1) / pairs;
-    if (a->rows_per_cta == 96 || (a->rows_per_cta == 0 && fits)) p.rows_cta = 96;
+    if (a->rows_per_cta == 96 || (a->rows_per_cta == 0 && fits && EPI == MFV_EPI_RESID_F32 && rows96_enabled())) p.rows_cta = 96;
   }
   p.tiles_m = (p.M + p.rows_cta * CG - 1) / (p.rows_cta * CG);
   p.kb_total = (p.K + BK - 1) / BK;

@@ -11,6 +11,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
 bool pdl_enabled();
+bool rows96_enabled();  // MFVIT_ROWS96=1: 96 rows per CTA in the 384-wide pair tiles of the forward (off by default)
 // Side stream of mfv_vit_backward: weight-gradient GEMMs and bias column sums are off the critical path (nothing in
 // the backward consumes them), so they run beside the dgrad / attention / LayerNorm chain and fill the SMs those
 // kernels leave idle (dgrad grids are 100 CTAs on 148 SMs at 32 pairs).  MFVIT_SIDE_STREAM=0 serialises everything.

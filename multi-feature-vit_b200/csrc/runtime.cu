@@ -40,7 +40,7 @@ static int g_device = -1;
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 // Runtime switches (defaults from the environment, overridable through mfv_set_option): -1 = not read yet
-static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1;
+static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1;
 static int env_flag(const char* name, int dflt, char off_char) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
@@ -68,6 +68,10 @@ bool legacy_attention() {
   if (g_opt_legacy_attn < 0) g_opt_legacy_attn = env_flag("MFVIT_ATTN", 0, 'l');
   return g_opt_legacy_attn == 1;
 }
+bool rows96_enabled() {
+  if (g_opt_rows96 < 0) g_opt_rows96 = env_flag("MFVIT_ROWS96", 0, '1');
+  return g_opt_rows96 == 1;
+}
 bool pdl_enabled() {
   if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
   return g_opt_pdl == 1;
@@ -78,7 +82,8 @@ bool pdl_enabled() {
 extern "C" const char* mfv_last_error_where(void) { return mfv::g_err_where; }
 
 // Runtime switches for A/B measurements and tests: "pdl" (programmatic dependent launch, default 1), "side_stream"
-// (weight gradients on a second stream, default 1), "legacy_attention" (mma.sync attention kernels, default 0).
+// (weight gradients on a second stream, default 1), "legacy_attention" (mma.sync attention kernels, default 0),
+// "rows96" (192-row pair tiles for the forward N = 384 GEMMs when they fill the SMs better, default 0).
 extern "C" int mfv_set_option(const char* key, int value) {
   using namespace mfv;
   if (!key) return MFV_ERR_ARG;
@@ -86,6 +91,7 @@ extern "C" int mfv_set_option(const char* key, int value) {
   if (k == "pdl") g_opt_pdl = value ? 1 : 0;
   else if (k == "side_stream") g_opt_side = value ? 1 : 0;
   else if (k == "legacy_attention") g_opt_legacy_attn = value ? 1 : 0;
+  else if (k == "rows96") g_opt_rows96 = value ? 1 : 0;
   else return MFV_ERR_ARG;
   return MFV_OK;
 }

@@ -67,6 +67,20 @@ def t_gemm_fwd(G, M, N, K, block_n=0):
     return f
 
 
+def t_gemm_rows96():
+    """opt-in 192-row pair tiles (rows_per_cta=96) of the 384-wide tile: residual forward and a bf16 dgrad, ragged M"""
+    for M in (6304, 197 * 3, 100):
+        torch.manual_seed(3)
+        x = bf(torch.randn(2, M, 256, device=dev)); w = bf(torch.randn(2, 384, 256, device=dev) * 0.05)
+        b = torch.randn(2, 384, device=dev); res = torch.randn(2, M, 384, device=dev)
+        ref = torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :] + res
+        out = ops.linear_fwd(x, w, b, EPI_RESID_F32, aux=res, block_n=384, cta_group=2, rows_per_cta=96)
+        report("gemm rows96 resid M%d" % M, out, ref, 1e-4, rel=True)
+        dy = bf(torch.randn(2, M, 512, device=dev)); w2 = bf(torch.randn(2, 512, 384, device=dev) * 0.05)
+        out = ops.linear_dgrad(dy, w2, EPI_BF16, block_n=384, cta_group=2, rows_per_cta=96)
+        report("gemm rows96 dgrad M%d" % M, out, torch.einsum("gmn,gnk->gmk", dy.float(), w2.float()), 2e-2, rel=True)
+
+
 def t_gemm_epilogues():
     torch.manual_seed(1)
     G, M, N, K = 2, 1000, 384, 256
@@ -362,6 +376,7 @@ def main():
     run("gemm_fwd wide384 ragged", t_gemm_fwd(2, 197 * 3, 384, 384, 384), flt)
     run("gemm_fwd N768 bn384", t_gemm_fwd(1, 1000, 768, 128, 384), flt)
     run("gemm epilogues", t_gemm_epilogues, flt)
+    run("gemm rows96", t_gemm_rows96, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
     run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
     run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)
