@@ -170,6 +170,14 @@ int mfv_fusion_fwd(const float* tok, const mfv_fusion_params* p, float* out_fuse
 int mfv_fusion_bwd(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
                    const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
                    int64_t heads, int64_t NC, void* stream);
+/* Same, but only dtok is complete in `stream` order on return: the contraction of the per-sample records into the
+ * parameter gradients (it feeds the optimizer only) runs on the library's side stream, beside the encoder backward.
+ * `saved`, d_fused, d_x and the gradient buffers must stay untouched until mfv_fusion_bwd_join(stream), which orders
+ * `stream` after that contraction (a no-op when nothing is pending or the side stream is disabled).                  */
+int mfv_fusion_bwd_deferred(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
+                            const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
+                            int64_t heads, int64_t NC, void* stream);
+int mfv_fusion_bwd_join(void* stream);
 
 /* ---- small-N linear (classification heads, N <= 32) ------------------------------------------------------------------
  * Replaces `head = nn.Linear(384, 3)` (MAIN_CA:309-310, MAIN_LPFT:288) applied to the CLS row.

@@ -683,10 +683,13 @@ extern "C" int mfv_fusion_fwd(const float* tok, const mfv_fusion_params* p, floa
   return MFV_OK;
 }
 
-extern "C" int mfv_fusion_bwd(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
-                              const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
-                              int64_t heads, int64_t NC, void* stream) {
-  using namespace mfv;
+namespace mfv {
+static bool g_fusion_wgrad_pending = false;  // a deferred weight-gradient contraction is in flight on the side stream
+static SideStream* g_fusion_ss = nullptr;
+
+static int fusion_bwd_impl(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
+                           const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
+                           int64_t heads, int64_t NC, void* stream, bool defer) {
   if (!p || !g || !saved || B <= 0 || S < 2 || heads <= 0 || heads > MAX_HEADS || NC <= 0 || NC > MAX_NC)
     return MFV_ERR_SHAPE;
   if (C != 384 || C % heads) return MFV_ERR_SHAPE;
@@ -703,8 +706,44 @@ extern "C" int mfv_fusion_bwd(const float* tok, const mfv_fusion_params* p, cons
   fusion_bwd_kernel<12><<<dim3(2, (unsigned)B), FUS_THREADS, smem, st>>>(tok, *p, d_fused, d_x, dtok, scratch, (int)B,
                                                                           (int)S, (int)heads, (int)NC, scale);
   MFV_LAUNCH_CHECK();
-  fusion_wgrad_kernel<12><<<dim3((unsigned)(C / 4), 5, 2), FUS_THREADS, 0, st>>>(scratch, d_fused, d_x, *g, (int)B,
+  // The contraction of the per-sample records into the parameter gradients feeds only the optimizer: deferred, it runs
+  // on the side stream beside the encoder backward that consumes dtok.
+  SideStream* ss = defer ? side_stream() : nullptr;
+  cudaStream_t sw = st;
+  if (ss) {
+    if (g_fusion_wgrad_pending) MFV_CUDA_CHECK(cudaStreamWaitEvent(st, g_fusion_ss->fusion_done, 0));  // never two in flight
+    MFV_CUDA_CHECK(cudaEventRecord(ss->fusion_fork, st));
+    MFV_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fusion_fork, 0));
+    sw = ss->stream;
+  }
+  fusion_wgrad_kernel<12><<<dim3((unsigned)(C / 4), 5, 2), FUS_THREADS, 0, sw>>>(scratch, d_fused, d_x, *g, (int)B,
                                                                                  (int)heads, (int)NC);
   MFV_LAUNCH_CHECK();
+  if (ss) {
+    MFV_CUDA_CHECK(cudaEventRecord(ss->fusion_done, sw));
+    g_fusion_wgrad_pending = true;
+    g_fusion_ss = ss;
+  }
+  return MFV_OK;
+}
+}  // namespace mfv
+
+extern "C" int mfv_fusion_bwd(const float* tok, const mfv_fusion_params* p, const float* saved, const float* d_fused,
+                              const float* d_x, float* dtok, const mfv_fusion_grads* g, int64_t B, int64_t S, int64_t C,
+                              int64_t heads, int64_t NC, void* stream) {
+  return mfv::fusion_bwd_impl(tok, p, saved, d_fused, d_x, dtok, g, B, S, C, heads, NC, stream, false);
+}
+
+extern "C" int mfv_fusion_bwd_deferred(const float* tok, const mfv_fusion_params* p, const float* saved,
+                                       const float* d_fused, const float* d_x, float* dtok, const mfv_fusion_grads* g,
+                                       int64_t B, int64_t S, int64_t C, int64_t heads, int64_t NC, void* stream) {
+  return mfv::fusion_bwd_impl(tok, p, saved, d_fused, d_x, dtok, g, B, S, C, heads, NC, stream, true);
+}
+
+extern "C" int mfv_fusion_bwd_join(void* stream) {
+  using namespace mfv;
+  if (!g_fusion_wgrad_pending) return MFV_OK;
+  MFV_CUDA_CHECK(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), g_fusion_ss->fusion_done, 0));
+  g_fusion_wgrad_pending = false;
   return MFV_OK;
 }

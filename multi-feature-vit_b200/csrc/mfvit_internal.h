@@ -19,6 +19,7 @@ struct SideStream {
   cudaStream_t stream;
   cudaEvent_t fork[2];  // main -> side: inputs of the MLP-half / attention-half weight gradients are ready
   cudaEvent_t done[2];  // side -> main: those weight gradients have finished reading the reusable buffers
+  cudaEvent_t fusion_fork, fusion_done;  // mfv_fusion_bwd_deferred / mfv_fusion_bwd_join (fusion.cu)
 };
 SideStream* side_stream();  // nullptr when disabled or creation failed
 bool legacy_attention();  // MFVIT_ATTN=legacy forces the mma.sync attention kernels (A/B measurements)

@@ -59,6 +59,8 @@ SideStream* side_stream() {
         ok = ok && cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) == cudaSuccess;
       }
+      ok = ok && cudaEventCreateWithFlags(&ss.fusion_fork, cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&ss.fusion_done, cudaEventDisableTiming) == cudaSuccess;
       if (ok) state = 1;
     }
   }

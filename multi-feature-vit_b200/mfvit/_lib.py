@@ -93,6 +93,9 @@ SIGNATURES = {
     "mfv_fusion_fwd": (C.c_int, [c_vp, C.POINTER(FusionParams), c_vp, c_vp, c_vp, i64, i64, i64, i64, i64, c_vp]),
     "mfv_fusion_bwd": (C.c_int, [c_vp, C.POINTER(FusionParams), c_vp, c_vp, c_vp, c_vp, C.POINTER(FusionGrads),
                                  i64, i64, i64, i64, i64, c_vp]),
+    "mfv_fusion_bwd_deferred": (C.c_int, [c_vp, C.POINTER(FusionParams), c_vp, c_vp, c_vp, c_vp, C.POINTER(FusionGrads),
+                                 i64, i64, i64, i64, i64, c_vp]),
+    "mfv_fusion_bwd_join": (C.c_int, [c_vp]),
     "mfv_linear_small_fwd": (C.c_int, [c_vp, i64, c_vp, c_vp, c_vp, i64, i64, i64, c_vp]),
     "mfv_linear_small_bwd": (C.c_int, [c_vp, i64, c_vp, c_vp, c_vp, i64, c_vp, c_vp, i64, i64, i64, c_vp]),
     "mfv_ce_small": (C.c_int, [c_vp] * 6 + [i64, i64, c_vp]),

@@ -204,15 +204,30 @@ def fusion_fwd(tok, params, B, S, Cd, heads, NC):
     return fused, x
 
 
-def fusion_bwd(tok, params, grads, d_fused, d_x, B, S, Cd, heads, NC, dtok=None):
+def fusion_scratch(tok, B, S, Cd, heads):
+    n = _lib_for(tok).mfv_fusion_saved_floats(B, S, Cd, heads)
+    return torch.empty(n, device=tok.device, dtype=torch.float32)
+
+
+def fusion_bwd(tok, params, grads, d_fused, d_x, B, S, Cd, heads, NC, dtok=None, scratch=None, defer=False):
+    """defer=True: only dtok is ordered on the current stream; the parameter gradients are finished by
+    fusion_bwd_join(), and `scratch`, d_fused, d_x must be kept alive and untouched until then."""
     lib = _lib_for(tok)
-    n = lib.mfv_fusion_saved_floats(B, S, Cd, heads)
-    scratch = torch.empty(n, device=tok.device, dtype=torch.float32)
+    if scratch is None:
+        if defer:
+            raise MfvError("a deferred fusion backward needs a caller-owned scratch buffer")
+        scratch = fusion_scratch(tok, B, S, Cd, heads)
     if dtok is None:
         dtok = torch.empty_like(tok)
-    check(lib.mfv_fusion_bwd(_p(tok), C.byref(params), _p(scratch), _p(d_fused), _p(d_x), _p(dtok), C.byref(grads), B,
-                             S, Cd, heads, NC, _stream()), "mfv_fusion_bwd")
+    fn = lib.mfv_fusion_bwd_deferred if defer else lib.mfv_fusion_bwd
+    check(fn(_p(tok), C.byref(params), _p(scratch), _p(d_fused), _p(d_x), _p(dtok), C.byref(grads), B, S, Cd, heads, NC,
+             _stream()), "mfv_fusion_bwd")
     return dtok
+
+
+def fusion_bwd_join(device=None):
+    lib = _lib.init(torch.cuda.current_device() if device is None or device.index is None else device.index)
+    check(lib.mfv_fusion_bwd_join(_stream()), "mfv_fusion_bwd_join")
 
 
 def linear_small_fwd(x, ldx, w, b, rows):

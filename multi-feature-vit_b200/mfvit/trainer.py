@@ -129,18 +129,23 @@ class MFViTCATrainer:
         key = (B, device)
         if key not in self._bufs:
             self._bufs[key] = (torch.empty_like(tok),
-                               torch.empty(2, B, self.NC, device=device, dtype=torch.float32))
-        dtok, d_x = self._bufs[key]
+                               torch.empty(2, B, self.NC, device=device, dtype=torch.float32),
+                               ops.fusion_scratch(tok, B, lay.S, lay.C, self.heads),
+                               torch.empty(B, self.NC, device=device, dtype=torch.float32))
+        dtok, d_x, scratch, d_fused = self._bufs[key]
+        d_fused.copy_(dlogits)
         d_x[0].copy_(dlogits)
         d_x[1].copy_(dlogits)
-        ops.fusion_bwd(tok, self._pstruct, self._gstruct, dlogits, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok)
+        # only dtok is needed by the encoder backward: the fusion's own parameter gradients are contracted on the
+        # library's side stream meanwhile and joined below (all buffers they read are owned by the trainer)
+        ops.fusion_bwd(tok, self._pstruct, self._gstruct, d_fused, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok,
+                       scratch=scratch, defer=True)
         self._pending = []
         if reduce_async and self._overlap_allreduce():
             # Data parallel: the encoder backward runs in three block segments; the slice of the flat gradient buffer a
             # segment finished is all-reduced (NCCL, asynchronously on its own stream) while the next segment computes.
             # Blocks are contiguous in the flat layout, so a slice is one contiguous range per branch.
             dist = torch.distributed
-            self._pending.append(dist.all_reduce(self._small.grad, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
             d = lay.depth
             cuts = sorted({d, (2 * d) // 3, d // 3, 0}, reverse=True)
             segments = [(cuts[i] - 1, cuts[i + 1]) for i in range(len(cuts) - 1)]
@@ -150,8 +155,11 @@ class MFViTCATrainer:
                     self._pending.append(dist.all_reduce(grad[g, lo:hi], op=dist.ReduceOp.AVG, group=self.pg,
                                                          async_op=True))
             grad = eng.backward(lease, dtok, segments=segments, on_segment=reduce_slice)
+            ops.fusion_bwd_join(device)
+            self._pending.append(dist.all_reduce(self._small.grad, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
         else:
             grad = eng.backward(lease, dtok)
+            ops.fusion_bwd_join(device)
         self._last = (fused, x)
         return loss, grad
 
