@@ -25,9 +25,11 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 16;             // four warps per TMEM lane quarter: each owns every fourth column piece
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int EPI_BUF = 2048;                 // one staging slot: 32 rows x 64 B = one 64B-swizzled TMA box
-constexpr int EPI_NBUF = 3;                   // slots in each epilogue warp's private ring
+// slots in each epilogue warp's private ring: 3, or 4 for the fc2-dgrad epilogue (two stores per piece: with four slots
+// the pre-GELU tiles of BOTH pieces of a tile are requested at tile start - with three, the second one waited for the
+// previous tile's last store and its L2 latency was exposed, 12 % of the stall samples in profiles/r01_summary.md)
+constexpr int epi_nbuf(int epi) { return epi == MFV_EPI_DGELU ? 4 : 3; }
 constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux (residual / pre-GELU) TMA loads: 2 in flight per epilogue warp
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_NBUF * EPI_BUF;
 
 struct GemmParams {
   int M, N, K, G;
@@ -50,16 +52,21 @@ struct GemmParams {
 // 384-column accumulator - for the N = 384 GEMMs (proj, fc2, every dgrad, qkv/fc1 wgrad) the A operand is then read from
 // L2 exactly once instead of three times.  These kernels are L2->SM bandwidth bound (about 10 TB/s on the chip, measured:
 // the mainloop-only time of every shape tracks its tile traffic), so tile traffic is what sets their speed.
-template <int BN, int CG>
+template <int BN, int CG, int NBUF>
 struct GemmSmem {
   static_assert(BN != 384 || CG == 2, "384-wide tiles need a CTA pair");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES > 40960) ? 2 : (STAGE_BYTES > 32768) ? 3 : (STAGE_BYTES > 24576 ? 4 : (STAGE_BYTES > 16384 ? 5 : 6));
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;  // TMEM accumulators: double-buffered when two fit in 512 columns
   static constexpr int BAR_BYTES = 512;
   static constexpr int ONES_BYTES = (BN == 384) ? 2048 : 0;  // [16 k][64 n] tile of 1.0 for the row-sum UMMA
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * NBUF * EPI_BUF;
+  // operand stages: what is left of the 227 KB after the epilogue rings (3 slots: 6/5/4/4/3/2 stages for 16/24/32/32/
+  // 40/48 KB stages, 4 slots: one fewer from 32 KB up), at most 6
+  static constexpr int AVAIL = 232448 - 1024 - BAR_BYTES - ONES_BYTES - EPI_BYTES;
+  static constexpr int STAGES = (AVAIL / STAGE_BYTES > 6) ? 6 : AVAIL / STAGE_BYTES;
+  static_assert(STAGES >= 2, "not enough shared memory for a double-buffered mainloop");
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + 1024;  // +1024: alignment
 };
 
@@ -100,11 +107,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                  const __grid_constant__ CUtensorMap tmC3, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
-  using S = GemmSmem<BN, CG>;
+  constexpr int EPI_NBUF = epi_nbuf(EPI);
+  using S = GemmSmem<BN, CG, EPI_NBUF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + S::STAGES * S::STAGE_BYTES;
-  uint8_t* bar_base = epi_base + EPI_BYTES;
+  uint8_t* bar_base = epi_base + S::EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tfull_bar = empty_bar + S::STAGES;
@@ -322,7 +330,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // right after the first store of piece i, into the slot whose previous store is then the second-newest bulk group
       // (wait_group.read 1 - never a wait on the store just issued).  upc = ring slots used per piece.
       const int upc = (epi == MFV_EPI_DGELU && p.has_c2) ? 2 : 1;
-      const int aux_ahead = (upc == 1) ? 2 : 1;
+      const int aux_ahead = (upc == 1 || EPI_NBUF >= 4) ? 2 : 1;
       const uint32_t use0 = use;
       auto issue_aux = [&](int i, int pending_ok) {  // lane 0 only
         bulk_wait_read_n(pending_ok);
@@ -466,7 +474,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *pp = make_uint4(o[0], o[1], o[2], o[3]);
             }
             publish(&tmC, st0, n0, row0, g, false);
-            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
             if (p.has_c2) {
               uint8_t* st1 = slot_ptr(use);
               acquire_slot();
@@ -476,6 +483,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     make_uint4(gk[4 * j], gk[4 * j + 1], gk[4 * j + 2], gk[4 * j + 3]);
               publish(&tmC2, st1, n0, row0, g, false);
             }
+            // the slot piece i + aux_ahead lands in was last read by a store that is at least the second-newest group
+            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
           }
         } else {
           {  // MFV_EPI_F32 (also serves MFV_EPI_ATOMIC_F32: p.epi selects the reduce-add store): raw fp32 tile
@@ -546,7 +555,7 @@ static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, i
 
 template <int BN, int CG, int EPI>
 static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BN, CG>;
+  using S = GemmSmem<BN, CG, epi_nbuf(EPI)>;
   static bool attr_set = false;
   if (!attr_set) {
     MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
