@@ -22,7 +22,12 @@ dev = torch.device("cuda:0")
 cxr.to(dev), enh.to(dev), fus.to(dev)
 tr = MFViTCATrainer(fus, cxr, enh)
 c, e, t = E.synthetic_pair(B, 224, device=dev)
-for _ in range(2 + steps):
+for _ in range(2):
     loss = tr.step(c, e, t)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: only the steps below are captured
+for _ in range(steps):
+    loss = tr.step(c, e, t)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("loss", float(loss))
