@@ -219,8 +219,10 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, in front of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            # NCCL's version banner (NCCL_DEBUG=VERSION, here set through the box's nccl.conf) goes to stdout, in front
+            # of the one JSON line; an explicit NCCL_DEBUG=INFO etc. from the caller is left alone
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     import importlib
