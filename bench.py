@@ -367,6 +367,26 @@ def main():
     barrier()
     u8_nosync_ms = u_start.elapsed_time(u_end)
 
+    # ---- data-parallel runs only: the same per-GPU work with the gradient all-reduce switched off (every rank steps its
+    # own replica), i.e. the single-GPU rate at THIS batch size - the denominator a weak-scaling efficiency needs
+    # (N = 1 of this benchmark runs configs[1], 32 pairs, not the 64 pairs per GPU of configs[2])
+    local_ms = None
+    if world > 1:
+        trainer._graph = None
+        trainer.local_only = True
+        if use_graph:
+            trainer.capture_graph(*dev_batches[0])
+        for i in range(3):
+            trainer.step(*dev_batches[i % nb])
+        barrier()
+        l_start, l_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l_start.record()
+        for i in range(args.steps):
+            trainer.step(*dev_batches[i % nb])
+        l_end.record()
+        barrier()
+        local_ms = l_start.elapsed_time(l_end)
+
     # ---- per-kernel-class device time (CUDA events on the launching stream), 3 extra steps; the library serialises the
     # weight-gradient side stream while profiling so that every class time is that class alone
     breakdown, dominant = {}, None
@@ -387,9 +407,9 @@ def main():
                                                                   "launches_per_step": cnt[i] / psteps}
         dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else None
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms, local_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms = (float(v) for v in t)
+        elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms, local_ms = (float(v) for v in t)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -440,6 +460,11 @@ def main():
                                       "crop, normalise) x 2 on the copy stream -> step; not the headline e2e (that one copies the float32 "
                                       "tensors the reference's loaders produce)"},
             "gpu_launches": launches,
+            "same_work_no_allreduce": None if local_ms is None else {
+                "value_per_gpu": B * args.steps / (local_ms * 1e-3), "unit": UNIT + " per GPU",
+                "ms_per_step": local_ms / args.steps,
+                "what": "every rank stepping its own replica on the same %d pairs with the all-reduce switched off "
+                        "(max over ranks): the single-GPU rate at this per-GPU batch" % B},
             "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches
                            if use_graph else "eager stream launches",
             "roofline": roof,

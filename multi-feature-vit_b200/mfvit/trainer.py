@@ -60,6 +60,7 @@ class MFViTCATrainer:
         self._mom_engine = None
         self._mom_small = None
         self.overlap_allreduce = os.environ.get("MFVIT_OVERLAP_ALLREDUCE", "1") != "0"
+        self.local_only = False     # True: never all-reduce (bench.py's same-work single-GPU reference inside a DP run)
         self._pending = []
         self._graph = None          # CUDA graph of one whole step (capture_graph)
         self.graph_launches = 0     # kernels of libmfvit.so inside the captured step
@@ -165,7 +166,7 @@ class MFViTCATrainer:
 
     def _overlap_allreduce(self):
         dist = torch.distributed
-        return (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+        return (not self.local_only and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
                 and dist.get_backend(self.pg) == "nccl" and self.overlap_allreduce)
 
     def all_reduce(self, grad):
@@ -173,6 +174,8 @@ class MFViTCATrainer:
             for w in self._pending:  # stream-level waits: the optimizer step is ordered after the NCCL kernels
                 w.wait()
             self._pending = []
+            return
+        if self.local_only:
             return
         if self.pg is None and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
             return
