@@ -219,10 +219,11 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            # NCCL's version banner (NCCL_DEBUG=VERSION, here set through the box's nccl.conf) goes to stdout, in front
-            # of the one JSON line; an explicit NCCL_DEBUG=INFO etc. from the caller is left alone
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "WARN"):
+            # at these two levels NCCL prints its version banner to stdout, in front of the one JSON line (the level
+            # may come from the box's nccl.conf, so it is overridden rather than unset); INFO / TRACE from the caller
+            # are left alone
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=device)
 
     import importlib
