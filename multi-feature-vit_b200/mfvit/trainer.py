@@ -143,12 +143,13 @@ class MFViTCATrainer:
                        scratch=scratch, defer=True)
         self._pending = []
         if reduce_async and self._overlap_allreduce():
-            # Data parallel: the encoder backward runs in three block segments; the slice of the flat gradient buffer a
+            # Data parallel: the encoder backward runs in MFVIT_DP_SEGMENTS (default three) block segments; the slice of the flat gradient buffer a
             # segment finished is all-reduced (NCCL, asynchronously on its own stream) while the next segment computes.
             # Blocks are contiguous in the flat layout, so a slice is one contiguous range per branch.
             dist = torch.distributed
             d = lay.depth
-            cuts = sorted({d, (2 * d) // 3, d // 3, 0}, reverse=True)
+            nseg = max(1, int(os.environ.get("MFVIT_DP_SEGMENTS", "3")))
+            cuts = sorted({(d * k) // nseg for k in range(nseg + 1)}, reverse=True)
             segments = [(cuts[i] - 1, cuts[i + 1]) for i in range(len(cuts) - 1)]
 
             def reduce_slice(grad, lo, hi):
