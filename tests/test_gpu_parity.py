@@ -60,9 +60,10 @@ def test_single_vit_forward_backward(heads):
     assert (tok_o - tok_r).abs().max().item() <= 5e-2 and E.cos(tok_o, tok_r) > 0.9999
 
 
-@pytest.mark.parametrize("B", [4, 32])
+@pytest.mark.parametrize("B", [1, 4, 7, 32])
 def test_mfvit_ca_forward_backward(B):
-    """BASELINE config 2: MF-ViT CA, two ViT-S/16 branches + CLS cross-attention fusion + summed aux heads."""
+    """BASELINE config 2: MF-ViT CA, two ViT-S/16 branches + CLS cross-attention fusion + summed aux heads.  B = 1 and 7
+    are the ragged cases: 197 and 1379 token rows, i.e. partial 256-row tiles in every GEMM and a last partial wave."""
     (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair()
     img_c, img_e, tgt = E.synthetic_pair(B, 224, device="cuda")
     out_r, loss_r, parts_r = E.mfvit_step(r_f, r_c, r_e, img_c, img_e, tgt)  # as written: 4 backbone passes
