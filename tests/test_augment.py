@@ -339,3 +339,31 @@ def test_run_phase_val_matches_the_oracle_and_train_updates():
     assert int(metrics.counters[0]) == B
     with pytest.raises(data.MfvError):
         loops.run_phase("train", MFViTCATrainer(o_f, o_c, o_e), train, metrics)
+
+
+def test_store_from_csv_follows_the_reference_dataset(tmp_path):
+    """PairedU8Store.from_csv: list format and decode path of loader.py:Dataset_covid (fields[1]/folder/fields[2], label =
+    fields[-2], cv2.imread -> PIL) and Resize((img_size, img_size)) of image_transform.py:55, for both image types."""
+    cv2 = pytest.importorskip("cv2")
+    T = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    from mfvit import data
+    rng = np.random.default_rng(2)
+    root = str(tmp_path)
+    names, labels = ["a.png", "b.png", "c.png"], [2, 0, 1]
+    for folder in ("data", "Train_Mix"):
+        os.makedirs(os.path.join(root, folder))
+        for n in names:
+            cv2.imwrite(os.path.join(root, folder, n), rng.integers(0, 256, size=(40, 52, 3), dtype=np.uint8))
+    csv = os.path.join(root, "train.txt")
+    with open(csv, "w") as f:
+        for i, (n, l) in enumerate(zip(names, labels)):
+            f.write("%d %s %s %d x\n" % (i, root, n, l))
+    store = data.PairedU8Store.from_csv("data", "Train_Mix", csv, img_size=32)
+    assert len(store) == 3 and store.labels.tolist() == labels and tuple(store.cxr.shape) == (3, 32, 32, 3)
+    for folder, got in (("data", store.cxr), ("Train_Mix", store.enh)):
+        for i, n in enumerate(names):
+            want = np.asarray(T.Resize((32, 32))(Image.fromarray(cv2.imread(os.path.join(root, folder, n)))))
+            assert np.array_equal(got[i].numpy(), want)
+    with pytest.raises(data.MfvError):
+        data.PairedU8Store.from_csv("data", "Train_Mix", csv, img_size=32, maintain_ratio=True)
