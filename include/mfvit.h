@@ -313,6 +313,15 @@ int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_bf16, void* 
 int mfv_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, void* shadow_f16,
                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled_wd,
                   int64_t step, void* stream);
+/* The same two steps with the per-step scalars read from DEVICE memory, so a step captured in a CUDA graph follows the
+ * learning-rate schedule (adjust_learning_rate, MAIN_CA:1043-1055 / MAIN_PRE:608-619) and Adam's bias correction
+ * without being re-captured: lr_dev f32 [1]; step_dev i64 [1] = 1-based count of this update (the caller increments it
+ * on the same stream before the call).                                                                               */
+int mfv_sgd_step_dev(float* p, const float* g, float* buf, void* shadow_bf16, void* shadow_f16, int64_t n,
+                     const float* lr_dev, float momentum, float weight_decay, int first_step, void* stream);
+int mfv_adam_step_dev(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, void* shadow_f16,
+                      int64_t n, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                      int decoupled_wd, const int64_t* step_dev, void* stream);
 
 /* ---- paired input pipeline, device side -----------------------------------------------------------
  * Replaces the per-sample torchvision transform of the training loaders (image_transform.py:50-84 composed at

@@ -276,7 +276,8 @@ ce_small_kernel(const float* __restrict__ a, const float* __restrict__ b, const 
 // ----------------------------------------------------------------------------------------------- optimiser steps
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                            __nv_bfloat16* __restrict__ shadow, __half* __restrict__ shadow_h, long long n, float lr,
-                           float mom, float wd, int first) {
+                           float mom, float wd, int first, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = __ldg(lr_dev);  // learning rate kept on the device: schedules work under CUDA-graph replay
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -313,8 +314,14 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m1,
                             float* __restrict__ m2, __nv_bfloat16* __restrict__ shadow, __half* __restrict__ shadow_h,
                             long long n, float lr, float b1, float b2, float eps, float wd, int decoupled, float bc1,
-                            float bc2_sqrt) {
+                            float bc2_sqrt, const float* __restrict__ lr_dev, const long long* __restrict__ step_dev) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (lr_dev) lr = __ldg(lr_dev);
+  if (step_dev) {  // bias corrections from the device-resident step count (1-based), as torch computes them per step
+    const float st = (float)__ldg(step_dev);
+    bc1 = 1.0f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.0f - powf(b2, st));
+  }
   const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float pv = p[i];
@@ -458,7 +465,20 @@ extern "C" int mfv_sgd_step(float* p, const float* g, float* buf, void* shadow_b
     return MFV_ERR_ALIGN;
   sgd_kernel<<<grid_for(n / 4 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
       p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n, lr, momentum,
-      weight_decay, first_step);
+      weight_decay, first_step, nullptr);
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+extern "C" int mfv_sgd_step_dev(float* p, const float* g, float* buf, void* shadow_bf16, void* shadow_f16, int64_t n,
+                                const float* lr_dev, float momentum, float weight_decay, int first_step, void* stream) {
+  if (n <= 0) return MFV_OK;
+  if (!lr_dev) return MFV_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(buf)) & 15)
+    return MFV_ERR_ALIGN;
+  sgd_kernel<<<grid_for(n / 4 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
+      p, g, buf, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n, 0.f, momentum,
+      weight_decay, first_step, lr_dev);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }
@@ -471,7 +491,19 @@ extern "C" int mfv_adam_step(float* p, const float* g, float* exp_avg, float* ex
   const float bc2 = 1.0f - powf(beta2, (float)step);
   adam_kernel<<<grid_for(n, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
       p, g, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n,
-      lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, sqrtf(bc2));
+      lr, beta1, beta2, eps, weight_decay, decoupled_wd, bc1, sqrtf(bc2), nullptr, nullptr);
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+extern "C" int mfv_adam_step_dev(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                                 void* shadow_f16, int64_t n, const float* lr_dev, float beta1, float beta2, float eps,
+                                 float weight_decay, int decoupled_wd, const int64_t* step_dev, void* stream) {
+  if (n <= 0) return MFV_OK;
+  if (!lr_dev || !step_dev) return MFV_ERR_ARG;
+  adam_kernel<<<grid_for(n, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
+      p, g, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), reinterpret_cast<__half*>(shadow_f16), n,
+      0.f, beta1, beta2, eps, weight_decay, decoupled_wd, 1.f, 1.f, lr_dev, reinterpret_cast<const long long*>(step_dev));
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }

@@ -116,6 +116,8 @@ SIGNATURES = {
     "mfv_fill_f32": (C.c_int, [c_vp, f32, i64, c_vp]),
     "mfv_sgd_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, i64, f32, f32, f32, C.c_int, c_vp]),
     "mfv_adam_step": (C.c_int, [c_vp] * 6 + [i64, f32, f32, f32, f32, f32, C.c_int, i64, c_vp]),
+    "mfv_sgd_step_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, i64, c_vp, f32, f32, C.c_int, c_vp]),
+    "mfv_adam_step_dev": (C.c_int, [c_vp] * 6 + [i64, c_vp, f32, f32, f32, f32, C.c_int, c_vp, c_vp]),
 }
 
 _lib = None

@@ -350,6 +350,20 @@ def sgd_step_(p, g, buf, shadow, lr, momentum, weight_decay, first_step, shadow1
                                    float(weight_decay), int(bool(first_step)), _stream()), "mfv_sgd_step")
 
 
+def sgd_step_dev_(p, g, buf, shadow, lr_dev, momentum, weight_decay, first_step, shadow16=None):
+    """SGD step with the learning rate read from the 1-element device tensor lr_dev (graph-replay safe schedules)."""
+    check(_lib_for(p).mfv_sgd_step_dev(_p(p), _p(g), _p(buf), _p(shadow), _p(shadow16), p.numel(), _p(lr_dev),
+                                       float(momentum), float(weight_decay), int(bool(first_step)), _stream()),
+          "mfv_sgd_step_dev")
+
+
+def adam_step_dev_(p, g, m1, m2, shadow, lr_dev, betas, eps, weight_decay, decoupled, step_dev, shadow16=None):
+    """Adam / AdamW step with lr and the 1-based step count read from device tensors (f32 [1], i64 [1])."""
+    check(_lib_for(p).mfv_adam_step_dev(_p(p), _p(g), _p(m1), _p(m2), _p(shadow), _p(shadow16), p.numel(), _p(lr_dev),
+                                        float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                        int(bool(decoupled)), _p(step_dev), _stream()), "mfv_adam_step_dev")
+
+
 def adam_step_(p, g, m1, m2, shadow, lr, betas, eps, weight_decay, decoupled, step, shadow16=None):
     check(_lib_for(p).mfv_adam_step(_p(p), _p(g), _p(m1), _p(m2), _p(shadow), _p(shadow16), p.numel(), float(lr), float(betas[0]),
                                     float(betas[1]), float(eps), float(weight_decay), int(bool(decoupled)), int(step),

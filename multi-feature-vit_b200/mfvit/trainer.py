@@ -45,7 +45,16 @@ class FlatParams:
 
 class MFViTCATrainer:
     def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
-                 train_backbones=True, metrics=None):
+                 train_backbones=True, metrics=None, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8):
+        """optimizer: "sgd" (torch.optim.SGD with momentum, MAIN_CA:445-449), "adam" (torch.optim.Adam, L2 weight decay,
+        MAIN_CA:453-459) or "adamw" (decoupled decay, MAIN_PRE:339).  The learning rate lives in a 1-element device
+        tensor (set_lr), Adam's step count in another, so a captured step follows adjust_learning_rate
+        (MAIN_CA:1043-1055) and the bias correction without being captured again."""
+        if optimizer not in ("sgd", "adam", "adamw"):
+            raise MfvError("optimizer must be 'sgd', 'adam' or 'adamw', not %r" % (optimizer,))
+        self.optimizer, self.betas, self.eps = optimizer, tuple(betas), eps
+        self._lr_dev = self._step_dev = None
+        self._adam_engine = self._adam_small = None
         self.fusion, self.vits = fusion, (vit_cxr, vit_enh)
         self.metrics = metrics      # mfvit.data.EpochMetrics: loss / hits / scores accumulated on the device per step
         self.lr, self.momentum, self.wd = lr, momentum, weight_decay
@@ -87,7 +96,19 @@ class MFViTCATrainer:
                                                     cls=FusionGrads)
             self._mom_small = torch.zeros_like(self._small.master)
         if self._mom_engine is None or self._mom_engine.device != device:
-            self._mom_engine = torch.zeros_like(eng.master)
+            self._mom_engine = torch.zeros_like(eng.master)  # SGD momentum buffer / Adam exp_avg
+        if self._lr_dev is None or self._lr_dev.device != device:
+            self._lr_dev = torch.full((1,), float(self.lr), device=device, dtype=torch.float32)
+            self._step_dev = torch.zeros(1, device=device, dtype=torch.int64)
+        if self.optimizer != "sgd" and (self._adam_engine is None or self._adam_engine.device != device):
+            self._adam_engine = torch.zeros_like(eng.master)      # exp_avg_sq
+            self._adam_small = torch.zeros_like(self._small.master)
+
+    def set_lr(self, lr):
+        """adjust_learning_rate (MAIN_CA:1043-1055): takes effect at the next step, captured graph or not."""
+        self.lr = float(lr)
+        if self._lr_dev is not None:
+            self._lr_dev.fill_(self.lr)
 
     def _trainable_ranges(self):
         eng, lay = self.engine, self.engine.layout
@@ -196,19 +217,31 @@ class MFViTCATrainer:
     def optimizer_step(self, grad):
         eng = self.engine
         first = self.steps == 0
+        adam = self.optimizer != "sgd"
+        if adam:
+            self._step_dev.add_(1)  # 1-based update count, read by the kernels on the device
+
+        def update(p, g, m, v, shadow, shadow16):
+            if adam:
+                ops.adam_step_dev_(p, g, m, v, shadow, self._lr_dev, self.betas, self.eps, self.wd,
+                                   self.optimizer == "adamw", self._step_dev, shadow16=shadow16)
+            else:
+                ops.sgd_step_dev_(p, g, m, shadow, self._lr_dev, self.momentum, self.wd, first, shadow16=shadow16)
+
         if self.train_backbones:
-            # contiguous runs of trainable tensors (pos_embed is a frozen table; stop_grad_conv1 freezes the conv):
+            # contiguous runs of trainable tensors (pos_embed is a fixed table; stop_grad_conv1 freezes the conv):
             # frozen ranges must not see weight decay, so they are skipped rather than stepped with a zero gradient
             for g, lo, hi in self._trainable_ranges():
                 sl = slice(lo, hi)
-                ops.sgd_step_(eng.master[g, sl], grad[g, sl], self._mom_engine[g, sl], eng.shadow[g, sl], self.lr,
-                              self.momentum, self.wd, first, shadow16=eng.shadow16[g, sl] if eng.fwd_f16 else None)
+                update(eng.master[g, sl], grad[g, sl], self._mom_engine[g, sl],
+                       self._adam_engine[g, sl] if adam else None, eng.shadow[g, sl],
+                       eng.shadow16[g, sl] if eng.fwd_f16 else None)
             if not self._shadow_complete:
                 ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1),
                                 eng.shadow16.view(-1) if eng.fwd_f16 else None)  # frozen ranges, once
                 self._shadow_complete = True
             eng.shadow_fresh = True  # the step rewrote the GEMM shadows: the next forward skips the cast pass
-        ops.sgd_step_(self._small.master, self._small.grad, self._mom_small, None, self.lr, self.momentum, self.wd, first)
+        update(self._small.master, self._small.grad, self._mom_small, self._adam_small if adam else None, None, None)
         self.steps += 1
 
     def _step_eager(self, img_cxr, img_enh, target):
@@ -241,7 +274,10 @@ class MFViTCATrainer:
         self._prepare(device)
         lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
         eng = self.engine
-        snap = [t.clone() for t in (eng.master, self._mom_engine, self._small.master, self._mom_small)]
+        state = [eng.master, self._mom_engine, self._small.master, self._mom_small, self._step_dev]
+        if self.optimizer != "sgd":
+            state += [self._adam_engine, self._adam_small]
+        snap = [t.clone() for t in state]
         steps0, fresh0 = self.steps, eng.shadow_fresh
         self._g_inputs = [torch.empty_like(t) for t in (img_cxr, img_enh, target)]
         for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
@@ -259,7 +295,7 @@ class MFViTCATrainer:
             self._g_loss = self._step_eager(*self._g_inputs)
         self.graph_launches = int(lib.mfv_launch_count() - n0)
         # undo the warm-up steps (capture itself executes nothing); the 16-bit GEMM shadows are rebuilt from the master
-        for dst, src in zip((eng.master, self._mom_engine, self._small.master, self._mom_small), snap):
+        for dst, src in zip(state, snap):
             dst.copy_(src)
         ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1), eng.shadow16.view(-1) if eng.fwd_f16 else None)
         if self.metrics is not None:

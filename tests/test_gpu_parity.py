@@ -314,3 +314,78 @@ def test_segmented_backward_equals_whole_backward():
     assert all(slices[i][0] == slices[i + 1][1] for i in range(len(slices) - 1))
     assert E.cos(g_seg, g_whole) > 0.999999
     assert (g_seg - g_whole).abs().max().item() <= 1e-4 * g_whole.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["sgd", "adam", "adamw"])
+def test_trainer_optimizers_match_torch_optim(name):
+    """MAIN_CA:445-459 (SGD with momentum / Adam with L2 decay) and MAIN_PRE:339 (AdamW): the fused flat-buffer steps
+    against torch.optim on the same gradients; frozen ranges (pos_embed) see neither update nor weight decay."""
+    from mfvit.trainer import MFViTCATrainer
+    _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=21)
+    tr = MFViTCATrainer(o_f, o_c, o_e, lr=2e-3, momentum=0.9, weight_decay=1e-2, optimizer=name)
+    img_c, img_e, tgt = E.synthetic_pair(4, 224, device="cuda")
+    _, grad = tr.forward_backward(img_c, img_e, tgt)
+    grad = grad.clone()
+    small_grad = tr._small.grad.clone()
+    eng = tr.engine
+    refs = []
+    for master, g in ((eng.master, grad), (tr._small.master, small_grad)):
+        p = master.detach().clone().requires_grad_(True)
+        p.grad = g.clone()
+        refs.append(p)
+    if name == "sgd":
+        opt = torch.optim.SGD(refs, lr=2e-3, momentum=0.9, weight_decay=1e-2)
+    elif name == "adam":
+        opt = torch.optim.Adam(refs, lr=2e-3, betas=(0.9, 0.999), weight_decay=1e-2)
+    else:
+        opt = torch.optim.AdamW(refs, lr=2e-3, betas=(0.9, 0.999), weight_decay=1e-2)
+    before = eng.master.clone()
+    for it in range(3):
+        if it == 2:  # a schedule step in between (adjust_learning_rate)
+            tr.set_lr(5e-4)
+            for gr in opt.param_groups:
+                gr["lr"] = 5e-4
+        tr._small.grad.copy_(small_grad)
+        tr.optimizer_step(grad)
+        opt.step()
+    torch.cuda.synchronize()
+    lay = eng.layout
+    mask = torch.zeros(eng.G, lay.P, dtype=torch.bool, device="cuda")
+    for g, lo, hi in tr._trainable_ranges():
+        mask[g, lo:hi] = True
+    ours, ref = eng.master, refs[0].detach()
+    assert torch.equal(ours[~mask], before[~mask]), "frozen ranges must not move"
+    err = (ours[mask] - ref[mask]).abs().max().item()
+    assert err <= 2e-6, "%s: max abs diff to torch.optim %.3e" % (name, err)
+    assert (tr._small.master - refs[1].detach()).abs().max().item() <= 2e-6
+    assert (ours[mask] - before[mask]).abs().max().item() > 1e-4  # it did move
+    # the 16-bit GEMM shadows were rewritten from the new master in the same pass
+    assert torch.equal(eng.shadow[mask], ours[mask].bfloat16())
+
+
+def test_learning_rate_schedule_reaches_the_captured_step():
+    """set_lr between replays of the captured step (lr lives on the device): lr = 0 freezes the parameters, and the
+    losses follow an eager trainer driven with the same schedule."""
+    from mfvit.trainer import MFViTCATrainer
+    batches = [E.synthetic_pair(4, 224, device="cuda", rank=i) for i in range(2)]
+    sched = [1e-3, 1e-3, 5e-4, 0.0]
+    runs = []
+    for use_graph in (True, False):
+        _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=5)
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=sched[0], momentum=0.9, optimizer="adam")
+        if use_graph:
+            tr.capture_graph(*batches[0])
+        losses = []
+        for i, lr in enumerate(sched):
+            tr.set_lr(lr)
+            if lr == 0.0:
+                torch.cuda.synchronize()
+                frozen = tr.engine.master.clone()
+            losses.append(float(tr.step(*batches[i % 2])))
+        torch.cuda.synchronize()
+        assert torch.equal(tr.engine.master, frozen), "lr = 0 must leave the parameters unchanged"
+        assert int(tr._step_dev) == len(sched)
+        runs.append(losses)
+        assert (tr.graph_replays == len(sched)) == use_graph
+    for a, b in zip(*runs):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), runs
