@@ -44,6 +44,8 @@ class FlatParams:
 
 
 class MFViTCATrainer:
+    local_only = False  # True: never all-reduce (bench.py's same-work single-GPU reference inside a data-parallel run)
+
     def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
                  train_backbones=True, metrics=None, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8):
         """optimizer: "sgd" (torch.optim.SGD with momentum, MAIN_CA:445-449), "adam" (torch.optim.Adam, L2 weight decay,
@@ -69,7 +71,6 @@ class MFViTCATrainer:
         self._mom_engine = None
         self._mom_small = None
         self.overlap_allreduce = os.environ.get("MFVIT_OVERLAP_ALLREDUCE", "1") != "0"
-        self.local_only = False     # True: never all-reduce (bench.py's same-work single-GPU reference inside a DP run)
         self._pending = []
         self._graph = None          # CUDA graph of one whole step (capture_graph)
         self.graph_launches = 0     # kernels of libmfvit.so inside the captured step

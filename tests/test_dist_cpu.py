@@ -52,6 +52,10 @@ def _worker(rank, world, port, out_dir):
     tr.all_reduce(big)
     res["grad_mean_big"] = float(big[0, 0])
     res["grad_mean_small"] = float(tr._small.grad[0])
+    tr.local_only = True  # bench.py's same-work reference: no collective, gradients stay local
+    local = torch.full((2, 4), float(rank + 1))
+    tr.all_reduce(local)
+    res["local_only_untouched"] = bool(torch.equal(local, torch.full((2, 4), float(rank + 1))))
     # (4) per-rank synthetic shards differ, same rank reproduces (SURVEY 8(d) seeding)
     import e2e_common as E
     c0, _, t0 = E.synthetic_pair(2, 32, rank=rank)
@@ -72,6 +76,7 @@ def test_two_rank_gloo(tmp_path):
         assert x["gather_order"] == [0.0, 0.0, 1.0, 1.0]          # rank-major
         assert x["ptr"] == 4 and x["queues_identical"]
         assert x["grad_mean_big"] == pytest.approx(15.0) and x["grad_mean_small"] == pytest.approx(1.5)
+        assert x["local_only_untouched"]
         assert x["shard_reproducible"]
     # the queue holds rank 0's keys first, then rank 1's
     assert torch.allclose(torch.tensor(r[0]["queue_cols"][:2]), torch.tensor(r[0]["own_keys"]))
