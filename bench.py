@@ -62,6 +62,14 @@ def gemm_class_flops(img, B, G=2, C=384, depth=12, hidden=1536):
     return {"gemm_fwd": G * B * (lin + patch), "gemm_dgrad": G * B * lin, "gemm_wgrad": G * B * (lin + patch)}
 
 
+def ln_class_bytes(img, B, G=2, C=384, depth=12):
+    """Algorithmic HBM bytes per step of the LayerNorm classes: forward = x f32 in, fp16 + bf16 copies
+    out, mean / rstd; backward = x f32, dy bf16, residual gradient f32 in, dx f32 + bf16 out, mean / rstd."""
+    rows = G * B * ((img // 16) ** 2 + 1)
+    return {"ln_fwd": 2 * depth * rows * (C * (4 + 2 + 2) + 8) + rows * (C * (4 + 4) + 8),
+            "ln_bwd": 2 * depth * rows * (C * (4 + 2 + 4 + 4 + 2) + 8) + rows * (C * (4 + 4 + 4 + 2) + 8)}
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -440,6 +448,20 @@ def main():
             d = breakdown[dominant]
             roof = {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": None, "traffic": traffic.get(dominant), "ms_per_step": d["ms_per_step"]}
+        # the largest HBM-bound class of the same profiled pass, against the measured copy bandwidth
+        roof_hbm = None
+        lb = ln_class_bytes(img, B)
+        hb = [k for k in lb if k in breakdown]
+        if hb:
+            k = max(hb, key=lambda n: breakdown[n]["ms_per_step"])
+            gbs = lb[k] / (breakdown[k]["ms_per_step"] * 1e-3) / 1e9
+            roof_hbm = {"kernel": k + "_kernel (%d launches of the step)" % round(breakdown[k]["launches_per_step"]),
+                        "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        "traffic": traffic.get(k), "ms_per_step": breakdown[k]["ms_per_step"],
+                        "peak_source": peaks["source"],
+                        "note": "in-step class time from CUDA events around every launch (cold inputs, ~2 us of event "
+                                "bracketing per launch); the kernel alone, graph-timed over a ring larger than L2: "
+                                "profiles/r01_hbm_bench.log"}
         step_tf = value * pair_flops(img) / 1e12
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         line = {
@@ -469,6 +491,7 @@ def main():
             "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches
                            if use_graph else "eager stream launches",
             "roofline": roof,
+            "roofline_hbm": roof_hbm,
             "step_tflops": step_tf,
             "step_frac_of_bf16_peak": {"measured_sustained": step_tf / peaks["bf16_sustained"] / world,
                                        "measured_burst": step_tf / peaks["bf16_burst"] / world,
