@@ -39,13 +39,14 @@ augment_u8_kernel(const uint8_t* __restrict__ src, const int* __restrict__ param
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int x = ox + k + left, y = oy + top;
-      bool ok = true;
       if (rot) {
         const int xx = a2 + y * a1 + x * a0, yy = a5 + y * a4 + x * a3;  // pixel-centre offsets are folded into a2 / a5
         x = xx >> 16;
         y = yy >> 16;
-        ok = x >= 0 && x < Ws && y >= 0 && y < Hs;
       }
+      // outside the source image: fill value 0 (rotation corners); also keeps a bad crop window in the device-side
+      // parameters from reading out of bounds
+      const bool ok = x >= 0 && x < Ws && y >= 0 && y < Hs;
       if (flip) x = Ws - 1 - x;
       const uint8_t* px = img + ((long long)y * Ws + x) * 3;
 #pragma unroll
