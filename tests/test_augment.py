@@ -168,6 +168,14 @@ def test_augment_kernel_is_bit_exact(golden_dir):
     with pytest.raises(data.MfvError):
         ops.augment_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8, device="cuda"), torch.zeros(1, 12, dtype=torch.int32, device="cuda"),
                        torch.zeros(3, device="cuda"), torch.ones(3, device="cuda"), 6)  # crop % 4
+    # a crop window that leaves the image (bad device-side parameters) reads nothing out of bounds: fill value 0
+    img = rng.integers(0, 256, size=(1, 32, 32, 3), dtype=np.uint8)
+    mean, std = A.STATS["Train_Mix"]
+    out = ops.augment_u8(torch.from_numpy(img).cuda(), data.pack_params([(True, 0.0, 8, 8)], 32, 32).cuda(),
+                         torch.tensor(mean, device="cuda"), torch.tensor(std, device="cuda"), 32)
+    padded = np.zeros((40, 40, 3), dtype=np.uint8)
+    padded[:32, :32] = img[0][:, ::-1]
+    assert torch.equal(out[0].cpu(), A.to_tensor_normalize(padded[8:40, 8:40], mean, std))
 
 
 @pytest.mark.gpu
