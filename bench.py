@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--impl", default="mfvit", choices=["mfvit", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=0, help="default: 32 at N=1 (configs[1]), 64 at N>1 (configs[2])")
     ap.add_argument("--img-size", type=int, default=224)
-    ap.add_argument("--cpu-sample-pairs", type=int, default=16)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=32, help="pairs per CPU step (32 = the batch of configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the "
                                                             "CUDA graph of the step (single-GPU runs)")
@@ -500,10 +500,10 @@ def main():
             "final_loss": loss_val,
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, dt, cores = cpu_reference_rate(img, args.cpu_sample_pairs, 4, 1)
+            rate, dt, cores = cpu_reference_rate(img, args.cpu_sample_pairs, 3, 1)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "%d pairs per step x (1 warm-up + 4 timed) steps of the as-written reference graph (4 backbone "
+                "sample": "%d pairs per step x (1 warm-up + 3 timed) steps of the as-written reference graph (4 backbone "
                           "passes), oracle port, fp32" % args.cpu_sample_pairs}
         print(json.dumps(line), flush=True)
     if world > 1:
