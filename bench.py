@@ -252,7 +252,7 @@ def main():
     cxr.to(device), enh.to(device), fus.to(device)
     from mfvit.data import EpochMetrics
     metrics = EpochMetrics(capacity=B * max(args.steps, 1), num_classes=3, device=device)
-    trainer = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, weight_decay=0.0, metrics=metrics)
+    trainer = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, weight_decay=0.0, metrics=metrics, train_backbones=True)
 
     # synthetic data: 4 rotating batches per rank, pinned host copies for the end-to-end leg
     nb = 4

@@ -28,7 +28,9 @@ extern "C" {
 
 /* ---- runtime ------------------------------------------------------------------------------------------------- */
 int mfv_abi_version(void);
-/* Binds the library to `device`; checks compute capability 10.x, resolves cuTensorMapEncodeTiled. */
+/* Binds the library to `device`; checks compute capability 10.x, resolves cuTensorMapEncodeTiled.  One device per
+ * process: a second call with a different device returns MFV_ERR_ARG (side stream, events and opt-in shared-memory
+ * attributes are process-wide state).                                                                             */
 int mfv_init(int device);
 const char* mfv_strerror(int code);
 /* "file:line: expression" of the last CUDA runtime failure returned to this thread ("" if none); debugging aid. */

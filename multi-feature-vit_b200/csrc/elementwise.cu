@@ -258,7 +258,14 @@ ce_small_kernel(const float* __restrict__ a, const float* __restrict__ b, const 
     float se = 0.f;
     for (int n = 0; n < NC; ++n) se += expf(z[n] - mx);
     const float lse = mx + logf(se);
-    const int t = (int)target[r];
+    const long long tl = target[r];
+    if (tl < 0 || tl >= NC) {  // torch's CE device-asserts here; never index z[] with it: the loss turns NaN instead
+      local = __int_as_float(0x7fc00000);
+      if (dlogits)
+        for (int n = 0; n < NC; ++n) dlogits[r * NC + n] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const int t = (int)tl;
     local += lse - z[t];
     if (dlogits)
       for (int n = 0; n < NC; ++n) dlogits[r * NC + n] = (expf(z[n] - lse) - (n == t ? 1.f : 0.f)) * inv_rows;

@@ -136,6 +136,12 @@ extern "C" int mfv_init(int device) {
   cudaDeviceProp prop;
   MFV_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return MFV_ERR_ARCH;  // sm_100a only: no fallback path exists
+  // One device per process (the deployment model: one process per GPU).  The side stream, its events, the opt-in
+  // shared-memory attributes and the SM count are process-wide state bound to the first device.
+  if (g_device >= 0 && g_device != device) {
+    note_error(__FILE__, __LINE__, "mfv_init called for a second device in one process");
+    return MFV_ERR_ARG;
+  }
   MFV_CUDA_CHECK(cudaSetDevice(device));
   g_num_sms = prop.multiProcessorCount;
   g_device = device;

@@ -39,9 +39,11 @@ class MoCo(nn.Module):
         self.base_encoder = base_encoder(num_classes=mlp_dim)
         self.momentum_encoder = base_encoder(num_classes=mlp_dim)
         self._build_projector_and_predictor_mlps(dim, mlp_dim)
-        for param_b, param_m in zip(self.base_encoder.parameters(), self.momentum_encoder.parameters()):
-            param_m.data.copy_(param_b.data)  # initialize
-            param_m.requires_grad = False  # not update by gradient
+        # BLD:48-52: the momentum encoder starts as a copy of the base encoder and never sees a gradient
+        with torch.no_grad():
+            for src, dst in zip(self.base_encoder.parameters(), self.momentum_encoder.parameters()):
+                dst.copy_(src)
+                dst.requires_grad_(False)
         self.register_buffer("queue", torch.randn(dim, self.K))
         self.queue = nn.functional.normalize(self.queue, dim=0)
         self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
@@ -54,18 +56,18 @@ class MoCo(nn.Module):
         # True: reproduce BLD:107-152 (all-gather the key images, global shuffle) even when it cannot change the result
         self.force_batch_shuffle = False
 
-    def _build_mlp(self, num_layers, input_dim, mlp_dim, output_dim, last_bn=True):  # BLD:62-78
-        mlp = []
-        for l in range(num_layers):
-            dim1 = input_dim if l == 0 else mlp_dim
-            dim2 = output_dim if l == num_layers - 1 else mlp_dim
-            mlp.append(nn.Linear(dim1, dim2, bias=False))
-            if l < num_layers - 1:
-                mlp.append(nn.BatchNorm1d(dim2))
-                mlp.append(nn.ReLU(inplace=True))
+    def _build_mlp(self, num_layers, input_dim, mlp_dim, output_dim, last_bn=True):
+        """BLD:62-78: bias-free Linear layers; hidden ones followed by BN + ReLU, the last one by a BN without affine
+        parameters when `last_bn`.  Module indices (= state-dict keys) match the reference's nn.Sequential."""
+        widths = [input_dim] + [mlp_dim] * (num_layers - 1) + [output_dim]
+        layers = []
+        for i, (fan_in, fan_out) in enumerate(zip(widths[:-1], widths[1:])):
+            layers.append(nn.Linear(fan_in, fan_out, bias=False))
+            if i + 1 < num_layers:
+                layers += [nn.BatchNorm1d(fan_out), nn.ReLU(inplace=True)]
             elif last_bn:
-                mlp.append(nn.BatchNorm1d(dim2, affine=False))
-        return nn.Sequential(*mlp)
+                layers.append(nn.BatchNorm1d(fan_out, affine=False))
+        return nn.Sequential(*layers)
 
     def _build_projector_and_predictor_mlps(self, dim, mlp_dim):
         pass
@@ -90,7 +92,7 @@ class MoCo(nn.Module):
         _, chunks, n, mx = self._ema_cache
         ops.ema_update_(chunks, n, mx, m)
         from mfvit.engine import engine_for
-        engine_for(self.momentum_encoder).shadow_fresh = False
+        engine_for(self.momentum_encoder).invalidate_shadow()
 
     # ------------------------------------------------------------------------------------------------ queue (BLD:91-105)
     @torch.no_grad()
@@ -100,7 +102,7 @@ class MoCo(nn.Module):
         if self._ptr_host is None:
             self._ptr_host = int(self.queue_ptr)  # one sync at the first step only (the reference syncs every step)
         ptr = self._ptr_host
-        assert self.K % batch_size == 0  # for simplicity
+        assert self.K % batch_size == 0  # BLD:99: the queue length must be a multiple of the global batch
         if holder is not None:
             holder["start"] = ptr
             holder["old"] = self.queue[:, ptr:ptr + batch_size].clone()
@@ -130,29 +132,30 @@ class MoCo(nn.Module):
         return self._queue16
 
     # ------------------------------------------------------------------------------------------------ shuffle (BLD:107-152)
+    @staticmethod
+    def _rank_world():
+        if _dist_on():
+            return torch.distributed.get_rank(), torch.distributed.get_world_size()
+        return 0, 1
+
     @torch.no_grad()
     def _batch_shuffle_ddp(self, x):
-        batch_size_this = x.shape[0]
-        x_gather = concat_all_gather(x)
-        batch_size_all = x_gather.shape[0]
-        num_gpus = batch_size_all // batch_size_this
-        idx_shuffle = torch.randperm(batch_size_all).cuda()
-        if _dist_on():
-            torch.distributed.broadcast(idx_shuffle, src=0)
-        idx_unshuffle = torch.argsort(idx_shuffle)
-        gpu_idx = torch.distributed.get_rank() if _dist_on() else 0
-        idx_this = idx_shuffle.view(num_gpus, -1)[gpu_idx]
-        return x_gather[idx_this], idx_unshuffle
+        """BLD:107-135: every rank takes its slice of one global permutation (drawn on each rank, rank 0's wins) of
+        the all-gathered batch; also returns the inverse permutation for _batch_unshuffle_ddp."""
+        rank, world = self._rank_world()
+        everything = concat_all_gather(x)
+        perm = torch.randperm(everything.shape[0]).to(x.device)  # CPU generator, as the reference draws it
+        if world > 1:
+            torch.distributed.broadcast(perm, src=0)
+        inverse = torch.argsort(perm)
+        mine = perm.chunk(world)[rank]
+        return everything[mine], inverse
 
     @torch.no_grad()
     def _batch_unshuffle_ddp(self, x, idx_unshuffle):
-        batch_size_this = x.shape[0]
-        x_gather = concat_all_gather(x)
-        batch_size_all = x_gather.shape[0]
-        num_gpus = batch_size_all // batch_size_this
-        gpu_idx = torch.distributed.get_rank() if _dist_on() else 0
-        idx_this = idx_unshuffle.view(num_gpus, -1)[gpu_idx]
-        return x_gather[idx_this]
+        """BLD:137-152: gather the shuffled features and pick this rank's rows in the original order."""
+        rank, world = self._rank_world()
+        return concat_all_gather(x)[idx_unshuffle.chunk(world)[rank]]
 
     def _shuffle_is_noop(self):
         """Shuffle-BN only changes which samples share BatchNorm statistics.  With one rank, or with SyncBatchNorm

@@ -155,6 +155,10 @@ def init(device_index):
     """mfv_init on first use of a device (validates sm_100, resolves the TMA descriptor encoder)."""
     lib = load()
     if device_index not in _inited_devices:
+        if _inited_devices:
+            raise MfvError("libmfvit.so is bound to cuda:%d in this process; cuda:%d needs its own process (one process "
+                           "per GPU: the side stream, events and kernel attributes are per-process state)"
+                           % (next(iter(_inited_devices)), int(device_index)))
         check(lib.mfv_init(int(device_index)), "mfv_init")
         _inited_devices.add(device_index)
     return lib

@@ -169,8 +169,18 @@ class ViTEngine:
         self.grads = [None, None]
         self.grad_idx = 0
         self.shadow_fresh = False
+        self._shadow_sig = None  # parameter versions the 16-bit shadows were last known to match
         self._ws = {}
         self._params = None  # per group: list of (name, Parameter)
+        ref = weakref.ref(self)
+
+        def _on_load(module, incompatible_keys):  # load_state_dict rewrote the fp32 master in place: shadows are stale
+            eng = ref()
+            if eng is not None:
+                eng.invalidate_shadow()
+
+        for m in self.modules:
+            m.register_load_state_dict_post_hook(_on_load)
 
     # ------------------------------------------------------------------------------------------ parameters
     def _named_params(self, g):
@@ -201,7 +211,7 @@ class ViTEngine:
                     view = self.master[g, off:off + p.numel()].view(p.shape)
                     view.copy_(p.detach().to(device=device, dtype=torch.float32))
                     p.data = view
-                    self.shadow_fresh = False
+                    self.invalidate_shadow()
 
     def is_adopted(self):
         if self.master is None or self._params is None:
@@ -221,9 +231,32 @@ class ViTEngine:
     def any_requires_grad(self):
         return any(p.requires_grad for g in range(self.G) for _, p in self._params[g])
 
+    # The 16-bit GEMM shadows are valid for ONE forward after somebody who rewrote them said so (mark_shadow_fresh: the
+    # fused optimizer step, capture_graph), and only while no Parameter was edited in place since: load_state_dict, a
+    # torch.optim step or p.copy_() bump Parameter._version without changing data_ptr.  Writers that bypass autograd's
+    # version counter (p.data.copy_, raw kernels such as the EMA update) must call invalidate_shadow().
+    def _param_sig(self):
+        if self._params is None:
+            return None
+        return sum(p._version for plist in self._params for _, p in plist)
+
+    def mark_shadow_fresh(self):
+        self.shadow_fresh = True
+        self._shadow_sig = self._param_sig()
+
+    def invalidate_shadow(self):
+        self.shadow_fresh = False
+        self._shadow_sig = None
+
+    def shadow_is_current(self):
+        return self.shadow_fresh and self._shadow_sig is not None and self._shadow_sig == self._param_sig()
+
+    def cast_shadow(self):
+        ops.cast_shadow(self.master.view(-1), self.shadow.view(-1), self.shadow16.view(-1) if self.fwd_f16 else None)
+
     def refresh_shadow(self):
-        if not self.shadow_fresh:
-            ops.cast_shadow(self.master.view(-1), self.shadow.view(-1), self.shadow16.view(-1) if self.fwd_f16 else None)
+        if not self.shadow_is_current():
+            self.cast_shadow()
         self.shadow_fresh = False  # a fresh flag is consumed by exactly one forward
 
     # ------------------------------------------------------------------------------------------ plan / workspaces

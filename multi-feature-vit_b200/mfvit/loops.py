@@ -20,7 +20,7 @@ def evaluate_batch(trainer, img_cxr, img_enh, target):
     eng, lay = trainer.engine, trainer.engine.layout
     tok, _ = eng.forward([img_cxr, img_enh], save=False)
     fused, x = ops.fusion_fwd(tok, trainer._pstruct, img_cxr.shape[0], lay.S, lay.C, trainer.heads, trainer.NC)
-    loss, _ = ops.ce_small(fused, x[0], x[1], target, want_grad=False)
+    loss, _ = ops.ce_small(fused, x[0], x[1], target.long(), want_grad=False)
     return loss, (fused, x[0], x[1])
 
 

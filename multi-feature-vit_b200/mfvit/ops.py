@@ -244,8 +244,20 @@ def linear_small_bwd(x, ldx, w, dy, dx, lddx, dw, db, rows):
                                            _stream()), "mfv_linear_small_bwd")
 
 
+def _check_labels(target, rows, device, what):
+    """The kernels read `target` as int64 [rows]: anything else would be reinterpreted silently (the reference casts
+    with target.long(), MAIN_CA:859)."""
+    if target.dtype != torch.int64 or tuple(target.shape) != (rows,) or not target.is_contiguous() \
+            or target.device != device:
+        raise MfvError("%s wants a contiguous int64 label tensor of shape [%d] on %s, got %s %s on %s"
+                       % (what, rows, device, target.dtype, tuple(target.shape), target.device))
+
+
 def ce_small(a, b, c, target, want_grad=True):
     rows, NC = a.shape
+    if NC > 32:
+        raise MfvError("ce_small handles at most 32 classes")
+    _check_labels(target, rows, a.device, "ce_small")
     loss = torch.empty(1, device=a.device, dtype=torch.float32)
     dl = torch.empty_like(a) if want_grad else None
     check(_lib_for(a).mfv_ce_small(_p(a), _p(b), _p(c), _p(target), _p(loss), _p(dl), rows, NC, _stream()),
@@ -269,6 +281,7 @@ def augment_u8(src_u8, params, mean3, std3, crop, out=None):
 
 def epoch_metrics_(a, b, c, target, loss, loss_sum, counters, vals, preds, gts):
     rows, NC = a.shape
+    _check_labels(target, rows, a.device, "epoch_metrics_")
     check(_lib_for(a).mfv_epoch_metrics(_p(a), _p(b), _p(c), _p(target), _p(loss), rows, NC, _p(loss_sum),
                                         _p(counters), vals.shape[0], _p(vals), _p(preds), _p(gts), _stream()),
           "mfv_epoch_metrics")

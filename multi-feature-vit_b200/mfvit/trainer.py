@@ -47,8 +47,13 @@ class MFViTCATrainer:
     local_only = False  # True: never all-reduce (bench.py's same-work single-GPU reference inside a data-parallel run)
 
     def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
-                 train_backbones=True, metrics=None, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8):
-        """optimizer: "sgd" (torch.optim.SGD with momentum, MAIN_CA:445-449), "adam" (torch.optim.Adam, L2 weight decay,
+                 train_backbones=False, metrics=None, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8):
+        """train_backbones=False (default) is the optimisation set of the reference AS WRITTEN: MAIN_CA:435-449 builds
+        the optimizer over Fus_CrossViT.parameters() only, i.e. the fusion's own 22 tensors - the two backbones and their
+        3-class heads receive gradients (when they require them) but are never stepped; requires_grad
+        of every fusion tensor is honoured.  train_backbones=True additionally steps both ViT-S/16 encoders and their
+        heads (full fine-tuning: the heavier step bench.py measures, and the one a 173 MB gradient all-reduce implies).
+        optimizer: "sgd" (torch.optim.SGD with momentum, MAIN_CA:445-449), "adam" (torch.optim.Adam, L2 weight decay,
         MAIN_CA:453-459) or "adamw" (decoupled decay, MAIN_PRE:339).  The learning rate lives in a 1-element device
         tensor (set_lr), Adam's step count in another, so a captured step follows adjust_learning_rate
         (MAIN_CA:1043-1055) and the bias correction without being captured again."""
@@ -145,7 +150,9 @@ class MFViTCATrainer:
         eng = self.engine
         B = img_cxr.shape[0]
         lay = eng.layout
-        tok, lease = eng.forward([img_cxr, img_enh], save=True)
+        target = target.long()  # MAIN_CA:859 (a no-op for int64 labels)
+        enc_grads = eng.any_requires_grad()  # frozen backbones (MAIN_CA:298-305 without --semi-supervised): no backward
+        tok, lease = eng.forward([img_cxr, img_enh], save=enc_grads)
         fused, x = ops.fusion_fwd(tok, self._pstruct, B, lay.S, lay.C, self.heads, self.NC)
         loss, dlogits = ops.ce_small(fused, x[0], x[1], target)
         ops.fill_(self._small.grad, 0.0)
@@ -164,7 +171,13 @@ class MFViTCATrainer:
         ops.fusion_bwd(tok, self._pstruct, self._gstruct, d_fused, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok,
                        scratch=scratch, defer=True)
         self._pending = []
-        if reduce_async and self._overlap_allreduce():
+        if not enc_grads:
+            ops.fusion_bwd_join(device)
+            grad = None
+            if reduce_async and self._overlap_allreduce():
+                self._pending.append(torch.distributed.all_reduce(self._small.grad, op=torch.distributed.ReduceOp.AVG,
+                                                                  group=self.pg, async_op=True))
+        elif reduce_async and self._overlap_allreduce():
             # Data parallel: the encoder backward runs in MFVIT_DP_SEGMENTS (default three) block segments; the slice of the flat gradient buffer a
             # segment finished is all-reduced (NCCL, asynchronously on its own stream) while the next segment computes.
             # Blocks are contiguous in the flat layout, so a slice is one contiguous range per branch.
@@ -208,12 +221,34 @@ class MFViTCATrainer:
         # mean over ranks (DDP semantics).  NCCL averages inside the collective (no extra pass over the 173 MB flat
         # gradient buffer); gloo (CPU tests) has no AVG, so pre-divide there.
         avg = torch.distributed.get_backend(self.pg) == "nccl"
-        for t in (grad, self._small.grad):
+        for t in ((self._small.grad,) if grad is None else (grad, self._small.grad)):
             if avg:
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG, group=self.pg)
             else:
                 t.div_(ws)
                 torch.distributed.all_reduce(t, group=self.pg)
+
+    def _small_ranges(self):
+        """Element ranges of the packed fusion / head buffer the optimizer steps: tensors that require grad, and - in
+        the reference's as-written mode - not the backbone heads (vhead_*, the last four tensors)."""
+        if getattr(self, "_sranges", None) is None:
+            fp = self._small
+            n_t = len(fp.params) if self.train_backbones else len(fp.params) - 4
+            out, off, run = [], 0, None
+            for i, p in enumerate(fp.params):
+                sz = (p.numel() + 3) // 4 * 4
+                if i < n_t and p.requires_grad:
+                    if run is not None and run[1] == off:
+                        run[1] = off + sz
+                    else:
+                        if run is not None:
+                            out.append(tuple(run))
+                        run = [off, off + sz]
+                off += sz
+            if run is not None:
+                out.append(tuple(run))
+            self._sranges = out
+        return self._sranges
 
     def optimizer_step(self, grad):
         eng = self.engine
@@ -238,11 +273,15 @@ class MFViTCATrainer:
                        self._adam_engine[g, sl] if adam else None, eng.shadow[g, sl],
                        eng.shadow16[g, sl] if eng.fwd_f16 else None)
             if not self._shadow_complete:
-                ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1),
-                                eng.shadow16.view(-1) if eng.fwd_f16 else None)  # frozen ranges, once
+                eng.cast_shadow()  # frozen ranges, once
                 self._shadow_complete = True
-            eng.shadow_fresh = True  # the step rewrote the GEMM shadows: the next forward skips the cast pass
-        update(self._small.master, self._small.grad, self._mom_small, self._adam_small if adam else None, None, None)
+            eng.mark_shadow_fresh()  # the step rewrote the GEMM shadows: the next forward skips the cast pass
+        else:
+            eng.mark_shadow_fresh()  # nobody steps the encoders here: the shadows the forward cast are still right
+        for lo, hi in self._small_ranges():
+            sl = slice(lo, hi)
+            update(self._small.master[sl], self._small.grad[sl], self._mom_small[sl],
+                   self._adam_small[sl] if adam else None, None, None)
         self.steps += 1
 
     def _step_eager(self, img_cxr, img_enh, target):
@@ -258,6 +297,12 @@ class MFViTCATrainer:
             for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
+            eng = self.engine
+            if eng._shadow_sig != eng._param_sig():
+                # the captured step holds no cast pass (its own optimizer rewrites the shadows): parameters edited from
+                # outside since the last replay (load_state_dict, p.copy_) are cast here, once
+                eng.cast_shadow()
+                eng.mark_shadow_fresh()
             self._graph.replay()
             self.steps += 1
             self.graph_replays += 1
@@ -279,7 +324,7 @@ class MFViTCATrainer:
         if self.optimizer != "sgd":
             state += [self._adam_engine, self._adam_small]
         snap = [t.clone() for t in state]
-        steps0, fresh0 = self.steps, eng.shadow_fresh
+        steps0 = self.steps
         self._g_inputs = [torch.empty_like(t) for t in (img_cxr, img_enh, target)]
         for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
             dst.copy_(src)
@@ -298,11 +343,11 @@ class MFViTCATrainer:
         # undo the warm-up steps (capture itself executes nothing); the 16-bit GEMM shadows are rebuilt from the master
         for dst, src in zip(state, snap):
             dst.copy_(src)
-        ops.cast_shadow(eng.master.view(-1), eng.shadow.view(-1), eng.shadow16.view(-1) if eng.fwd_f16 else None)
+        eng.cast_shadow()
         if self.metrics is not None:
             self.metrics.reset()  # the warm-up steps are not part of the epoch
         self.steps = max(steps0, 1)  # the captured step is a steady-state one (momentum buffers exist)
-        eng.shadow_fresh = True
+        eng.mark_shadow_fresh()
         self._graph = graph
         return self
 

@@ -78,7 +78,7 @@ def cos(a, b):
     return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
 
 
-def grad_report(named_ref, named_ours):
+def grad_report(named_ref, named_ours, to_cpu=False):
     """per-tensor cosine similarity of gradients; returns (min_cos, worst_name, table)."""
     ours = dict(named_ours)
     rows = []
@@ -87,6 +87,8 @@ def grad_report(named_ref, named_ours):
             continue
         g = ours[n].grad
         assert g is not None, "missing gradient for %s" % n
+        if to_cpu:
+            g = g.cpu()
         rows.append((cos(g, p.grad), n, float(p.grad.abs().max())))
     rows.sort()
     return rows[0][0], rows[0][1], rows

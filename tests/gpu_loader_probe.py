@@ -10,7 +10,7 @@ from mfvit.trainer import MFViTCATrainer
 B, img, steps = 32, 224, 40
 dev = torch.device("cuda", 0)
 _, (fus, cxr, enh) = E.build_mfvit_pair(seed=0)
-tr = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9)
+tr = MFViTCATrainer(fus, cxr, enh, lr=1e-3, momentum=0.9, train_backbones=True)
 batch = E.synthetic_pair(B, img, device="cuda")
 for _ in range(3):
     tr.step(*batch)

@@ -20,7 +20,7 @@ for v in (cxr, enh):
 fus = fm.Fus_CrossViT(cxr, enh)
 dev = torch.device("cuda:0")
 cxr.to(dev), enh.to(dev), fus.to(dev)
-tr = MFViTCATrainer(fus, cxr, enh)
+tr = MFViTCATrainer(fus, cxr, enh, train_backbones=True)
 c, e, t = E.synthetic_pair(B, 224, device=dev)
 for _ in range(2):
     loss = tr.step(c, e, t)

@@ -265,7 +265,7 @@ def test_loader_feeds_the_captured_step_and_metrics_stay_on_device():
     for use_loader in (True, False):
         _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=9)
         metrics = data.EpochMetrics(capacity=N, num_classes=3)
-        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics)
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics, train_backbones=True)
         tr.capture_graph(*E.synthetic_pair(B, crop, device="cuda"))
         assert int(metrics.counters[0]) == 0  # warm-up steps of the capture are not part of the epoch
         losses, vals = [], []
@@ -318,7 +318,7 @@ def test_run_phase_val_matches_the_oracle_and_train_updates():
     store = data.PairedU8Store(cxr, enh, labels)
     (r_f, r_c, r_e), (o_f, o_c, o_e) = E.build_mfvit_pair(seed=17)
     metrics = data.EpochMetrics(capacity=N, num_classes=3)
-    tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics)
+    tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, metrics=metrics, train_backbones=True)
     val = data.PairedDeviceLoader(store, B, crop=crop, training=False, shuffle=False)
     v_loss, v_auc, v_acc = loops.run_phase("val", tr, val, metrics, N)
     master0 = tr.engine.master.clone()
@@ -346,7 +346,7 @@ def test_run_phase_val_matches_the_oracle_and_train_updates():
     assert np.isfinite(t_loss) and not torch.equal(tr.engine.master, master0)
     assert int(metrics.counters[0]) == B
     with pytest.raises(data.MfvError):
-        loops.run_phase("train", MFViTCATrainer(o_f, o_c, o_e), train, metrics)
+        loops.run_phase("train", MFViTCATrainer(o_f, o_c, o_e, train_backbones=True), train, metrics)
 
 
 def test_store_from_csv_follows_the_reference_dataset(tmp_path):

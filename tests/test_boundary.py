@@ -217,3 +217,70 @@ def test_noprediction_builder_surface():
     ma, mb = mk(a), mk(b)
     assert sorted(ma.state_dict().keys()) == sorted(mb.state_dict().keys())
     assert ma.predictor_on_keys and not mb.predictor_on_keys and isinstance(mb, a.MoCo)
+
+
+def test_checkpoints_record_the_head_split_and_loaders_refuse_a_mismatch(tmp_path):
+    """qkv.weight is [1152, 384] for 6 heads of 64 and for 12 heads of 32: a state dict cannot tell, so
+    checkpoints written with model= carry the head count, a mismatch raises, and an unmarked checkpoint warns."""
+    import vits
+    from mfvit import checkpoint as ck
+    six = vits.vit_small(num_classes=3)
+    path = ck.save_checkpoint(str(tmp_path), {"state_dict": six.state_dict()}, is_best=True, model=six)
+    assert torch.load(path)["mfvit_arch"]["num_heads"] == 6
+    ck.load_finetuned_branch(vits.vit_small(num_classes=3), path)  # same split: silent
+    with pytest.raises(RuntimeError, match="attention heads"):
+        ck.load_finetuned_branch(vits.vit_small_ori(num_classes=3), path)
+    unmarked = ck.save_checkpoint(str(tmp_path), {"state_dict": six.state_dict()}, is_best=False)
+    with pytest.warns(UserWarning, match="12 heads of 32"):
+        ck.load_finetuned_branch(vits.vit_small(num_classes=3), unmarked)
+
+
+def test_shadow_freshness_follows_parameter_versions():
+    """a `fresh` flag set by the optimizer step must not survive an in-place edit of the fp32 master
+    (load_state_dict, p.copy_).  Host logic only: no kernels are launched here."""
+    import vits
+    from mfvit.engine import ViTEngine
+    m = vits.vit_small(num_classes=3)
+    eng = ViTEngine([m])
+    eng._params = [eng._named_params(0)]  # what adopt() records, without touching a device
+    eng.mark_shadow_fresh()
+    assert eng.shadow_is_current()
+    with torch.no_grad():
+        m.blocks[0].mlp.fc1.bias.add_(1.0)  # what torch.optim / p.copy_ do: bumps Parameter._version
+    assert not eng.shadow_is_current()
+    eng.mark_shadow_fresh()
+    m.load_state_dict(vits.vit_small(num_classes=3).state_dict())
+    assert not eng.shadow_is_current() and eng._shadow_sig is None  # post-hook invalidated it
+    eng.mark_shadow_fresh()
+    eng.invalidate_shadow()  # what raw writers (EMA kernel, p.data edits) must call
+    assert not eng.shadow_is_current()
+
+
+def test_label_tensors_are_validated_before_the_kernel_sees_them():
+    from mfvit import MfvError, ops
+    logits = torch.zeros(4, 3)
+    for bad in (torch.zeros(4, dtype=torch.int32), torch.zeros(5, dtype=torch.int64), torch.zeros(4, 1, dtype=torch.int64)):
+        with pytest.raises(MfvError, match="int64"):
+            ops._check_labels(bad, 4, logits.device, "ce_small")
+    ops._check_labels(torch.zeros(4, dtype=torch.int64), 4, logits.device, "ce_small")
+
+
+def test_trainer_default_is_the_reference_optimisation_set():
+    """MAIN_CA:435-449: the optimizer is built over Fus_CrossViT.parameters() - 22 tensors; backbones and their heads are
+    never stepped.  Checks the packed-buffer ranges the fused optimizer kernels are given."""
+    import vits_returnftrs as vits
+    from mfvit.trainer import FlatParams, MFViTCATrainer
+    fm = importlib.import_module(FUS_MOD)
+    cxr, enh = vits.vit_small(num_classes=3), vits.vit_small(num_classes=3)
+    fus = fm.Fus_CrossViT(cxr, enh)
+    n_fusion = sum((p.numel() + 3) // 4 * 4 for p in fus.parameters())
+    for full in (False, True):
+        tr = MFViTCATrainer(fus, cxr, enh, train_backbones=full)
+        params, _ = fus._fusion_params(cxr, enh)
+        tr._small = FlatParams(params, torch.device("cpu"))
+        covered = sum(hi - lo for lo, hi in tr._small_ranges())
+        assert covered == (tr._small.n if full else n_fusion)
+    fus.mlp_head_cxr[0].bias.requires_grad = False  # requires_grad is honoured inside the packed buffer
+    tr = MFViTCATrainer(fus, cxr, enh)
+    tr._small = FlatParams(fus._fusion_params(cxr, enh)[0], torch.device("cpu"))
+    assert sum(hi - lo for lo, hi in tr._small_ranges()) == n_fusion - 4

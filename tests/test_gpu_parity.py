@@ -274,7 +274,7 @@ def test_cuda_graph_step_equals_eager_step():
     runs = []
     for use_graph in (False, True):
         _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=9)
-        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9)
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=1e-3, momentum=0.9, train_backbones=True)
         if use_graph:
             before = None
             tr._prepare(batches[0][0].device)
@@ -322,7 +322,7 @@ def test_trainer_optimizers_match_torch_optim(name):
     against torch.optim on the same gradients; frozen ranges (pos_embed) see neither update nor weight decay."""
     from mfvit.trainer import MFViTCATrainer
     _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=21)
-    tr = MFViTCATrainer(o_f, o_c, o_e, lr=2e-3, momentum=0.9, weight_decay=1e-2, optimizer=name)
+    tr = MFViTCATrainer(o_f, o_c, o_e, lr=2e-3, momentum=0.9, weight_decay=1e-2, optimizer=name, train_backbones=True)
     img_c, img_e, tgt = E.synthetic_pair(4, 224, device="cuda")
     _, grad = tr.forward_backward(img_c, img_e, tgt)
     grad = grad.clone()
@@ -372,7 +372,7 @@ def test_learning_rate_schedule_reaches_the_captured_step():
     runs = []
     for use_graph in (True, False):
         _, (o_f, o_c, o_e) = E.build_mfvit_pair(seed=5)
-        tr = MFViTCATrainer(o_f, o_c, o_e, lr=sched[0], momentum=0.9, optimizer="adam")
+        tr = MFViTCATrainer(o_f, o_c, o_e, lr=sched[0], momentum=0.9, optimizer="adam", train_backbones=True)
         if use_graph:
             tr.capture_graph(*batches[0])
         losses = []
