@@ -165,6 +165,104 @@ def cpu_reference_rate(img, sample_pairs, steps, warmup):
     return sample_pairs / dt, dt, torch.get_num_threads()
 
 
+def gpu_eager_reference(img, B, device, steps=8, warmup=3):
+    """The "kernel to beat" on the same B200 (SURVEY 8(d) last row): the reference graph in stock
+    PyTorch - cuBLASLt / ATen library kernels - (i) fp32 as written (4 backbone passes, FUS:128-135), (ii) fp32
+    de-duplicated, (iii) bf16 autocast de-duplicated, (iv) the same with F.scaled_dot_product_attention (flash / cuDNN
+    kernels) in place of the explicit softmax.  fwd + bwd + SGD step on every parameter, like the measured step.  A
+    baseline leg like cpu_baseline: it runs the oracle port, after and outside every timed region of this repo's path."""
+    import torch.nn.functional as F
+
+    import e2e_common as E
+    from oracle import vit_ref
+    out = {"unit": UNIT, "pairs_per_step": B, "steps": steps,
+           "what": "oracle port of the reference modules under stock PyTorch %s on the same GPU, fwd+bwd+SGD, "
+                   "CUDA-event timed" % torch.__version__}
+    fus, cxr, enh, opt = build_oracle(img)
+    for m in (fus, cxr, enh):
+        m.to(device)
+    opt = torch.optim.SGD([p for m in (fus, cxr, enh) for p in m.parameters() if p.requires_grad], lr=1e-3, momentum=0.9)
+    img_c, img_e, tgt = (t.to(device) for t in E.synthetic_pair(B, img))
+    plain_attention = vit_ref.Attention.forward
+
+    def sdpa_attention(self, x):
+        Bq, N, C = x.shape
+        qkv = self.qkv(x).reshape(Bq, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale)
+        return self.proj(o.transpose(1, 2).reshape(Bq, N, C))
+
+    def timed(dedup, autocast, sdpa):
+        vit_ref.Attention.forward = sdpa_attention if sdpa else plain_attention
+        try:
+            def one():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    fused, x_c, x_e = fus(cxr, enh, img_c, img_e, dedup=dedup)
+                    loss = F.cross_entropy((fused + x_c + x_e).float(), tgt)
+                loss.backward()
+                opt.step()
+            for _ in range(warmup):
+                one()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                one()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            return {"pairs_per_s": B / ms * 1e3, "ms_per_step": ms}
+        finally:
+            vit_ref.Attention.forward = plain_attention
+
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out["fp32_as_written"] = timed(False, False, False)
+        out["fp32_dedup"] = timed(True, False, False)
+        out["bf16_autocast_dedup"] = timed(True, True, False)
+        out["bf16_autocast_dedup_sdpa"] = timed(True, True, True)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    del fus, cxr, enh, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_gradient_check(trainer, device, rank, world, img, pairs=8):
+    """Data-parallel correctness on the hardware the scaling numbers come from: the all-reduced gradient of `pairs`
+    pairs per rank equals the gradient ONE rank computes on the concatenated batch (same replica, all-reduce off).
+    Runs through MFViTCATrainer.forward_backward + all_reduce, i.e. the same NCCL path as the timed step."""
+    import torch.distributed as dist
+
+    import e2e_common as E
+    c, e, t = (x.to(device) for x in E.synthetic_pair(pairs, img, rank=900 + rank))
+    graph, trainer._graph = trainer._graph, None
+    local0 = trainer.local_only
+    try:
+        trainer.local_only = False
+        _, g = trainer.forward_backward(c, e, t, reduce_async=True)
+        trainer.all_reduce(g)
+        g_dp, s_dp = g.clone(), trainer._small.grad.clone()
+        gc = [torch.empty_like(c) for _ in range(world)]
+        ge = [torch.empty_like(e) for _ in range(world)]
+        gt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gc, c), dist.all_gather(ge, e), dist.all_gather(gt, t)
+        trainer.local_only = True
+        _, g1 = trainer.forward_backward(torch.cat(gc), torch.cat(ge), torch.cat(gt))
+        s1 = trainer._small.grad
+        cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+        res = {"pairs_per_rank": pairs, "encoder_grad_cos": cos(g_dp, g1), "fusion_grad_cos": cos(s_dp, s1),
+               "encoder_grad_max_rel": float((g_dp - g1).abs().max() / g1.abs().max().clamp_min(1e-30)),
+               "what": "all-reduced gradient of %d pairs/rank vs one rank on the concatenated %d pairs"
+                       % (pairs, pairs * world)}
+        res["ok"] = res["encoder_grad_cos"] >= 0.9999 and res["fusion_grad_cos"] >= 0.9999
+        return res
+    finally:
+        trainer.local_only = local0
+        trainer._graph = graph
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -174,7 +272,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, per_gpu=args.pairs_per_gpu),
+        "config": dict(workload_config(args, per_gpu=args.pairs_per_gpu),
+                       reference_arm_ran="ONE process on the host cores, %d pairs per step, no GPU and no data "
+                                         "parallelism (the reference's MAIN_CA is single-device, MAIN_CA:59-60); the "
+                                         "value is that process's pairs/s whatever --gpus says" % sample),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d pairs per step, as-written graph (4 backbone passes, FUS:128-135), oracle port of "
                                    "the reference (timm ViT is absent from the reference tree), fp32, %d threads"
@@ -207,6 +308,9 @@ def main():
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--cpu-sample-pairs", type=int, default=32, help="pairs per CPU step (32 = the batch of configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-moco", action="store_true", help="skip the MoCo pretraining-step leg (key moco_dp)")
+    ap.add_argument("--moco-batch", type=int, default=128, help="images per GPU and view of the MoCo leg (configs[3])")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the stock-PyTorch GPU baseline leg (N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the "
                                                             "CUDA graph of the step (single-GPU runs)")
     args = ap.parse_args()
@@ -420,6 +524,49 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms, local_ms = (float(v) for v in t)
 
+    graph_launches = trainer.graph_launches
+    # ---- data-parallel correctness on this hardware (N > 1): all-reduced gradient == one rank on the concatenated batch
+    dp_check = None
+    if world > 1:
+        try:
+            dp_check = dp_gradient_check(trainer, device, rank, world, img)
+        except Exception as exc:  # noqa: BLE001 - a failed self-check must not lose the measured line
+            dp_check = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+
+    # ---- BASELINE configs[3]: the MoCo-v3-structure / v2-loss pretraining step under SyncBatchNorm + DDP over NCCL
+    # (MAIN_PRE:297,312), 128 images per GPU, K = 65 536, with its self-checks (tests/moco_dp_common.py).  N = 1 runs it
+    # over a 1-rank NCCL group.
+    moco_dp = None
+    if not args.no_moco:
+        trainer._graph = None
+        torch.cuda.empty_cache()
+        try:
+            import moco_dp_common
+            if world == 1 and not dist.is_initialized():
+                import socket
+                sk = socket.socket()
+                sk.bind(("127.0.0.1", 0))
+                port = sk.getsockname()[1]
+                sk.close()
+                dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1,
+                                        device_id=device)
+            moco_dp = moco_dp_common.run(device, rank, world, batch=args.moco_batch, steps=min(args.steps, 10), warmup=3)
+        except Exception as exc:  # noqa: BLE001
+            moco_dp = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+        if world == 1 and dist.is_initialized():
+            try:
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001
+                pass
+
+    # ---- the kernel to beat: the reference graph under stock PyTorch on this GPU (rank 0, N = 1 only)
+    eager_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            eager_ref = gpu_eager_reference(img, B, device)
+        except Exception as exc:  # noqa: BLE001
+            eager_ref = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank == 0:
         peaks = measured_peaks()
         pairs = B * world
@@ -464,15 +611,33 @@ def main():
                                 "profiles/r01_hbm_bench.log"}
         step_tf = value * pair_flops(img) / 1e12
         h2d = sum(t.numel() * t.element_size() for t in host[0])
+        same_work = None if local_ms is None else {
+            "value_per_gpu": B * args.steps / (local_ms * 1e-3), "unit": UNIT + " per GPU",
+            "ms_per_step": local_ms / args.steps,
+            "exposed_allreduce_ms": elapsed_ms / args.steps - local_ms / args.steps,
+            "what": "every rank stepping its own replica on the same %d pairs with the all-reduce switched off (max "
+                    "over ranks): the single-GPU rate at THIS per-GPU batch, i.e. the weak-scaling denominator (N = 1 "
+                    "of this benchmark runs configs[1], 32 pairs)" % B}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 operands fwd / bf16 operands bwd, fp32 accumulate + fp32 residual stream and master weights",
-            "data": "synthetic", "config": workload_config(args, per_gpu=B),
-            "clocks": clocks,
+            "data": "synthetic",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / e_steps},
+            "gpu_launches": launches,
+            # data-parallel runs: the honest weak-scaling denominator and the correctness of the reduction, up front
+            "same_work_no_allreduce": same_work,
+            "dp_gradient_check": dp_check,
+            "moco_dp": moco_dp,
+            "roofline": roof,
+            "config": dict(workload_config(args, per_gpu=B),
+                           trained_parameters="all: both ViT-S/16 encoders, their heads and the fusion (full fine-tuning, "
+                                              "MFViTCATrainer(train_backbones=True)); the reference as written steps "
+                                              "only the fusion's 22 tensors (MAIN_CA:435-449)"),
+            "clocks": clocks,
+            "gpu_eager_reference": eager_ref,
             "e2e_u8_loader": {"value": pairs * e_steps / (u8_ms * 1e-3), "unit": UNIT,
                               "h2d_bytes_per_step": loader.h2d_bytes_per_batch, "d2h_bytes_per_step": 4,
                               "ms_per_step": u8_ms / e_steps,
@@ -482,15 +647,8 @@ def main():
                               "path": "pinned uint8 store -> gather -> H2D -> mfv_augment_u8 (flip, +-1 deg rotation, "
                                       "crop, normalise) x 2 on the copy stream -> step; not the headline e2e (that one copies the float32 "
                                       "tensors the reference's loaders produce)"},
-            "gpu_launches": launches,
-            "same_work_no_allreduce": None if local_ms is None else {
-                "value_per_gpu": B * args.steps / (local_ms * 1e-3), "unit": UNIT + " per GPU",
-                "ms_per_step": local_ms / args.steps,
-                "what": "every rank stepping its own replica on the same %d pairs with the all-reduce switched off "
-                        "(max over ranks): the single-GPU rate at this per-GPU batch" % B},
-            "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % trainer.graph_launches
+            "launch_mode": "CUDA graph of the whole step (%d kernels per replay)" % graph_launches
                            if use_graph else "eager stream launches",
-            "roofline": roof,
             "roofline_hbm": roof_hbm,
             "step_tflops": step_tf,
             "step_frac_of_bf16_peak": {"measured_sustained": step_tf / peaks["bf16_sustained"] / world,

@@ -27,6 +27,8 @@ _BLOCK_FIELDS = [
 # Forward GEMM operand format.  "fp16": IEEE half operands in the forward (8x finer than bf16 -> logits within 2e-3 of the
 # fp32 reference), bf16 in the backward (range-safe gradients).  "bf16": bf16 everywhere (no dual-format activations).
 FWD_PRECISION = os.environ.get("MFVIT_FWD_PRECISION", "fp16")
+FP16_SAFE_BOUND = 3.0e4     # half of the largest finite fp16 value: headroom for the GEMMs' own rounding
+FP16_CHECK_EVERY = 64       # shadow casts between two range checks (weights move slowly; the bound has 10-100x slack)
 
 
 def _align8(n):
@@ -170,6 +172,7 @@ class ViTEngine:
         self.grad_idx = 0
         self.shadow_fresh = False
         self._shadow_sig = None  # parameter versions the 16-bit shadows were last known to match
+        self._casts = 0
         self._ws = {}
         self._params = None  # per group: list of (name, Parameter)
         ref = weakref.ref(self)
@@ -256,8 +259,58 @@ class ViTEngine:
 
     def refresh_shadow(self):
         if not self.shadow_is_current():
+            self._casts += 1
+            if self.fwd_f16 and (self._casts == 1 or self._casts % FP16_CHECK_EVERY == 0):
+                self.check_fp16_range()
             self.cast_shadow()
         self.shadow_fresh = False  # a fresh flag is consumed by exactly one forward
+
+    # ------------------------------------------------------------------------------------------ fp16 range policy
+    # The fp16-forward mode stores xn, qkv, attn_o and gelu(u) as IEEE half (max 65504).  Instead of testing every
+    # element in the issue-bound GEMM epilogues, the engine PROVES the forward cannot overflow from the weights alone:
+    # LayerNorm output rows have ||xn||_2 <= sqrt(C) max|gamma| + ||beta||_2, so every output of the Linear that follows
+    # is bounded by that times the largest weight-row norm plus the largest bias (Cauchy-Schwarz); attention outputs are
+    # convex combinations of v rows; gelu(u) <= |u|.  While the bound stays below FP16_SAFE_BOUND the fp16 forward is
+    # safe for ANY input; when it does not (weights of pathological scale), the engine switches itself to the all-bf16
+    # forward (same kernels, bf16 operands: no overflow below 3e38, logits within the bf16 tolerance) and warns once.
+    def fp16_range_bound(self):
+        """Upper bound (device scalar) of |value| over every fp16-stored forward activation, for any input."""
+        lay, m = self.layout, self.master
+        C_, D = lay.C, lay.depth
+        rel = {nm: lay.offset["blocks.0." + nm] - lay.off_block0 for nm, _ in _BLOCK_FIELDS}
+
+        def blk(name, *shape):  # [G, depth, *shape] strided view of one tensor of every block
+            st = [lay.P, lay.block_stride]
+            acc = 1
+            tail = []
+            for d in reversed(shape):
+                tail.append(acc)
+                acc *= d
+            return m.as_strided((self.G, D) + tuple(shape), tuple(st + tail[::-1]), lay.off_block0 + rel[name])
+
+        worst = m.new_zeros(())
+        for ln, w, b, N in (("norm1", "attn.qkv", "attn.qkv", 3 * C_), ("norm2", "mlp.fc1", "mlp.fc1", lay.hidden)):
+            gam, bet = blk(ln + ".weight", C_), blk(ln + ".bias", C_)
+            xn_l2 = (C_ ** 0.5) * gam.abs().amax(-1) + bet.norm(dim=-1)            # [G, depth]
+            xn_abs = (C_ ** 0.5) * gam.abs().amax(-1) + bet.abs().amax(-1)
+            rows = blk(w + ".weight", N, C_).norm(dim=-1).amax(-1)                 # largest weight-row norm
+            out = xn_l2 * rows + blk(b + ".bias", N).abs().amax(-1)
+            worst = torch.maximum(worst, torch.maximum(out.max(), xn_abs.max()))
+        return worst
+
+    def check_fp16_range(self):
+        """Switches the engine to the bf16 forward when the fp16 one is not provably overflow-free.  Returns the bound."""
+        if not self.fwd_f16 or self.master is None:
+            return None
+        bound = float(self.fp16_range_bound())
+        if not (bound < FP16_SAFE_BOUND):  # also catches NaN / inf weights
+            import warnings
+            warnings.warn("mfvit: forward activations may reach %.3g, beyond the fp16 range bound %.3g for these weights; "
+                          "this encoder now runs its forward with bf16 operands (MFVIT_FWD_PRECISION=bf16 selects that "
+                          "from the start)" % (bound, FP16_SAFE_BOUND))
+            self.fwd_f16 = False
+            self.invalidate_shadow()
+        return bound
 
     # ------------------------------------------------------------------------------------------ plan / workspaces
     def _workspace(self, B, save):

@@ -62,3 +62,35 @@ def cosine_momentum(epoch_float, total_epochs, m0):
     """MAIN_PRE:626-629."""
     import math
     return 1.0 - 0.5 * (1.0 + math.cos(math.pi * epoch_float / total_epochs)) * (1.0 - m0)
+
+
+class MoCoViT(nn.Module):
+    """The whole model of BLD:16-60,215-225 and its forward BLD:154-199, assembled from the functions above over the
+    oracle ViT (oracle/vit_ref.py).  Test infrastructure: the module tree and state-dict keys equal the reference's, so
+    weights move between this class, the real reference class (tests/golden/moco_ref.pt pins the pieces against it) and
+    the drop-in with load_state_dict(strict=True)."""
+
+    def __init__(self, base_encoder, dim=256, mlp_dim=4096, T=1.0, K=65536):
+        super().__init__()
+        self.T, self.K = T, K
+        self.base_encoder = base_encoder(num_classes=mlp_dim)                    # BLD:28-30
+        self.momentum_encoder = base_encoder(num_classes=mlp_dim)
+        hidden = self.base_encoder.head.weight.shape[1]                          # BLD:216-225
+        del self.base_encoder.head, self.momentum_encoder.head
+        self.base_encoder.head = build_mlp(3, hidden, mlp_dim, dim)
+        self.momentum_encoder.head = build_mlp(3, hidden, mlp_dim, dim)
+        self.predictor = build_mlp(2, dim, mlp_dim, dim)
+        for pb, pm in zip(self.base_encoder.parameters(), self.momentum_encoder.parameters()):   # BLD:48-52
+            pm.data.copy_(pb.data)
+            pm.requires_grad = False
+        self.register_buffer("queue", F.normalize(torch.randn(dim, K), dim=0))  # BLD:55-57
+        self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+
+    def forward(self, im_q, im_k, m):
+        q = self.predictor(self.base_encoder(im_q))                              # BLD:163-164
+        with torch.no_grad():                                                    # BLD:168-181 (shuffle: identity at 1 rank)
+            ema_update(list(self.momentum_encoder.parameters()), list(self.base_encoder.parameters()), m)
+            k = self.predictor(self.momentum_encoder(im_k))
+        logits, labels, _, kn = infonce_logits(q, k, self.queue, self.T)          # BLD:165,175,183-194
+        dequeue_and_enqueue(self.queue, self.queue_ptr, kn.detach(), self.K)     # BLD:197
+        return logits, labels

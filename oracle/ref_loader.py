@@ -38,11 +38,14 @@ class _RefPath:
         self.saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("model", "moco")}
         for k in self.saved:
             del sys.modules[k]
-        sys.path.insert(0, REF_ROOT)
+        # the reference's moco/ has no __init__.py (a namespace package): a regular package of the same name anywhere
+        # on sys.path - the drop-in's - would win, so the drop-in directory is hidden for the duration of the import
+        self.saved_path = list(sys.path)
+        sys.path[:] = [REF_ROOT] + [p for p in sys.path if os.path.basename(os.path.normpath(p)) != "dropin"]
         return self
 
     def __exit__(self, *exc):
-        sys.path.remove(REF_ROOT)
+        sys.path[:] = self.saved_path
         self.loaded = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("model", "moco")}
         for k in self.loaded:
             del sys.modules[k]

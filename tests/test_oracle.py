@@ -184,3 +184,98 @@ def test_cosine_momentum_schedule():
     assert abs(moco_ref.cosine_momentum(0.0, 100, 0.99) - 0.99) < 1e-12
     assert abs(moco_ref.cosine_momentum(100.0, 100, 0.99) - 1.0) < 1e-12
     assert 0.99 < moco_ref.cosine_momentum(50.0, 100, 0.99) < 1.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (authoring container)")
+def test_whole_model_moco_restatement_equals_the_real_reference_class():
+    """oracle/moco_ref.MoCoViT (used by the GPU parity tests as the MoCo step oracle) against the REAL MoCo_ViT.forward
+    of BLD on the same tiny encoder, seed and inputs: logits, labels, queue and pointer are identical (the reference's
+    batch shuffle permutes which rows share nothing at one rank, so results agree exactly)."""
+    from functools import partial
+    from types import SimpleNamespace
+
+    import torch.distributed as dist
+    from oracle import ref_loader
+    _, _, bld_py = ref_loader.load_reference()
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # BLD:121,194 hard-code .cuda()
+    try:
+        factory = partial(vit_ref.VisionTransformerMoCo, img_size=32, patch_size=16, embed_dim=64, depth=2, num_heads=2)
+        torch.manual_seed(77)
+        real = bld_py.MoCo_ViT(factory, SimpleNamespace(arch="vit_tiny"), 32, 48, 0.2)
+        mine = moco_ref.MoCoViT(factory, 32, 48, 0.2)
+        mine.load_state_dict(real.state_dict(), strict=True)
+        with torch.no_grad():
+            for a, b in zip(real.base_encoder.parameters(), mine.base_encoder.parameters()):
+                d = torch.randn_like(a) * 0.01
+                a.add_(d)
+                b.add_(d)
+        real.eval(), mine.eval()  # running statistics: the shuffle of BLD:171 cannot change anything
+        im_q, im_k = torch.randn(8, 3, 32, 32), torch.randn(8, 3, 32, 32)
+        for step in range(2):
+            lr, yr = real(im_q, im_k, 0.99)
+            lm, ym = mine(im_q, im_k, 0.99)
+            assert torch.allclose(lr, lm, atol=1e-6), float((lr - lm).abs().max())
+            assert torch.equal(yr, ym) and int(real.queue_ptr) == int(mine.queue_ptr) == 8 * (step + 1)
+            assert torch.allclose(real.queue, mine.queue, atol=1e-7)
+            for a, b in zip(real.momentum_encoder.parameters(), mine.momentum_encoder.parameters()):
+                assert torch.equal(a, b)  # EMA bit-exact
+    finally:
+        torch.Tensor.cuda = saved_cuda
+
+
+def test_pos_embed_against_an_independent_hand_written_sincos():
+    """dropin/vits.py and oracle/vit_ref.py share their sin-cos code, and the torchvision cross-check copies
+    pos_embed across - so the layout is pinned here by a scalar loop written from the MoCo-v3 definition alone
+    (facebookresearch/moco-v3 vits.py, build_2d_sincos_position_embedding): `grid_w, grid_h = meshgrid(arange(w),
+    arange(h))` with torch's default 'ij' indexing makes grid_w vary along the FIRST axis, and both grids are flattened
+    row-major.  Token t of the flattened Conv2d output (patch row t // grid, patch column t % grid) therefore gets
+    a = t // grid in the "w" blocks and b = t % grid in the "h" blocks:
+        [sin(a w_d), cos(a w_d), sin(b w_d), cos(b w_d)],  w_d = 10000^(-d / (C/4)),
+    i.e. upstream's "w" runs over patch ROWS - a quirk that is invisible on square grids but fixes which axis lands in
+    which channel block; the class token gets a zero row."""
+    import math
+
+    import vits
+    C, grid = 384, 14
+    quarter = C // 4
+    expect = torch.zeros(1 + grid * grid, C, dtype=torch.float64)
+    for t in range(grid * grid):
+        a, b = t // grid, t % grid
+        for d in range(quarter):
+            omega = 1.0 / (10000.0 ** (d / quarter))
+            expect[1 + t, d] = math.sin(a * omega)
+            expect[1 + t, quarter + d] = math.cos(a * omega)
+            expect[1 + t, 2 * quarter + d] = math.sin(b * omega)
+            expect[1 + t, 3 * quarter + d] = math.cos(b * omega)
+    for mod in (vits.vit_small(), vit_ref.vit_small()):
+        pe = mod.pos_embed.detach()[0].double()
+        assert pe.shape == expect.shape and not mod.pos_embed.requires_grad
+        assert (pe - expect).abs().max().item() < 2e-6
+    # a 24 x 24 grid (384 x 384 inputs) follows the same rule
+    pe = vits.vit_small(img_size=384).pos_embed.detach()[0].double()
+    a, b, d = 17, 5, 3
+    omega = 1.0 / (10000.0 ** (d / quarter))
+    row = 1 + a * 24 + b
+    assert abs(float(pe[row, d]) - math.sin(a * omega)) < 2e-6 and abs(float(pe[row, 2 * quarter + d]) - math.sin(b * omega)) < 2e-6
+
+
+def test_schedules_follow_the_reference_formulas():
+    """MAIN_PRE:608-629 and MAIN_CA:1043-1055, evaluated by hand at a few points."""
+    import math
+
+    from mfvit import schedules as S
+    lr = S.base_lr(1.5e-4, 1024)                       # MAIN_PRE:286-288: lr * batch / 4
+    assert abs(lr - 1.5e-4 * 256) < 1e-12 and S.base_lr(0.03, 256, cos=False) == 0.03
+    assert S.pretrain_lr(0.0, lr, 100, 10) == 0.0 and abs(S.pretrain_lr(5.0, lr, 100, 10) - lr / 2) < 1e-12
+    assert abs(S.pretrain_lr(10.0, lr, 100, 10) - lr) < 1e-12
+    assert abs(S.pretrain_lr(55.0, lr, 100, 10) - lr * 0.5 * (1 + math.cos(math.pi * 45 / 90))) < 1e-12
+    assert abs(S.pretrain_lr(100.0, lr, 100, 10)) < 1e-12
+    assert abs(S.pretrain_lr(61.0, 1.0, 100, cos=False, schedule=(30, 60)) - 0.01) < 1e-12
+    assert abs(S.moco_momentum(0.0, 100, 0.99) - 0.99) < 1e-12 and abs(S.moco_momentum(100.0, 100, 0.99) - 1.0) < 1e-12
+    assert abs(S.moco_momentum(25.0, 100, 0.99) - moco_ref.cosine_momentum(25.0, 100, 0.99)) < 1e-15
+    assert abs(S.finetune_lr(25, 0.1, 50, cos=True) - 0.05) < 1e-12 and S.finetune_lr(45, 0.1, 50, schedule=(20, 40)) == pytest.approx(0.001)
