@@ -78,12 +78,18 @@ def cos(a, b):
     return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
 
 
-def grad_report(named_ref, named_ours, to_cpu=False):
-    """per-tensor cosine similarity of gradients; returns (min_cos, worst_name, table)."""
+def grad_report(named_ref, named_ours, to_cpu=False, skip_zero=False):
+    """per-tensor cosine similarity of gradients; returns (min_cos, worst_name, table).  skip_zero: leave out tensors
+    whose reference gradient is zero up to rounding (< 1e-6 of the largest gradient entry of the model) - e.g. the final
+    LayerNorm bias in front of a bias-free Linear + train-mode BatchNorm, whose true gradient is exactly 0."""
     ours = dict(named_ours)
     rows = []
+    named_ref = list(named_ref)
+    top = max([float(p.grad.abs().max()) for _, p in named_ref if p.grad is not None] + [0.0])
     for n, p in named_ref:
         if p.grad is None:
+            continue
+        if skip_zero and float(p.grad.abs().max()) < 1e-6 * top:
             continue
         g = ours[n].grad
         assert g is not None, "missing gradient for %s" % n

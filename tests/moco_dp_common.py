@@ -45,10 +45,14 @@ def structured_views(B, hw, rank, device):
 
 
 def _grad_cos(named_a, named_b):
+    """min per-tensor gradient cosine; tensors whose gradient is zero up to rounding are left out (the final LayerNorm
+    bias feeds a bias-free Linear + train-mode BatchNorm: its true gradient is exactly 0, what is there is 1e-8 noise)."""
     b = dict(named_b)
+    named_a = list(named_a)
+    top = max([float(p.grad.abs().max()) for _, p in named_a if p.grad is not None] + [0.0])
     worst, name = 1.0, None
     for n, p in named_a:
-        if p.grad is None:
+        if p.grad is None or float(p.grad.abs().max()) < 1e-6 * top:
             continue
         c = E.cos(p.grad, b[n].grad)
         if c < worst:
@@ -85,7 +89,7 @@ def run(device, rank, world, batch=128, steps=10, warmup=3, check_batch=None, hw
     F.cross_entropy(single_logits, single_labels).backward()
     mine = single_logits[rank * cb:(rank + 1) * cb]
     # the keys this step enqueued are part of neither logits (enqueue happens after the logits), so columns agree 1:1
-    out["parity_logits_max_abs"] = float((logits - mine).abs().max())
+    out["parity_logits_max_abs"] = float((logits.detach() - mine.detach()).abs().max())
     worst, name = _grad_cos(single.base_encoder.named_parameters(), ddp.module.base_encoder.named_parameters())
     w2, n2 = _grad_cos(single.predictor.named_parameters(), ddp.module.predictor.named_parameters())
     out["parity_grad_cos_min"] = min(worst, w2)
