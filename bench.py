@@ -238,9 +238,10 @@ def dp_gradient_check(trainer, device, rank, world, img, pairs=8):
     import e2e_common as E
     c, e, t = (x.to(device) for x in E.synthetic_pair(pairs, img, rank=900 + rank))
     graph, trainer._graph = trainer._graph, None
-    local0 = trainer.local_only
+    local0, ovl0 = trainer.local_only, trainer.overlap_optimizer
     try:
         trainer.local_only = False
+        trainer.overlap_optimizer = False  # gradients only: nothing may be stepped between the two passes
         _, g = trainer.forward_backward(c, e, t, reduce_async=True)
         trainer.all_reduce(g)
         g_dp, s_dp = g.clone(), trainer._small.grad.clone()
@@ -259,7 +260,7 @@ def dp_gradient_check(trainer, device, rank, world, img, pairs=8):
         res["ok"] = res["encoder_grad_cos"] >= 0.9999 and res["fusion_grad_cos"] >= 0.9999
         return res
     finally:
-        trainer.local_only = local0
+        trainer.local_only, trainer.overlap_optimizer = local0, ovl0
         trainer._graph = graph
 
 

@@ -35,8 +35,9 @@ int mfv_init(int device);
 const char* mfv_strerror(int code);
 /* "file:line: expression" of the last CUDA runtime failure returned to this thread ("" if none); debugging aid. */
 const char* mfv_last_error_where(void);
-/* Runtime switches (A/B measurements, tests): key in {"pdl", "side_stream", "legacy_attention"}; the defaults come
- * from the environment (MFVIT_PDL=0, MFVIT_SIDE_STREAM=0, MFVIT_ATTN=legacy).                                       */
+/* Runtime switches (A/B measurements, tests): key in {"pdl", "side_stream", "legacy_attention", "rows96", "fuse_ln"};
+ * the defaults come from the environment (MFVIT_PDL=0, MFVIT_SIDE_STREAM=0, MFVIT_ATTN=legacy, MFVIT_ROWS96=1,
+ * MFVIT_FUSE_LN=0).                                                                                                 */
 int mfv_set_option(const char* key, int value);
 int mfv_num_sms(void);
 /* Number of kernels this library has launched so far in the process (bench.py reports the per-step delta). */
@@ -59,7 +60,11 @@ enum {
   MFV_EPI_RESID_F32 = 2,  /* C(f32)   = acc + bias + aux(f32)                               (proj, fc2)          */
   MFV_EPI_DGELU = 3,      /* C(bf16)  = acc * gelu_erf'(aux(bf16) = u)                      (fc2 dgrad)          */
   MFV_EPI_F32 = 4,        /* C(f32)   = acc + bias                                                               */
-  MFV_EPI_ATOMIC_F32 = 5  /* C(f32)  += acc  (red.global.add; split-K weight gradients)                          */
+  MFV_EPI_ATOMIC_F32 = 5, /* C(f32)  += acc  (red.global.add; split-K weight gradients)                          */
+  MFV_EPI_RESID_LN = 6    /* C(f32) = x = acc + bias + aux(f32) ; C2 = LayerNorm(x) (16-bit or f32), C3 = optional bf16
+                           * copy, ln_mean / ln_rstd = the row statistics.  N == 384 only: the 256 x 384 pair tile owns whole
+                           * rows, so proj / fc2 also emit the operand of the NEXT Linear (LayerNorm fused into
+                           * the producing epilogue; the standalone LayerNorm launch and its fp32 re-read disappear)      */
 };
 typedef struct {
   const void* A;
@@ -85,6 +90,14 @@ typedef struct {
    * sums of A over the reduction dimension, i.e. the bias gradient of a weight-gradient GEMM (A = dY read MN-major),
    * computed by one extra N=16 UMMA per k-step against a tile of ones.  NULL = off.                                */
   float* row_sum;
+  /* MFV_EPI_RESID_LN only: gamma / beta f32 [G][N] (group stride bias_gstride); mean / rstd f32 [G][M] outputs (group
+   * stride M) saved for the backward; eps; ln_out_f32 = 1: C2 is f32 [G][M][N] (the final norm writes the tokens). */
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
+  int32_t ln_out_f32;
 } mfv_gemm_args;
 int mfv_gemm(const mfv_gemm_args* args, void* stream);
 
@@ -96,11 +109,12 @@ int mfv_gemm(const mfv_gemm_args* args, void* stream);
 int mfv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16, int y16_is_f16,
                       void* y_bf16_copy, float* y_f32, float* mean, float* rstd, int64_t G, int64_t rows, int64_t C,
                       int64_t gb_gstride, float eps, void* stream);
-/* dx = dres (optional residual-path gradient, f32) + LN'(dy); dy is bf16 (dy_bf16) or f32 (dy_f32).
- * Writes dx as f32 and (optionally) a bf16 copy that feeds the next dgrad/wgrad GEMMs.
+/* dx = dres (optional residual-path gradient: f32 `dres` or bf16 `dres_bf16`, not both) + LN'(dy); dy is bf16
+ * (dy_bf16) or f32 (dy_f32).  Writes dx as f32 (dx_f32, optional) and / or as the bf16 copy that feeds the next
+ * dgrad / wgrad GEMMs (dx_bf16, optional).
  * dgamma/dbeta f32 [G][C] are ACCUMULATED (+=) with red.global.add; dx_colsum (optional, f32 [G][C], +=) receives the
  * column sums of dx, i.e. the bias gradient of the Linear whose output was added into x (proj / fc2), for free.                                                   */
-int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x, const float* mean,
+int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const void* dres_bf16, const float* x, const float* mean,
                       const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                       float* dx_colsum, int64_t G, int64_t rows, int64_t C, int64_t gb_gstride, void* stream);
 

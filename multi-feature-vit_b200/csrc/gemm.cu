@@ -43,6 +43,13 @@ struct GemmParams {
   float* row_sum;         // BN == 384, fp32 reduce-add epilogue: += row sums of A (bias gradient of a wgrad GEMM)
   long long bias_gstride;
   const float* bias;
+  // MFV_EPI_RESID_LN: LayerNorm of the finished row, fused into the epilogue (gamma / beta share bias_gstride)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
+  int ln_out_f32;
 };
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) computes 256 x BN; each CTA stages its own
@@ -61,13 +68,14 @@ struct GemmSmem {
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;  // TMEM accumulators: double-buffered when two fit in 512 columns
   static constexpr int BAR_BYTES = 512;
   static constexpr int ONES_BYTES = (BN == 384) ? 2048 : 0;  // [16 k][64 n] tile of 1.0 for the row-sum UMMA
+  static constexpr int LN_BYTES = (BN == 384) ? NUM_EPI_WARPS * 32 * 8 : 0;  // (mean, M2) of each warp's share of a row
   static constexpr int EPI_BYTES = NUM_EPI_WARPS * NBUF * EPI_BUF;
   // operand stages: what is left of the 227 KB after the epilogue rings (3 slots: 6/5/4/4/3/2 stages for 16/24/32/32/
   // 40/48 KB stages, 4 slots: one fewer from 32 KB up), at most 6
-  static constexpr int AVAIL = 232448 - 1024 - BAR_BYTES - ONES_BYTES - EPI_BYTES;
+  static constexpr int AVAIL = 232448 - 1024 - BAR_BYTES - ONES_BYTES - LN_BYTES - EPI_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES > 6) ? 6 : AVAIL / STAGE_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a double-buffered mainloop");
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + 1024;  // +1024: alignment
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + LN_BYTES + 1024;  // +1024: alignment
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -118,6 +126,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + S::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint8_t* ones_tile = bar_base + S::BAR_BYTES;  // BN == 384 only
+  float2* ln_part = reinterpret_cast<float2*>(ones_tile + S::ONES_BYTES);  // BN == 384 only: [16 warps][32 lanes]
   uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + AUX_BARS);
 
@@ -279,8 +288,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* abar = aux_bar + 2 * ew;
     uint32_t aux_phase = 0u;  // bit j = parity of abar[j]
     constexpr int epi = EPI;
-    constexpr bool has_aux = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_DGELU);
-    constexpr bool out32 = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_F32);
+    constexpr bool has_aux = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_DGELU || epi == MFV_EPI_RESID_LN);
+    constexpr bool out32 = (epi == MFV_EPI_RESID_F32 || epi == MFV_EPI_F32 || epi == MFV_EPI_RESID_LN);
+    static_assert(epi != MFV_EPI_RESID_LN || BN == 384, "the fused LayerNorm needs a tile that owns whole rows");
     constexpr int PW = out32 ? 16 : 32;  // columns per piece
     constexpr int npieces = BN / PW;
     auto slot_ptr = [&](uint32_t u) { return ring + (u % EPI_NBUF) * EPI_BUF; };
@@ -366,6 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         if (row0 + lane < p.M) atomicAdd(p.row_sum + (long long)g * p.bias_gstride + row0 + lane, __uint_as_float(rs));
       }
+      [[maybe_unused]] float ln_m = 0.f, ln_s = 0.f;  // MFV_EPI_RESID_LN: mean and sum of squared deviations so far
 #pragma unroll 1
       for (int i = 0; i < n_my; ++i) {
         const int c = h + 4 * i;
@@ -384,7 +395,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         }
-        if (i == n_my - 1) release_accumulator(as);  // last TMEM read of the tile: the MMA warp may reuse the buffer
+        if (epi != MFV_EPI_RESID_LN && i == n_my - 1)
+          release_accumulator(as);  // last TMEM read of the tile: the MMA warp may reuse the buffer
         if (bias) {
           const float* bp = bias + n0;
 #pragma unroll
@@ -451,6 +463,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             publish(&tmC, st0, n0, row0, g, false);
             if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
           }
+        } else if constexpr (epi == MFV_EPI_RESID_LN) {
+          {  // pass 1 of the fused LayerNorm: x = acc + bias + residual -> C (fp32) as above, x kept in TMEM over the
+             // accumulator, and the running (mean, M2) of this thread's columns (pairwise / Chan update: no cancellation)
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4* pp = reinterpret_cast<float4*>(st0 + stage_off(lane, j));
+              const float4 rr = *pp;
+              y[4 * j] = f[4 * j] + rr.x; y[4 * j + 1] = f[4 * j + 1] + rr.y;
+              y[4 * j + 2] = f[4 * j + 2] + rr.z; y[4 * j + 3] = f[4 * j + 3] + rr.w;
+              *pp = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            }
+            publish(&tmC, st0, n0, row0, g, false);
+            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
+            {
+              uint32_t yb[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) yb[k] = __float_as_uint(y[k]);
+              tmem_st16(trow + (uint32_t)(c * PW), yb);
+            }
+            float s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s1 += y[k];
+            const float pm = s1 * (1.0f / 16.0f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { const float d = y[k] - pm; m2 = fmaf(d, d, m2); }
+            if (i == 0) {
+              ln_m = pm; ln_s = m2;
+            } else {
+              const float na = 16.0f * (float)i, nn = na + 16.0f, dl = pm - ln_m;
+              ln_m = fmaf(dl, 16.0f / nn, ln_m);
+              ln_s += fmaf(dl * dl, na * 16.0f / nn, m2);
+            }
+          }
         } else if constexpr (epi == MFV_EPI_DGELU) {
           {  // C(bf16) = acc * gelu'(u) in place over u = aux (bf16); C2 (optional) = gelu(u) bf16
             uint32_t gk[16];
@@ -493,6 +540,93 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
                   make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             publish(&tmC, st0, n0, row0, g, p.epi == MFV_EPI_ATOMIC_F32);
+          }
+        }
+      }
+      if constexpr (epi == MFV_EPI_RESID_LN) {
+        // ---- row statistics: the four warps of this TMEM lane quarter own 96 columns each of the same 32 rows
+        tmem_st_wait();
+        ln_part[ew * 32 + lane] = make_float2(ln_m, ln_s);
+        tc_fence_before();
+        named_bar_sync(1u + (uint32_t)q, 128u);  // the four epilogue warps of TMEM lane quarter q: ew = (ew & 3) + 4 h
+        tc_fence_after();
+        float mean = 0.f, m2 = 0.f;
+        float2 part[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          part[k] = ln_part[((ew & 3) + 4 * k) * 32 + lane];
+          mean += part[k].x;
+          m2 += part[k].y;
+        }
+        mean *= 0.25f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float d = part[k].x - mean; m2 = fmaf(96.0f * d, d, m2); }
+        const float rstd = rsqrtf(m2 * (1.0f / 384.0f) + p.ln_eps);
+        if (h == 0 && row0 + lane < p.M) {
+          p.ln_mean[(long long)g * p.M + row0 + lane] = mean;
+          p.ln_rstd[(long long)g * p.M + row0 + lane] = rstd;
+        }
+                const float* gam = p.ln_gamma + (long long)g * p.bias_gstride + ncol0;
+        const float* bet = p.ln_beta + (long long)g * p.bias_gstride + ncol0;
+        // ---- pass 2: x back out of TMEM, normalised, to C2 (and C3)
+        if (!p.ln_out_f32) {
+#pragma unroll 1
+          for (int j = 0; j < 3; ++j) {  // 32-column pieces h, h + 4, h + 8 of the 12
+            const int c2 = h + 4 * j;
+            uint32_t v[32];
+            tmem_ld32(trow + (uint32_t)(c2 * 32), v);
+            tmem_ld_wait();
+            if (j == 2) release_accumulator(as);
+            float o[32];
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c2 * 32 + k));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bet + c2 * 32 + k));
+              o[k] = fmaf((__uint_as_float(v[k]) - mean) * rstd, g4.x, b4.x);
+              o[k + 1] = fmaf((__uint_as_float(v[k + 1]) - mean) * rstd, g4.y, b4.y);
+              o[k + 2] = fmaf((__uint_as_float(v[k + 2]) - mean) * rstd, g4.z, b4.z);
+              o[k + 3] = fmaf((__uint_as_float(v[k + 3]) - mean) * rstd, g4.w, b4.w);
+            }
+            uint8_t* s2 = slot_ptr(use);
+            acquire_slot();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              *reinterpret_cast<uint4*>(s2 + stage_off(lane, jj)) =
+                  make_uint4(pack16(o[8 * jj], o[8 * jj + 1]), pack16(o[8 * jj + 2], o[8 * jj + 3]),
+                             pack16(o[8 * jj + 4], o[8 * jj + 5]), pack16(o[8 * jj + 6], o[8 * jj + 7]));
+            publish(&tmC2, s2, ncol0 + c2 * 32, row0, g, false);
+            if (p.has_c3) {
+              uint8_t* s3 = slot_ptr(use);
+              acquire_slot();
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                *reinterpret_cast<uint4*>(s3 + stage_off(lane, jj)) =
+                    make_uint4(pack_bf16(o[8 * jj], o[8 * jj + 1]), pack_bf16(o[8 * jj + 2], o[8 * jj + 3]),
+                               pack_bf16(o[8 * jj + 4], o[8 * jj + 5]), pack_bf16(o[8 * jj + 6], o[8 * jj + 7]));
+              publish(&tmC3, s3, ncol0 + c2 * 32, row0, g, false);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < n_my; ++i) {  // fp32 output (final norm -> tokens): the 16-column pieces of pass 1
+            const int c = h + 4 * i;
+            uint32_t v[32];
+            tmem_ld16(trow + (uint32_t)(c * 16), v);
+            tmem_ld_wait();
+            if (i == n_my - 1) release_accumulator(as);
+            uint8_t* s2 = slot_ptr(use);
+            acquire_slot();
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + k));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + k));
+              *reinterpret_cast<float4*>(s2 + stage_off(lane, k >> 2)) =
+                  make_float4(fmaf((__uint_as_float(v[k]) - mean) * rstd, g4.x, b4.x),
+                              fmaf((__uint_as_float(v[k + 1]) - mean) * rstd, g4.y, b4.y),
+                              fmaf((__uint_as_float(v[k + 2]) - mean) * rstd, g4.z, b4.z),
+                              fmaf((__uint_as_float(v[k + 3]) - mean) * rstd, g4.w, b4.w));
+            }
+            publish(&tmC2, s2, ncol0 + c * 16, row0, g, false);
           }
         }
       }
@@ -593,6 +727,13 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 3;  // bit0: skip everything, bit1: skip the bulk stores
   p.bias_gstride = a->bias_gstride;
   p.bias = (const float*)a->bias;
+  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_mean = a->ln_mean; p.ln_rstd = a->ln_rstd;
+  p.ln_eps = a->ln_eps; p.ln_out_f32 = a->ln_out_f32;
+  if (EPI == MFV_EPI_RESID_LN) {
+    if (BN != 384 || a->N != 384 || !a->ln_gamma || !a->ln_beta || !a->ln_mean || !a->ln_rstd || !a->C2 || !a->bias)
+      return MFV_ERR_ARG;
+    if (a->ln_out_f32 && a->C3) return MFV_ERR_ARG;
+  }
   p.row_sum = nullptr;
   if (a->row_sum) {
     if (BN != 384 || a->epilogue != MFV_EPI_ATOMIC_F32 || a->N != 384) return MFV_ERR_ARG;
@@ -607,7 +748,7 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
                           p.b_f16);
   if (rc) return rc;
   const int e = a->epilogue;
-  const bool c32 = (e == MFV_EPI_RESID_F32 || e == MFV_EPI_F32 || e == MFV_EPI_ATOMIC_F32);
+  const bool c32 = (e == MFV_EPI_RESID_F32 || e == MFV_EPI_F32 || e == MFV_EPI_ATOMIC_F32 || e == MFV_EPI_RESID_LN);
   // C: u of the GELU epilogue is always bf16; other 16-bit outputs follow out_f16
   rc = encode_tile_map(&tmC, a->C, c32 ? 4 : 2, (e == MFV_EPI_BF16) ? p.out_f16 : 0, a->M, a->N, a->ldc, a->c_gstride,
                        p.G);
@@ -625,8 +766,16 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  if (e == MFV_EPI_RESID_F32 || e == MFV_EPI_DGELU) {
-    rc = encode_tile_map(&tmAux, a->aux, e == MFV_EPI_RESID_F32 ? 4 : 2, 0, a->M, a->N, a->aux_ld, a->aux_gstride, p.G);
+  if (e == MFV_EPI_RESID_LN) {  // C2 = LayerNorm(x): 16-bit (out_f16 selects fp16) or f32; C3 = optional bf16 copy
+    rc = encode_tile_map(&tmC2, a->C2, a->ln_out_f32 ? 4 : 2, p.out_f16, a->M, a->N, a->ldc, a->c_gstride, p.G);
+    if (rc) return rc;
+    if (a->C3) {
+      rc = encode_tile_map(&tmC3, a->C3, 2, 0, a->M, a->N, a->ldc, a->c_gstride, p.G);
+      if (rc) return rc;
+    }
+  }
+  if (e == MFV_EPI_RESID_F32 || e == MFV_EPI_DGELU || e == MFV_EPI_RESID_LN) {
+    rc = encode_tile_map(&tmAux, a->aux, e == MFV_EPI_DGELU ? 2 : 4, 0, a->M, a->N, a->aux_ld, a->aux_gstride, p.G);
     if (rc) return rc;
   }
 
@@ -664,6 +813,9 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
     case MFV_EPI_GELU: return launch_gemm_epi<BN, CG, MFV_EPI_GELU>(a, stream);
     case MFV_EPI_RESID_F32: return launch_gemm_epi<BN, CG, MFV_EPI_RESID_F32>(a, stream);
     case MFV_EPI_DGELU: return launch_gemm_epi<BN, CG, MFV_EPI_DGELU>(a, stream);
+    case MFV_EPI_RESID_LN:
+      if constexpr (BN == 384) return launch_gemm_epi<BN, CG, MFV_EPI_RESID_LN>(a, stream);
+      else return MFV_ERR_ARG;
     case MFV_EPI_F32:
     case MFV_EPI_ATOMIC_F32: return launch_gemm_epi<BN, CG, MFV_EPI_F32>(a, stream);
     default: return MFV_ERR_ARG;
@@ -677,7 +829,8 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
   if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->G <= 0) return MFV_ERR_SHAPE;
   if (a->N % 32 != 0) return MFV_ERR_SHAPE;
   if (a->ldc % 8 != 0) return MFV_ERR_ALIGN;
-  if ((a->epilogue == MFV_EPI_RESID_F32 || a->epilogue == MFV_EPI_DGELU) && !a->aux) return MFV_ERR_ARG;
+  if ((a->epilogue == MFV_EPI_RESID_F32 || a->epilogue == MFV_EPI_DGELU || a->epilogue == MFV_EPI_RESID_LN) && !a->aux)
+    return MFV_ERR_ARG;
   if (a->epilogue == MFV_EPI_GELU && !a->C2) return MFV_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // Tile selection (0 = auto).  These GEMMs are L2->SM bandwidth bound, so the widest tile that fits wins: CTA pairs
@@ -685,6 +838,10 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
   int bn = a->block_n;
   int cg = a->cta_group;
   const bool pair_ok = a->M > 128 && cg != 1;
+  if (a->epilogue == MFV_EPI_RESID_LN) {  // whole rows in one tile: 384-wide pair tiles only
+    if (a->N != 384 || a->M <= 128) return MFV_ERR_SHAPE;
+    return launch_gemm<384, 2>(a, s);
+  }
   if (bn == 0) {
     if (a->N == 384 && pair_ok && a->epilogue != MFV_EPI_GELU) bn = 384;
     else if (a->N >= 512 && pair_ok) bn = 256;

@@ -66,7 +66,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ dres,
-              const float* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const __nv_bfloat16* __restrict__ dres16, const float* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ gamma, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
               long long rows_per_group, long long gb_gstride) {
@@ -117,6 +117,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
       if (dres) {
         const float4 rr = reinterpret_cast<const float4*>(dres + row * C)[lane + 32 * i];
         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+      } else if (dres16) {
+        const uint2 pk = reinterpret_cast<const uint2*>(dres16 + row * C)[lane + 32 * i];
+        const float2 a = unpack_bf16(pk.x), b = unpack_bf16(pk.y);
+        o.x += a.x; o.y += a.y; o.z += b.x; o.w += b.y;
       }
       ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
       if (dx32) reinterpret_cast<float4*>(dx32 + row * C)[lane + 32 * i] = o;
@@ -126,6 +130,108 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ 
   }
   if (!dgamma && !dbeta && !dxsum) return;
   // block reduction of the column partials: three rounds through smem (dgamma, dbeta, sum of dx)
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 t = pass == 0 ? dg[i] : (pass == 1 ? db[i] : ds[i]);
+      *reinterpret_cast<float4*>(&red[warp][(lane + 32 * i) * 4]) = t;
+    }
+    __syncthreads();
+    if (out) {
+      for (int c = threadIdx.x; c < C; c += LN_WARPS * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) acc += red[w][c];
+        atomicAdd(out + g * gb_gstride + c, acc);
+      }
+    }
+  }
+}
+
+// The backward's common case - dy in bf16, the residual-path gradient in bf16 (or absent) - with TWO rows per warp
+// iteration and every load of both rows issued before the first reduction.  The generic kernel above is latency-bound
+// (a warp owns ~5 rows of a 32-pair step, each a serial chain load -> two warp reductions -> store: 54 % of the HBM peak
+// in-step with one row in flight); 16-bit inputs stay packed in registers until they are used.
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+ln_bwd16_kernel(const __nv_bfloat16* __restrict__ dy16, const __nv_bfloat16* __restrict__ dres16,
+                const float* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                const float* __restrict__ gamma, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16,
+                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+                long long rows_per_group, long long gb_gstride) {
+  constexpr int C = NV * 128;
+  constexpr int R = 2;  // rows in flight per warp
+  __shared__ float red[LN_WARPS][C + 4];
+  griddep_wait();    // PDL launch: the producers of dy / dres may still be draining
+  griddep_launch();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long g = blockIdx.y;
+  const float4* gm = reinterpret_cast<const float4*>(gamma + g * gb_gstride);
+  float4 dg[NV], db[NV], ds[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const long long stride = (long long)gridDim.x * LN_WARPS;
+  for (long long r0 = (long long)blockIdx.x * LN_WARPS + warp; r0 < rows_per_group; r0 += R * stride) {
+    float4 xv[R][NV];
+    uint2 dq[R][NV], rq[R][NV];
+    float mean[R], rstd[R];
+    bool live[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const long long r = r0 + k * stride;
+      live[k] = r < rows_per_group;
+      const long long row = g * rows_per_group + (live[k] ? r : r0);
+      mean[k] = mean_in[row];
+      rstd[k] = rstd_in[row];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xv[k][i] = reinterpret_cast<const float4*>(x + row * C)[lane + 32 * i];
+        dq[k][i] = reinterpret_cast<const uint2*>(dy16 + row * C)[lane + 32 * i];
+        rq[k][i] = dres16 ? reinterpret_cast<const uint2*>(dres16 + row * C)[lane + 32 * i] : make_uint2(0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!live[k]) continue;  // warp-uniform
+      const long long row = g * rows_per_group + r0 + k * stride;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4& v = xv[k][i];  // becomes x_hat in place
+        v = make_float4((v.x - mean[k]) * rstd[k], (v.y - mean[k]) * rstd[k], (v.z - mean[k]) * rstd[k],
+                        (v.w - mean[k]) * rstd[k]);
+        const float2 a = unpack_bf16(dq[k][i].x), b = unpack_bf16(dq[k][i].y);
+        const float4 gmi = __ldg(gm + lane + 32 * i);
+        dg[i].x += a.x * v.x; dg[i].y += a.y * v.y; dg[i].z += b.x * v.z; dg[i].w += b.y * v.w;
+        db[i].x += a.x; db[i].y += a.y; db[i].z += b.x; db[i].w += b.y;
+        const float4 dd = make_float4(a.x * gmi.x, a.y * gmi.y, b.x * gmi.z, b.y * gmi.w);
+        s1 += (dd.x + dd.y) + (dd.z + dd.w);
+        s2 += (dd.x * v.x + dd.y * v.y) + (dd.z * v.z + dd.w * v.w);
+      }
+      const float c1 = warp_sum(s1) * (1.0f / C), c2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 v = xv[k][i];
+        const float2 a = unpack_bf16(dq[k][i].x), b = unpack_bf16(dq[k][i].y);
+        const float2 ra = unpack_bf16(rq[k][i].x), rb = unpack_bf16(rq[k][i].y);
+        const float4 gmi = __ldg(gm + lane + 32 * i);
+        float4 o;
+        o.x = rstd[k] * (a.x * gmi.x - c1 - v.x * c2) + ra.x;
+        o.y = rstd[k] * (a.y * gmi.y - c1 - v.y * c2) + ra.y;
+        o.z = rstd[k] * (b.x * gmi.z - c1 - v.z * c2) + rb.x;
+        o.w = rstd[k] * (b.y * gmi.w - c1 - v.w * c2) + rb.y;
+        ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
+        if (dx32) reinterpret_cast<float4*>(dx32 + row * C)[lane + 32 * i] = o;
+        if (dx16)
+          reinterpret_cast<uint2*>(dx16 + row * C)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+  if (!dgamma && !dbeta && !dxsum) return;
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
@@ -169,13 +275,15 @@ extern "C" int mfv_layernorm_fwd(const float* x, const float* gamma, const float
   return MFV_OK;
 }
 
-extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x,
-                                 const float* mean, const float* rstd, const float* gamma, float* dx_f32,
+extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const void* dres_bf16,
+                                 const float* x, const float* mean, const float* rstd, const float* gamma, float* dx_f32,
                                  void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int64_t G, int64_t rows,
                                  int64_t C, int64_t gb_gstride, void* stream) {
   using namespace mfv;
   if (G <= 0 || rows <= 0) return MFV_ERR_SHAPE;
   if (!dy_bf16 && !dy_f32) return MFV_ERR_ARG;
+  if (dres && dres_bf16) return MFV_ERR_ARG;
+  const __nv_bfloat16* dres16 = reinterpret_cast<const __nv_bfloat16*>(dres_bf16);
   long long bx = (rows + LN_WARPS - 1) / LN_WARPS;
   const long long cap = (2LL * num_sms() + G - 1) / G;
   if (bx > cap) bx = cap;
@@ -183,10 +291,20 @@ extern "C" int mfv_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dy16 = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  if (dy16 && !dres) {  // 16-bit inputs: two rows in flight per warp
+    switch (C) {
+      case 256: MFV_CUDA_CHECK(launch_pdl(ln_bwd16_kernel<2>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+      case 384: MFV_CUDA_CHECK(launch_pdl(ln_bwd16_kernel<3>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+      case 768: MFV_CUDA_CHECK(launch_pdl(ln_bwd16_kernel<6>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+      default: return MFV_ERR_SHAPE;
+    }
+    MFV_LAUNCH_CHECK();
+    return MFV_OK;
+  }
   switch (C) {
-    case 256: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<2>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
-    case 384: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
-    case 768: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<6>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+    case 256: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<2>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+    case 384: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
+    case 768: MFV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<6>, grid, dim3(LN_WARPS * 32), 0, s, dy16, dy_f32, dres, dres16, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, dx_colsum, rows, gb_gstride)); break;
     default: return MFV_ERR_SHAPE;
   }
   MFV_LAUNCH_CHECK();

@@ -11,6 +11,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 int num_sms();
 bool pdl_enabled();
+bool fuse_ln_enabled();  // MFVIT_FUSE_LN=0: standalone LayerNorm launches instead of the fused proj / fc2 epilogue
+bool dx32_stream_enabled();  // MFVIT_DX32=1: fp32 residual-gradient stream through the LayerNorm backward (default: bf16)
 bool rows96_enabled();  // MFVIT_ROWS96=1: 96 rows per CTA in the 384-wide pair tiles of the forward (off by default)
 // Side stream of mfv_vit_backward: weight-gradient GEMMs and bias column sums are off the critical path (nothing in
 // the backward consumes them), so they run beside the dgrad / attention / LayerNorm chain and fill the SMs those

@@ -40,7 +40,7 @@ static int g_device = -1;
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 // Runtime switches (defaults from the environment, overridable through mfv_set_option): -1 = not read yet
-static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1;
+static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1, g_opt_fuse_ln = -1, g_opt_dx32 = -1;
 static int env_flag(const char* name, int dflt, char off_char) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
@@ -74,6 +74,14 @@ bool rows96_enabled() {
   if (g_opt_rows96 < 0) g_opt_rows96 = env_flag("MFVIT_ROWS96", 0, '1');
   return g_opt_rows96 == 1;
 }
+bool fuse_ln_enabled() {
+  if (g_opt_fuse_ln < 0) g_opt_fuse_ln = env_flag("MFVIT_FUSE_LN", 1, '0');
+  return g_opt_fuse_ln == 1;
+}
+bool dx32_stream_enabled() {
+  if (g_opt_dx32 < 0) g_opt_dx32 = env_flag("MFVIT_DX32", 0, '1');
+  return g_opt_dx32 == 1;
+}
 bool pdl_enabled() {
   if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
   return g_opt_pdl == 1;
@@ -85,7 +93,8 @@ extern "C" const char* mfv_last_error_where(void) { return mfv::g_err_where; }
 
 // Runtime switches for A/B measurements and tests: "pdl" (programmatic dependent launch, default 1), "side_stream"
 // (weight gradients on a second stream, default 1), "legacy_attention" (mma.sync attention kernels, default 0),
-// "rows96" (192-row pair tiles for the forward N = 384 GEMMs when they fill the SMs better, default 0).
+// "rows96" (192-row pair tiles for the forward N = 384 GEMMs when they fill the SMs better, default 0), "fuse_ln"
+// (LayerNorm inside the proj / fc2 epilogues, default 1).
 extern "C" int mfv_set_option(const char* key, int value) {
   using namespace mfv;
   if (!key) return MFV_ERR_ARG;
@@ -94,6 +103,8 @@ extern "C" int mfv_set_option(const char* key, int value) {
   else if (k == "side_stream") g_opt_side = value ? 1 : 0;
   else if (k == "legacy_attention") g_opt_legacy_attn = value ? 1 : 0;
   else if (k == "rows96") g_opt_rows96 = value ? 1 : 0;
+  else if (k == "fuse_ln") g_opt_fuse_ln = value ? 1 : 0;
+  else if (k == "dx32") g_opt_dx32 = value ? 1 : 0;
   else return MFV_ERR_ARG;
   return MFV_OK;
 }

@@ -73,6 +73,28 @@ static int linear_fwd(const PlanView& v, const void* A, long long K, long long w
   ProfScope ps(PROF_GEMM_FWD, st);
   return mfv_gemm(&a, st);
 }
+// x_new = x_old + y W^T + bias AND the LayerNorm of x_new in the same epilogue (MFV_EPI_RESID_LN, C == 384): the operand
+// of the next Linear (xn, + bf16 copy), or the fp32 tokens when this is the last Linear in front of the final norm
+static int linear_fwd_ln(const PlanView& v, const void* A, long long K, long long w_off, long long b_off, float* x_new,
+                         const float* x_old, long long ln_w_off, long long ln_b_off, int stat_idx, void* xn16,
+                         void* xn_copy, float* out_f32, cudaStream_t st) {
+  const long long C = v.p->C;
+  mfv_gemm_args a = {};
+  a.A = A; a.B = v.wf(w_off); a.C = x_new; a.aux = x_old;
+  a.C2 = out_f32 ? (void*)out_f32 : xn16; a.C3 = out_f32 ? nullptr : xn_copy;
+  a.dtype_flags = v.p->fwd_f16 ? (3 | 4) : 0;
+  a.bias = v.w32(b_off);
+  a.M = v.M; a.N = C; a.K = K; a.G = v.p->G;
+  a.lda = K; a.ldb = K; a.ldc = C;
+  a.a_gstride = v.M * K; a.b_gstride = v.p->P; a.c_gstride = v.M * C;
+  a.aux_ld = C; a.aux_gstride = v.M * C; a.bias_gstride = v.p->P;
+  a.epilogue = MFV_EPI_RESID_LN;
+  a.ln_gamma = v.w32(ln_w_off); a.ln_beta = v.w32(ln_b_off);
+  a.ln_mean = v.mean(stat_idx); a.ln_rstd = v.rstd(stat_idx);
+  a.ln_eps = 1e-6f; a.ln_out_f32 = out_f32 ? 1 : 0;
+  ProfScope ps(PROF_GEMM_FWD, st);
+  return mfv_gemm(&a, st);
+}
 // dx = dy W: A = dy [G][M][N] K-major (reduction over N), B = W [N][K] read MN-major
 static int linear_dgrad(const PlanView& v, const void* dY, long long N, long long w_off, long long K, int epi, void* C,
                         void* C2, const void* aux, long long aux_ld, cudaStream_t st) {
@@ -194,31 +216,53 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
   }
   RCP(PROF_EMBED, mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
 
+  // LayerNorm placement: with C == 384 the proj / fc2 GEMMs own whole rows (256 x 384 pair tiles) and normalise what
+  // they just wrote (MFV_EPI_RESID_LN) - only the first LayerNorm of block 0 (input: the embedding) is a launch of its
+  // own.  Other widths (and MFVIT_FUSE_LN=0) keep the standalone kernels.
+  const bool fuse_ln = (C == 384) && M > 128 && fuse_ln_enabled();
+  const int last = 2 * (int)p->depth;
   for (int l = 0; l < p->depth; ++l) {
     float* x_in = v.x(2 * l);
     float* x_mid = v.x(2 * l + 1);
     float* x_out = v.x(2 * l + 2);
     const bool dual = v.dual();
-    RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), p->fwd_f16,
-                         dual ? v.xn_b(2 * l) : nullptr, nullptr, v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f,
-                         st));
+    const bool final_block = (l == (int)p->depth - 1);
+    if (l == 0 || !fuse_ln)
+      RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_in, v.w32(v.boff(l, p->r_ln1_w)), v.w32(v.boff(l, p->r_ln1_b)), v.xn(2 * l), p->fwd_f16,
+                           dual ? v.xn_b(2 * l) : nullptr, nullptr, v.mean(2 * l), v.rstd(2 * l), G, M, C, p->P, 1e-6f,
+                           st));
     RC(linear_fwd(v, v.xn(2 * l), C, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), 3 * C, MFV_EPI_BF16, v.qkv(l),
                   nullptr, nullptr, nullptr, 0, st));
     RCP(PROF_ATTN_FWD, mfv_attn_fwd(v.qkv(l), p->fwd_f16, v.ao(l), p->fwd_f16, dual ? v.ao_b(l) : nullptr, v.lse(l), G * p->B, p->S, p->H, D, scale,
                     st));
-    RC(linear_fwd(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), C, MFV_EPI_RESID_F32, x_mid, nullptr,
-                  nullptr, x_in, C, st));
-    RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), p->fwd_f16,
-                         dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C,
-                         p->P, 1e-6f, st));
+    if (fuse_ln) {
+      RC(linear_fwd_ln(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), x_mid, x_in,
+                       v.boff(l, p->r_ln2_w), v.boff(l, p->r_ln2_b), 2 * l + 1, v.xn(2 * l + 1),
+                       dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, st));
+    } else {
+      RC(linear_fwd(v, v.ao(l), C, v.boff(l, p->r_proj_w), v.boff(l, p->r_proj_b), C, MFV_EPI_RESID_F32, x_mid, nullptr,
+                    nullptr, x_in, C, st));
+      RCP(PROF_LN_FWD, mfv_layernorm_fwd(x_mid, v.w32(v.boff(l, p->r_ln2_w)), v.w32(v.boff(l, p->r_ln2_b)), v.xn(2 * l + 1), p->fwd_f16,
+                           dual ? v.xn_b(2 * l + 1) : nullptr, nullptr, v.mean(2 * l + 1), v.rstd(2 * l + 1), G, M, C,
+                           p->P, 1e-6f, st));
+    }
     RC(linear_fwd(v, v.xn(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), Hd, MFV_EPI_GELU, v.u(l),
                   v.g(l), nullptr, nullptr, 0, st));
-    RC(linear_fwd(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), C, MFV_EPI_RESID_F32, x_out, nullptr,
-                  nullptr, x_mid, C, st));
+    if (fuse_ln && !final_block) {  // fc2 also writes LN1 of the next block
+      RC(linear_fwd_ln(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), x_out, x_mid,
+                       v.boff(l + 1, p->r_ln1_w), v.boff(l + 1, p->r_ln1_b), 2 * l + 2, v.xn(2 * l + 2),
+                       dual ? v.xn_b(2 * l + 2) : nullptr, nullptr, st));
+    } else if (fuse_ln) {           // ... or the final norm: fp32 tokens
+      RC(linear_fwd_ln(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), x_out, x_mid, p->off_norm_w,
+                       p->off_norm_b, last, nullptr, nullptr, p->tokens, st));
+    } else {
+      RC(linear_fwd(v, v.g(l), Hd, v.boff(l, p->r_fc2_w), v.boff(l, p->r_fc2_b), C, MFV_EPI_RESID_F32, x_out, nullptr,
+                    nullptr, x_mid, C, st));
+    }
   }
-  const int last = 2 * (int)p->depth;
-  RCP(PROF_LN_FWD, mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, 0, nullptr, p->tokens,
-                       v.mean(last), v.rstd(last), G, M, C, p->P, 1e-6f, st));
+  if (!fuse_ln)
+    RCP(PROF_LN_FWD, mfv_layernorm_fwd(v.x(last), v.w32(p->off_norm_w), v.w32(p->off_norm_b), nullptr, 0, nullptr, p->tokens,
+                         v.mean(last), v.rstd(last), G, M, C, p->P, 1e-6f, st));
   return MFV_OK;
 }
 
@@ -262,12 +306,20 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     pending[h] = false;
     return MFV_OK;
   };
-  int cur = 0;  // dx[cur] holds the gradient of the residual stream (always 0 at a block boundary: two flips per block)
+  int cur = 0;  // dx[cur] / dx16[cur] hold the gradient of the residual stream (always 0 at a block boundary: two flips per block)
+  // Residual-gradient stream.  Default: bf16 only - the copy the dgrad / wgrad GEMMs read anyway is also what the next
+  // LayerNorm backward adds its result to, so the fp32 read + write of the stream (44 % of the LayerNorm-backward
+  // traffic) disappears; 24 roundings to bf16 along the depth cost ~0.5 % relative error on the earliest gradients
+  // (cosine 0.9999+).  MFVIT_DX32=1 keeps the fp32 stream of round 1.  The very last LayerNorm backward (block 0) still
+  // writes fp32: the embedding backward reads it.
+  const bool dx32 = dx32_stream_enabled();
+  auto res32 = [&](int c) -> const float* { return dx32 ? p->dx[c] : nullptr; };
+  auto res16 = [&](int c) -> const void* { return dx32 ? nullptr : p->dx16[c]; };
   // final norm
   // each LN backward also emits colsum(dx) = bias gradient of the Linear feeding that residual add (fc2 / proj)
   if (flags & MFV_BWD_HEAD)
-    RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
-                         p->dx[cur], p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
+                         dx32 ? p->dx[cur] : nullptr, p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
                          v.gr(v.boff((int)p->depth - 1, p->r_fc2_b)), G, M, C, p->P, st));
   for (int l = block_hi; l >= block_lo; --l) {
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
@@ -280,8 +332,8 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     RC(side_done(0));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RC(join(1));  // the previous block's attention-half weight gradients still read dx16[cur ^ 1]
-    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
-                         v.w32(v.boff(l, p->r_ln2_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, res32(cur), res16(cur), v.x(2 * l + 1), v.mean(2 * l + 1), v.rstd(2 * l + 1),
+                         v.w32(v.boff(l, p->r_ln2_w)), dx32 ? p->dx[cur ^ 1] : nullptr, p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln2_w)),
                          v.gr(v.boff(l, p->r_ln2_b)), v.gr(v.boff(l, p->r_proj_b)), G, M, C, p->P, st));
     cur ^= 1;
     // ---- attention half: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
@@ -294,8 +346,9 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     RC(side_done(1));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RC(join(0));  // fc2's weight gradient of this block reads dx16[cur ^ 1], which the LayerNorm backward below rewrites
-    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, p->dx[cur], v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
-                         v.w32(v.boff(l, p->r_ln1_w)), p->dx[cur ^ 1], p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
+    // fp32 output only where somebody reads it: the fp32-stream mode, or block 0 (the embedding backward)
+    RCP(PROF_LN_BWD, mfv_layernorm_bwd(p->dxn, nullptr, res32(cur), res16(cur), v.x(2 * l), v.mean(2 * l), v.rstd(2 * l),
+                         v.w32(v.boff(l, p->r_ln1_w)), (dx32 || l == 0) ? p->dx[cur ^ 1] : nullptr, p->dx16[cur ^ 1], v.gr(v.boff(l, p->r_ln1_w)),
                          v.gr(v.boff(l, p->r_ln1_b)), l > 0 ? v.gr(v.boff(l - 1, p->r_fc2_b)) : nullptr, G, M, C, p->P,
                          st));
     cur ^= 1;

@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("a_mn_major", i32), ("b_mn_major", i32), ("epilogue", i32), ("splits", i32), ("block_n", i32),
         ("dtype_flags", i32), ("cta_group", i32), ("rows_per_cta", i32),
         ("row_sum", c_vp),
+        ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_mean", c_vp), ("ln_rstd", c_vp), ("ln_eps", f32), ("ln_out_f32", i32),
     ]
 
 
@@ -63,7 +64,7 @@ class VitPlan(C.Structure):
     )
 
 
-EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_DGELU, EPI_F32, EPI_ATOMIC_F32 = range(6)
+EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_DGELU, EPI_F32, EPI_ATOMIC_F32, EPI_RESID_LN = range(7)
 
 # name -> (restype, argtypes); mirrors include/mfvit.h one to one
 SIGNATURES = {
@@ -80,7 +81,7 @@ SIGNATURES = {
     "mfv_prof_read": (C.c_int, [c_vp, c_vp, C.c_int]),
     "mfv_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
-    "mfv_layernorm_bwd": (C.c_int, [c_vp] * 12 + [i64, i64, i64, i64, c_vp]),
+    "mfv_layernorm_bwd": (C.c_int, [c_vp] * 13 + [i64, i64, i64, i64, c_vp]),
     "mfv_attn_fwd": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_attn_bwd": (C.c_int, [c_vp, C.c_int] + [c_vp] * 5 + [i64, i64, i64, i64, f32, c_vp]),
     "mfv_attn_bwd_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),

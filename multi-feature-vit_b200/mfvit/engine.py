@@ -170,6 +170,7 @@ class ViTEngine:
         self.fwd_f16 = FWD_PRECISION == "fp16"
         self.grads = [None, None]
         self.grad_idx = 0
+        self._next_grad = None
         self.shadow_fresh = False
         self._shadow_sig = None  # parameter versions the 16-bit shadows were last known to match
         self._casts = 0
@@ -399,6 +400,13 @@ class ViTEngine:
         self.grad_idx = nxt
         return self.grads[nxt]
 
+    def next_grad_buffer(self):
+        """The flat buffer the NEXT backward will write (picked now so that a caller can zero it ahead of time, off the
+        critical path, and pass zero=False to backward)."""
+        if self._next_grad is None:
+            self._next_grad = self._pick_grad_buffer()
+        return self._next_grad
+
     def backward(self, lease, dtokens, zero=True, segments=None, on_segment=None):
         """Encoder backward.  `segments` (optional): list of (block_hi, block_lo) covering depth-1 .. 0 in descending
         order; `on_segment(grad, lo_elem, hi_elem)` is called after each one with the element range of every group's flat
@@ -407,7 +415,8 @@ class ViTEngine:
             raise MfvError("backward called without saved activations (forward ran with save=False?)")
         ws = lease.ws
         lib = _lib.init(self.device.index)
-        grad = self._pick_grad_buffer()
+        grad = self._next_grad if self._next_grad is not None else self._pick_grad_buffer()
+        self._next_grad = None
         if zero:
             ops.fill_(grad.view(-1), 0.0)
         dtokens = dtokens.contiguous()

@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESID_F32, EmaChunk, FusionGrads,
+from ._lib import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESID_F32, EPI_RESID_LN, EmaChunk, FusionGrads,
                    FusionParams, GemmArgs, MfvError, check)
 
 
@@ -25,9 +25,14 @@ def _stream():
 
 def gemm(A, B, Cout, *, M, N, K, G=1, lda, ldb, ldc, a_gstride=0, b_gstride=0, c_gstride=0, bias=None,
          bias_gstride=0, aux=None, aux_ld=0, aux_gstride=0, C2=None, C3=None, a_mn=False, b_mn=False, epilogue=EPI_BF16,
-         splits=1, block_n=0, dtype_flags=0, cta_group=0, row_sum=None, rows_per_cta=0):
+         splits=1, block_n=0, dtype_flags=0, cta_group=0, row_sum=None, rows_per_cta=0, ln=None):
+    """ln (MFV_EPI_RESID_LN): dict(gamma, beta, mean, rstd, eps, out_f32)."""
     lib = _lib_for(A)
     a = GemmArgs()
+    if ln is not None:
+        a.ln_gamma, a.ln_beta = ln["gamma"].data_ptr(), ln["beta"].data_ptr()
+        a.ln_mean, a.ln_rstd = ln["mean"].data_ptr(), ln["rstd"].data_ptr()
+        a.ln_eps, a.ln_out_f32 = float(ln["eps"]), int(bool(ln.get("out_f32", False)))
     a.A, a.B, a.C, a.C2, a.bias, a.aux = (A.data_ptr(), B.data_ptr(), Cout.data_ptr(),
                                            C2.data_ptr() if C2 is not None else None,
                                            bias.data_ptr() if bias is not None else None,
@@ -57,6 +62,26 @@ def linear_fwd(x16, w16, bias=None, epilogue=EPI_BF16, out=None, out2=None, aux=
     return gemm(x16, w16, out, M=M, N=N, K=K, G=G, lda=K, ldb=K, ldc=N, a_gstride=M * K, b_gstride=N * K,
                 c_gstride=M * N, bias=bias, bias_gstride=N, aux=aux, aux_ld=N, aux_gstride=M * N, C2=out2, C3=out3,
                 epilogue=epilogue, block_n=block_n, dtype_flags=dtype_flags, cta_group=cta_group, rows_per_cta=rows_per_cta)
+
+
+def linear_fwd_ln(x16, w16, bias, resid, gamma, beta, eps=1e-6, out_f32=False, f16=False, bf16_copy=False,
+                  rows_per_cta=0):
+    """x_new = resid + x16 @ w16^T + bias and LayerNorm(x_new) from the same epilogue (MFV_EPI_RESID_LN, N == 384).
+    Returns (x_new f32, y (16-bit, or f32 with out_f32), y_bf16_copy | None, mean, rstd)."""
+    G, M, K = x16.shape
+    N = w16.shape[1]
+    dev = x16.device
+    x_new = torch.empty(G, M, N, device=dev, dtype=torch.float32)
+    y = torch.empty(G, M, N, device=dev, dtype=torch.float32 if out_f32 else (torch.float16 if f16 else torch.bfloat16))
+    ycopy = torch.empty(G, M, N, device=dev, dtype=torch.bfloat16) if bf16_copy else None
+    mean = torch.empty(G, M, device=dev, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    flags = (3 if x16.dtype == torch.float16 else 0) | (4 if f16 else 0)
+    gemm(x16, w16, x_new, M=M, N=N, K=K, G=G, lda=K, ldb=K, ldc=N, a_gstride=M * K, b_gstride=N * K, c_gstride=M * N,
+         bias=bias, bias_gstride=N, aux=resid, aux_ld=N, aux_gstride=M * N, C2=y, C3=ycopy, epilogue=EPI_RESID_LN,
+         dtype_flags=flags, rows_per_cta=rows_per_cta,
+         ln=dict(gamma=gamma, beta=beta, mean=mean, rstd=rstd, eps=eps, out_f32=out_f32))
+    return x_new, y, ycopy, mean, rstd
 
 
 def linear_dgrad(dy16, w16, epilogue=EPI_BF16, aux=None, out=None, block_n=0, cta_group=0, out2=None, rows_per_cta=0):
@@ -95,14 +120,18 @@ def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False, f16=False
     return y16, y32, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, want_bf16=True, dx_colsum=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None, dgamma=None, dbeta=None, want_bf16=True, dx_colsum=None,
+                  want_f32=True):
+    """dres: f32 or bf16 residual-path gradient (or None)."""
     G, rows, Cd = x.shape
     lib = _lib_for(x)
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if want_f32 else None
     dx16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
     dy16 = dy if dy.dtype == torch.bfloat16 else None
     dy32 = dy if dy.dtype == torch.float32 else None
-    check(lib.mfv_layernorm_bwd(_p(dy16), _p(dy32), _p(dres), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx16),
+    dres32 = dres if dres is not None and dres.dtype == torch.float32 else None
+    dres16 = dres if dres is not None and dres.dtype == torch.bfloat16 else None
+    check(lib.mfv_layernorm_bwd(_p(dy16), _p(dy32), _p(dres32), _p(dres16), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx16),
                                 _p(dgamma), _p(dbeta), _p(dx_colsum), G, rows, Cd,
                                 gamma.stride(0) if gamma.dim() > 1 else 0,
                                 _stream()), "mfv_layernorm_bwd")

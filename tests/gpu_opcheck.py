@@ -81,6 +81,32 @@ def t_gemm_rows96():
         report("gemm rows96 dgrad M%d" % M, out, torch.einsum("gmn,gnk->gmk", dy.float(), w2.float()), 2e-2, rel=True)
 
 
+def t_gemm_resid_ln():
+    """MFV_EPI_RESID_LN: residual add + LayerNorm of the finished row inside the proj / fc2 epilogue."""
+    for M, K, f16, rows in ((6304, 384, True, 0), (197 * 3, 1536, False, 0), (1379, 384, True, 96), (200, 256, False, 0)):
+        torch.manual_seed(5)
+        dt = torch.float16 if f16 else torch.bfloat16
+        x = torch.randn(2, M, K, device=dev).to(dt)
+        w = (torch.randn(2, 384, K, device=dev) * 0.05).to(dt)
+        b = torch.randn(2, 384, device=dev) * 0.1
+        res = torch.randn(2, M, 384, device=dev) * 2 + 0.7  # non-zero row means: the variance must not cancel
+        gam = 1 + 0.1 * torch.randn(2, 384, device=dev)
+        bet = 0.1 * torch.randn(2, 384, device=dev)
+        xr = torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :] + res
+        mu, var = xr.mean(-1), xr.var(-1, unbiased=False)
+        yr = (xr - mu[..., None]) * torch.rsqrt(var[..., None] + 1e-6) * gam[:, None, :] + bet[:, None, :]
+        tag = "M%d K%d %s rows%d" % (M, K, "f16" if f16 else "bf16", rows)
+        x_new, y, ycopy, mean, rstd = ops.linear_fwd_ln(x, w, b, res, gam, bet, 1e-6, f16=f16, bf16_copy=f16, rows_per_cta=rows)
+        report("gemm resid+LN x " + tag, x_new, xr, 1e-4, rel=True)
+        report("gemm resid+LN mean " + tag, mean, mu, 1e-5)
+        report("gemm resid+LN rstd " + tag, rstd, torch.rsqrt(var + 1e-6), 1e-4, rel=True)
+        report("gemm resid+LN y " + tag, y, yr, 2e-3 if f16 else 1.6e-2, rel=False)
+        if ycopy is not None:
+            report("gemm resid+LN y bf16 copy " + tag, ycopy, yr, 1.6e-2)
+        _, y32, _, _, _ = ops.linear_fwd_ln(x, w, b, res, gam, bet, 1e-6, out_f32=True)
+        report("gemm resid+LN y f32 " + tag, y32, yr, 2e-5, rel=True)
+
+
 def t_gemm_epilogues():
     torch.manual_seed(1)
     G, M, N, K = 2, 1000, 384, 256
@@ -377,6 +403,7 @@ def main():
     run("gemm_fwd N768 bn384", t_gemm_fwd(1, 1000, 768, 128, 384), flt)
     run("gemm epilogues", t_gemm_epilogues, flt)
     run("gemm rows96", t_gemm_rows96, flt)
+    run("gemm resid+LN", t_gemm_resid_ln, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
     run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
     run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_sizes_match_header_layout():
     from mfvit import _lib
     import ctypes
-    assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 13 * 8 + 8 * 4 + 8
+    assert ctypes.sizeof(_lib.GemmArgs) == 7 * 8 + 13 * 8 + 8 * 4 + 8 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.FusionParams) == 13 * 2 * 8
     assert ctypes.sizeof(_lib.EmaChunk) == 24
     # mfv_vit_plan: 10 i64 + 4 ptr + 20 i64 + 2 ptr + 11 ptr + 4 i32 + 4 ptr + (1 + 2 + 2 + 7) ptr

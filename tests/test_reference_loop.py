@@ -25,7 +25,10 @@ MAIN_CA = ("main_vit_covid_test_val_single_img_type_5draws_rev_v2loss_v3structur
            "trainval_sum.py")
 
 
-def _import_reference_script(tmp_path):
+MAIN_LPFT = "main_vit_covid_test_val_single_img_type_5draws_rev_v2loss_v3structure_vitsmall.py"
+
+
+def _import_reference_script(tmp_path, script=MAIN_CA):
     sys.path.insert(0, os.path.join(ROOT, "multi-feature-vit_b200", "tools"))
     import overlay
     import_root = overlay.make_overlay(STAGED, str(tmp_path / "deploy"))
@@ -38,11 +41,12 @@ def _import_reference_script(tmp_path):
             del sys.modules[name]
     sys.path.insert(0, import_root)
     try:
-        spec = importlib.util.spec_from_file_location("reference_main_ca", os.path.join(str(tmp_path / "deploy"), MAIN_CA))
+        spec = importlib.util.spec_from_file_location("reference_" + script[:-3], os.path.join(str(tmp_path / "deploy"), script))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         assert os.path.realpath(mod.vits.__file__).startswith(os.path.realpath(import_root))
-        assert os.path.realpath(mod.Fus_CrossViT.__init__.__code__.co_filename).startswith(os.path.realpath(import_root))
+        if hasattr(mod, "Fus_CrossViT"):
+            assert os.path.realpath(mod.Fus_CrossViT.__init__.__code__.co_filename).startswith(os.path.realpath(import_root))
         return mod
     finally:
         sys.path[:] = saved_path
@@ -113,3 +117,63 @@ def test_reference_train_function_runs_unmodified_over_the_dropin(tmp_path):
     for n in p0:                                                # the optimizer stepped the fusion's tensors identically
         assert (p0[n] - p1[n]).abs().max().item() <= 2e-4, n
     assert E.cos(g0, g1) >= 0.999                               # backbones received gradients (never stepped, fact 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(STAGED), reason="baseline/_ref/reference not staged")
+@pytest.mark.parametrize("semi_supervised", [False, True])
+def test_reference_lpft_train_and_test_functions_over_the_dropin(tmp_path, semi_supervised):
+    """MAIN_LPFT's own train() (:647-763) and test() (:765-826), imported from the deployed tree, over the oracle ViT and
+    over the drop-in `vits.vit_small` - linear probe (everything but the head frozen, MAIN_LPFT:283-286) and
+    --semi-supervised fine-tuning - and the sync-free ViTClassifierTrainer / run_phase on the same batches."""
+    from mfvit.data import EpochMetrics
+    from mfvit.finetune import ViTClassifierTrainer, run_phase
+    ref_main = _import_reference_script(tmp_path, MAIN_LPFT)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n_batches, B = 2, 8
+    loaders = {ph: [((c, c), t.int()) for c, _, t in (E.synthetic_pair(B, 224, rank=20 * pi + i) for i in range(n_batches))]
+               for pi, ph in enumerate(("train", "val"))}
+    num_imgs = {"train": n_batches * B, "val": n_batches * B}
+    args = types.SimpleNamespace(semi_supervised=semi_supervised)
+
+    def freeze(m):  # MAIN_LPFT:283-286
+        if not semi_supervised:
+            for name, p in m.named_parameters():
+                if name not in ("head.weight", "head.bias"):
+                    p.requires_grad = False
+        return m
+
+    def make_dropin(ref):
+        v = ref_main.vits.__dict__["vit_small"]()                       # MAIN_LPFT:276
+        v.head = nn.Linear(v.head.in_features, 3)                       # MAIN_LPFT:288
+        v.load_state_dict(ref.state_dict(), strict=True)
+        assert str(tmp_path / "deploy") in type(v).__init__.__code__.co_filename
+        return freeze(v.cuda())
+
+    results = {}
+    for which in ("oracle", "dropin"):
+        ref, _ = E.build_vit_pair(seed=33)
+        model = freeze(ref) if which == "oracle" else make_dropin(ref)
+        params = [p for p in model.parameters() if p.requires_grad]    # MAIN_LPFT:380-392
+        assert semi_supervised or len(params) == 2
+        opt = torch.optim.SGD(params, 0.05, momentum=0.9, weight_decay=0.0)
+        writer = _Writer()
+        out = ref_main.train(loaders, model, nn.CrossEntropyLoss().cuda(), opt, 0, args, num_imgs, writer)
+        t_loss, t_auc, t_acc = ref_main.test(loaders["val"], model, nn.CrossEntropyLoss().cuda(), opt, 0, num_imgs["val"])
+        results[which] = (float(out[0]), dict((t, v) for t, v, _ in writer.rows), float(t_loss), float(t_acc),
+                          model.head.weight.detach().clone(), model.blocks[5].mlp.fc1.weight.detach().clone())
+    (l0, w0, tl0, ta0, h0, f0), (l1, w1, tl1, ta1, h1, f1) = results["oracle"], results["dropin"]
+    assert abs(l0 - l1) <= 2e-3 and abs(w0["train/loss"] - w1["train/loss"]) <= 2e-3 and abs(tl0 - tl1) <= 2e-3
+    assert abs(ta0 - ta1) <= 1.0 / (n_batches * B) + 1e-9
+    assert (h0 - h1).abs().max().item() <= 2e-4
+    assert E.cos(f0, f1) >= 0.999999 and (semi_supervised or torch.equal(f1, E.build_vit_pair(seed=33)[0].blocks[5].mlp.fc1.weight))
+    # the sync-free trainer on the same batches: same epoch numbers as the reference loop over the oracle
+    ref, _ = E.build_vit_pair(seed=33)
+    mine = make_dropin(ref)
+    metrics = EpochMetrics(capacity=n_batches * B, num_classes=3, device="cuda")
+    tr = ViTClassifierTrainer(mine, lr=0.05, momentum=0.9, metrics=metrics)
+    dev = lambda phase: [(c.cuda(), t.cuda()) for (c, _), t in loaders[phase]]  # noqa: E731
+    tl, _, _ = run_phase("train", tr, dev("train"), metrics, num_imgs["train"])
+    vl, _, vacc = run_phase("val", tr, dev("val"), metrics, num_imgs["val"])
+    assert abs(tl - w0["train/loss"]) <= 2e-3 and abs(vl - l0) <= 2e-3 and abs(vacc - ta0) <= 1.0 / (n_batches * B) + 1e-9
+    assert (mine.head.weight - h0).abs().max().item() <= 2e-4
