@@ -145,6 +145,18 @@ int mfv_attn_bwd_ws(const void* qkv, int qkv_is_f16, const void* o, const void* 
  *   row 0 = cls + pos[0], row 1+p = acc[p] + bias + pos[1+p].                                                         */
 int mfv_patchify(const float* img, void* patches, int patches_is_f16, void* patches_bf16_copy, int64_t GB, int64_t HW,
                  void* stream);
+/* The same three steps as ONE im2col-free GEMM (default forward path, C == 384): the A operand is fetched by TMA from the
+ * NCHW fp32 images through a 5-D tensor map (j, i, patch column, patch row, channel x image) as dense [patch][64 k] fp32
+ * tiles, rounded to the 16-bit operand format in shared memory by the epilogue warps (no patch matrix in HBM), and
+ * multiplied on tcgen05 with the 16-bit weight shadow w16 [G][C][768] (fp16 when w_is_f16, else bf16); the epilogue adds
+ * bias + position embedding and writes x f32 [G][B][np+1][C] including the class-token row.  img0 / img1: the images of
+ * group 0 / 1 (img1 unused for G == 1); bias / cls / pos inside the groups' parameter blocks (p_gstride elements apart). */
+/* Test aid: the raw shared-memory image (8192 floats) of ONE 5-D TMA box of mfv_patch_embed_tma's image map. */
+int mfv_debug_patch_tma_probe(const float* img, float* out8192, int64_t B, int64_t HW, int64_t kb, int64_t ph0, int64_t cb,
+                              void* stream);
+int mfv_patch_embed_tma(const float* img0, const float* img1, const void* w16, int w_is_f16, const float* bias,
+                        const float* cls, const float* pos, float* x, int64_t G, int64_t B, int64_t HW, int64_t C,
+                        int64_t p_gstride, void* stream);
 int mfv_embed_finish(const float* acc, const float* bias, const float* cls, const float* pos, float* x, int64_t G,
                      int64_t B, int64_t np, int64_t C, int64_t p_gstride, void* stream);
 /* backward of the above: dacc bf16 [G][B*np][C] (for the conv weight gradient GEMM), dbias/dcls accumulated.
@@ -320,6 +332,9 @@ int mfv_vit_backward_range(const mfv_vit_plan* plan, void* stream, int block_hi,
 /* ---- elementwise / optimiser ------------------------------------------------------------------------------------------
  * f32 master -> 16-bit shadow weights for the GEMM operands: bf16 (backward) and/or fp16 (forward); either may be NULL. */
 int mfv_cast_shadow(const float* src, void* dst_bf16, void* dst_f16, int64_t n, void* stream);
+/* bf16 -> f32: the data-parallel trainer all-reduces the weight gradients as bf16 (half the NVLink volume of the DDP
+ * fp32 all-reduce, MAIN_PRE:312) and widens the averaged result back into the fp32 buffer the optimizer reads.        */
+int mfv_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
 int mfv_fill_f32(float* dst, float value, int64_t n, void* stream);
 /* torch.optim.SGD semantics (MAIN_CA:449): g += wd*p ; buf = mom*buf + g (buf = g on first step) ; p -= lr*buf.
  * Optionally refreshes the bf16 shadow in the same pass.                                                              */

@@ -26,6 +26,20 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+// bf16 -> f32 (gradients all-reduced in bf16 come back into the fp32 buffer the optimizer reads)
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+    const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+  }
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __bfloat162float(src[i]);
+}
+
 __global__ void fill_f32_kernel(float* __restrict__ dst, float v, long long n) {
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -364,6 +378,15 @@ extern "C" int mfv_cast_shadow(const float* src, void* dst_bf16, void* dst_f16, 
     return MFV_ERR_ALIGN;
   cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), reinterpret_cast<__half*>(dst_f16), n);
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+extern "C" int mfv_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* stream) {
+  if (n <= 0) return MFV_OK;
+  if ((reinterpret_cast<uintptr_t>(src_bf16) | reinterpret_cast<uintptr_t>(dst)) & 15) return MFV_ERR_ALIGN;
+  cast_bf16_f32_kernel<<<grid_for(n / 8 + 1, 256, 16 * num_sms()), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), dst, n);
   MFV_LAUNCH_CHECK();
   return MFV_OK;
 }

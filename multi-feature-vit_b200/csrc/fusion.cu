@@ -656,20 +656,686 @@ fusion_wgrad_kernel(const float* __restrict__ scratch, const float* __restrict__
   }
 }
 
+
+// =====================================================================================================================
+// Batched path (round 2).  The single-kernel forward / backward above give every (sample, direction) CTA its own pass
+// over six 590 KB weight matrices: 64 CTAs x 2.4 MB of L2 reads behind a chain of dependent mat-vecs (78 us forward,
+// 146 us backward at 32 pairs).  Here the mat-vecs of ALL samples of a direction are one small batched product each -
+// every weight matrix is read once per launch - and only the per-sample work (LayerNorms, the streaming softmax pass
+// over the 197 rows, the heads) stays per instance:
+//   forward : ln0 -> Q = Xh0 Wq^T -> T_h = Wk_h^T q_h -> streaming pass (u, lse) -> O = Wv u -> Y = Wp o + bp -> LN2 + heads
+//   backward: heads/LN2 -> dO = Wp^T dY -> dU_h = Wv_h^T dO_h -> streaming pass (d rows, dT) -> dQ = Wk dT
+//             -> dXh0 += Wq^T dQ -> LN1 backward of the CLS row + the records the weight-gradient kernel contracts
+// Per-instance state lives in the caller's `saved` buffer: [records B*2*recf][forward state 2B*FWD][backward temps 2B*BWT].
+// Instance index r = b * 2 + d (the order of the records).
+__host__ __device__ inline size_t fus2_fwd_floats(int C, int heads) { return (size_t)C * (8 + 2 * heads) + 16; }
+__host__ __device__ inline size_t fus2_bwt_floats(int C, int heads) { return (size_t)C * (2 + heads) + 16; }
+struct Fus2Off {  // offsets (floats) inside one instance's forward-state block
+  size_t f0, n0, xh0, q, t, u, o, y, chat, e, misc;  // misc: [0] rstd0, [1] rstd2, [4..8) lse
+  __host__ __device__ Fus2Off(int C, int heads) {
+    f0 = 0; n0 = C; xh0 = 2 * (size_t)C; q = 3 * (size_t)C; t = 4 * (size_t)C; u = t + (size_t)heads * C;
+    o = u + (size_t)heads * C; y = o + C; chat = y + C; e = chat + C; misc = e + C;
+  }
+};
+struct Fus2Rec {  // offsets inside one record (layout of fus_rec_floats, read by fusion_wgrad_kernel)
+  size_t dq, xh0, q, dt, d_o, u, dy, o, dz, chat, e, f0, dg1, db1;
+  __host__ __device__ Fus2Rec(int C, int heads) {
+    dq = 0; xh0 = C; q = 2 * (size_t)C; dt = 3 * (size_t)C; d_o = dt + (size_t)heads * C; u = d_o + C;
+    dy = u + (size_t)heads * C; o = dy + C; dz = o + C; chat = dz + C; e = chat + C; f0 = e + C; dg1 = f0 + C;
+    db1 = dg1 + C;
+  }
+};
+struct Fus2Bwt {  // backward temporaries per instance
+  size_t du, dxh0, df0, misc;
+  __host__ __device__ Fus2Bwt(int C, int heads) { du = 0; dxh0 = (size_t)heads * C; df0 = dxh0 + C; misc = df0 + C; }
+};
+
+// LN1 of the CLS row of every instance: one warp per instance.
+template <int CPL>
+__global__ void __launch_bounds__(128)
+fus2_ln0_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, float* __restrict__ fwd, size_t fstride,
+                int B, int S, int heads) {
+  constexpr int C = CPL * 32;
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= 2 * B) return;
+  const int b = r >> 1, d = r & 1;
+  const Fus2Off O(C, heads);
+  float* st = fwd + (size_t)r * fstride;
+  const float* row = tok + ((size_t)d * B + b) * S * C;
+  float v[CPL], n[CPL];
+  load_row<CPL>(v, row, lane);
+  float rstd;
+  ln_stats<CPL>(v, n, 1e-5f, rstd);
+  float xh[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = col_of<CPL>(i, lane);
+    xh[i] = n[i] * __ldg(prm.ln1_w[d] + c) + __ldg(prm.ln1_b[d] + c);
+  }
+  store_row<CPL>(v, st + O.f0, lane);
+  store_row<CPL>(n, st + O.n0, lane);
+  store_row<CPL>(xh, st + O.xh0, lane);
+  if (lane == 0) st[O.misc] = rstd;
+}
+
+// out[r][i] = W_d[i] . vec[r][sel(i)] (+ bias_d[i]) for the instances r = b*2+d of direction d = blockIdx.y, 32 instances
+// per blockIdx.z.  The 32 vectors are staged in shared memory with every load in flight at once (the stage is latency-
+// bound: a dependent chain of L2 reads is what made the first version slower than the single-kernel path); one warp per
+// weight row, held in registers.  nsel = 1, or heads (the vector of the head the 8 output rows of the block belong to:
+// o = Wv u_h, dq = Wk dt_h; hd is a multiple of 8).
+constexpr int FUS2_RB = 32;  // instances per rowdot CTA
+constexpr int FUS2_CB = 16;  // instances per coldot CTA
+template <int CPL>
+__global__ void __launch_bounds__(256)
+fus2_rowdot_kernel(const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ bias0,
+                   const float* __restrict__ bias1, const float* __restrict__ in, size_t in_stride,
+                   float* __restrict__ out, size_t out_stride, int B, int nsel, int hd) {
+  constexpr int C = CPL * 32;
+  extern __shared__ __align__(16) float fsm[];  // [FUS2_RB][C]
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = blockIdx.y;
+  const int b_base = blockIdx.z * FUS2_RB;
+  const int i = blockIdx.x * 8 + warp;
+  const float* W = d ? W1 : W0;
+  const float* bias = d ? bias1 : bias0;
+  const size_t sel = nsel > 1 ? (size_t)((blockIdx.x * 8) / hd) * C : 0;
+  for (int idx = threadIdx.x; idx < FUS2_RB * (C / 4); idx += 256) {
+    const int k = idx / (C / 4), c4 = idx - k * (C / 4);
+    const int b = min(b_base + k, B - 1);
+    reinterpret_cast<float4*>(fsm)[idx] = reinterpret_cast<const float4*>(in + (size_t)(b * 2 + d) * in_stride + sel)[c4];
+  }
+  float w[CPL];
+  load_row<CPL>(w, W + (size_t)i * C, lane);
+  const float bi = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  float mine = 0.f;  // lane k keeps the result of instance k
+#pragma unroll 4
+  for (int k = 0; k < FUS2_RB; ++k) {
+    const float s = dot_row<CPL>(w, fsm + (size_t)k * C, lane);
+    if (lane == k) mine = s;
+  }
+  const int b = b_base + lane;
+  if (b < B) out[(size_t)(b * 2 + d) * out_stride + i] = mine + bi;
+}
+
+// out[r][s][c] (+)= sum_{i in segment s} W_d[i][c] * vec[r][i]   (W^T products: t_h = Wk_h^T q_h, do = Wp^T dy, du_h = Wv_h^T
+// do_h, dxh0 += Wq^T dq).  grid (C/32, 2, ceil(B/16)): a CTA owns 32 columns for 16 instances.  Both the W[:, 32 columns]
+// slice (48 KB) and the 16 instance vectors (24 KB) are staged in shared memory with all loads in flight at once;
+// thread = (column, 2 instances).
+template <int CPL>
+__global__ void __launch_bounds__(256)
+fus2_coldot_kernel(const float* __restrict__ W0, const float* __restrict__ W1, const float* __restrict__ in,
+                   size_t in_stride, float* __restrict__ out, size_t out_stride, int B, int segs, int accumulate) {
+  constexpr int C = CPL * 32;
+  extern __shared__ __align__(16) float fsm[];
+  float* ws = fsm;                 // [C][32]
+  float* vec = fsm + C * 32;       // [FUS2_CB][C]
+  griddep_wait();
+  griddep_launch();
+  const int d = blockIdx.y;
+  const int b_base = blockIdx.z * FUS2_CB;
+  const float* W = (d ? W1 : W0) + blockIdx.x * 32;
+  for (int idx = threadIdx.x; idx < C * 8; idx += 256) {  // 8 float4 per weight row slice
+    const int i = idx >> 3, c4 = idx & 7;
+    reinterpret_cast<float4*>(ws)[idx] = __ldg(reinterpret_cast<const float4*>(W + (size_t)i * C) + c4);
+  }
+  for (int idx = threadIdx.x; idx < FUS2_CB * (C / 4); idx += 256) {
+    const int k = idx / (C / 4), c4 = idx - k * (C / 4);
+    const int b = min(b_base + k, B - 1);
+    reinterpret_cast<float4*>(vec)[idx] = reinterpret_cast<const float4*>(in + (size_t)(b * 2 + d) * in_stride)[c4];
+  }
+  __syncthreads();
+  const int cl = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + cl;
+  const int k0 = (threadIdx.x >> 5) * 2;  // this thread's two instances: k0, k0 + 1
+  const int seg_len = C / segs;
+  for (int s = 0; s < segs; ++s) {
+    float a0 = 0.f, a1 = 0.f;
+    const float* wp = ws + (size_t)(s * seg_len) * 32 + cl;
+    const float* v0 = vec + (size_t)k0 * C + s * seg_len;
+    const float* v1 = v0 + C;
+#pragma unroll 8
+    for (int i = 0; i < seg_len; ++i) {
+      const float w = wp[i * 32];
+      a0 = fmaf(w, v0[i], a0);
+      a1 = fmaf(w, v1[i], a1);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = b_base + k0 + k;
+      if (b < B) {
+        float* o = out + (size_t)(b * 2 + d) * out_stride + (size_t)s * C + c;
+        const float a = k ? a1 : a0;
+        *o = accumulate ? *o + a : a;
+      }
+    }
+  }
+}
+
+// Streaming pass of the forward for one instance: online softmax per head over the S LayerNorm'd rows -> u, lse.
+template <int CPL>
+__global__ void __launch_bounds__(FUS_THREADS, 1)
+fus2_stream_fwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, float* __restrict__ fwd, size_t fstride,
+                       int B, int S, int heads, float scale) {
+  constexpr int C = CPL * 32;
+  extern __shared__ __align__(16) float fsm[];
+  griddep_wait();
+  griddep_launch();
+  const int d = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Fus2Off O(C, heads);
+  float* st = fwd + (size_t)(b * 2 + d) * fstride;
+  float* s_g1 = fsm; float* s_b1 = s_g1 + C; float* s_f0 = s_b1 + C; float* s_t = s_f0 + C;
+  float* s_merge = s_t + heads * C;                           // [FUS_WARPS][heads][C]
+  float* s_stat = s_merge + (size_t)FUS_WARPS * heads * C;     // [FUS_WARPS][MAX_HEADS][2]
+  float* s_lse = s_stat + FUS_WARPS * MAX_HEADS * 2;
+  const float* other = tok + ((size_t)(1 - d) * B + b) * S * C;
+  for (int c = tid; c < C; c += FUS_THREADS) {
+    s_g1[c] = prm.ln1_w[d][c];
+    s_b1[c] = prm.ln1_b[d][c];
+    s_f0[c] = st[O.f0 + c];
+    for (int h = 0; h < heads; ++h) s_t[h * C + c] = st[O.t + (size_t)h * C + c];
+  }
+  __syncthreads();
+  {
+    float m[MAX_HEADS], l[MAX_HEADS], uacc[MAX_HEADS][CPL];
+#pragma unroll
+    for (int h = 0; h < MAX_HEADS; ++h) {
+      m[h] = -INFINITY; l[h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) uacc[h][i] = 0.f;
+    }
+    float vn[CPL];
+    if (warp < S) load_row<CPL>(vn, warp == 0 ? s_f0 : other + (size_t)warp * C, lane);
+    for (int j = warp; j < S; j += FUS_WARPS) {
+      float v[CPL], xh[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = vn[i];
+      if (j + FUS_WARPS < S) load_row<CPL>(vn, other + (size_t)(j + FUS_WARPS) * C, lane);
+      float rstd;
+      ln_stats<CPL>(v, xh, 1e-5f, rstd);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = col_of<CPL>(i, lane);
+        xh[i] = xh[i] * s_g1[c] + s_b1[c];
+      }
+#pragma unroll
+      for (int h = 0; h < MAX_HEADS; ++h) {
+        if (h < heads) {
+          const float s = scale * dot_row<CPL>(xh, s_t + h * C, lane);
+          const float mn = fmaxf(m[h], s);
+          const float a = __expf(m[h] - mn), p = __expf(s - mn);
+          l[h] = l[h] * a + p;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) uacc[h][i] = uacc[h][i] * a + p * xh[i];
+          m[h] = mn;
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < MAX_HEADS; ++h) {
+      if (h < heads) {
+        store_row<CPL>(uacc[h], s_merge + ((size_t)warp * heads + h) * C, lane);
+        if (lane == 0) { s_stat[(warp * MAX_HEADS + h) * 2] = m[h]; s_stat[(warp * MAX_HEADS + h) * 2 + 1] = l[h]; }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float mm = -INFINITY;
+    for (int w = 0; w < FUS_WARPS; ++w) mm = fmaxf(mm, s_stat[(w * MAX_HEADS + tid) * 2]);
+    float ll = 0.f;
+    for (int w = 0; w < FUS_WARPS; ++w) {
+      const float mw = s_stat[(w * MAX_HEADS + tid) * 2];
+      ll += (mw == -INFINITY) ? 0.f : s_stat[(w * MAX_HEADS + tid) * 2 + 1] * __expf(mw - mm);
+    }
+    s_lse[tid] = mm + __logf(ll);
+    st[O.misc + 4 + tid] = s_lse[tid];
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += FUS_THREADS) {
+    for (int h = 0; h < heads; ++h) {
+      float acc = 0.f;
+      for (int w = 0; w < FUS_WARPS; ++w) {
+        const float mw = s_stat[(w * MAX_HEADS + h) * 2];
+        if (mw != -INFINITY) acc += s_merge[((size_t)w * heads + h) * C + c] * __expf(mw - s_lse[h]);
+      }
+      st[O.u + (size_t)h * C + c] = acc;
+    }
+  }
+}
+
+// c = f0 + y ; LN2 ; e = f0 + LN2(c) ; logits.  One CTA per sample, warp d = direction d; fused = fused_0 + fused_1.
+template <int CPL>
+__global__ void __launch_bounds__(64)
+fus2_ln2_heads_kernel(const mfv_fusion_params prm, float* __restrict__ fwd, size_t fstride, float* __restrict__ out_fused,
+                      float* __restrict__ out_x, int B, int heads, int NC) {
+  constexpr int C = CPL * 32;
+  __shared__ float part[2][MAX_NC];
+  griddep_wait();
+  griddep_launch();
+  const int b = blockIdx.x, d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Fus2Off O(C, heads);
+  float* st = fwd + (size_t)(b * 2 + d) * fstride;
+  float f0[CPL], v[CPL], n[CPL], e[CPL];
+  load_row<CPL>(f0, st + O.f0, lane);
+  load_row<CPL>(v, st + O.y, lane);
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) v[i] += f0[i];
+  float rstd;
+  ln_stats<CPL>(v, n, 1e-6f, rstd);
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = col_of<CPL>(i, lane);
+    e[i] = f0[i] + n[i] * __ldg(prm.ln2_w[d] + c) + __ldg(prm.ln2_b[d] + c);
+  }
+  store_row<CPL>(n, st + O.chat, lane);
+  store_row<CPL>(e, st + O.e, lane);
+  if (lane == 0) st[O.misc + 1] = rstd;
+  for (int n_ = 0; n_ < NC; ++n_) {
+    const float s = dot_row<CPL>(e, prm.head_w[d] + (size_t)n_ * C, lane) + (prm.head_b[d] ? prm.head_b[d][n_] : 0.f);
+    if (lane == 0) part[d][n_] = s;
+    if (prm.vhead_w[d]) {
+      const float x = dot_row<CPL>(f0, prm.vhead_w[d] + (size_t)n_ * C, lane) + (prm.vhead_b[d] ? prm.vhead_b[d][n_] : 0.f);
+      if (lane == 0) out_x[((size_t)d * B + b) * NC + n_] = x;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NC) out_fused[(size_t)b * NC + threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x];
+}
+
+// Backward of the heads and LN2 for one instance (one warp): dz = Wh^T dfused, df0 = dz + Wvh^T dx, dy = LN2'(dz), df0 += dy.
+template <int CPL>
+__global__ void __launch_bounds__(128)
+fus2_bwd_heads_kernel(const mfv_fusion_params prm, const float* __restrict__ d_fused, const float* __restrict__ d_x,
+                      const float* __restrict__ fwd, size_t fstride, float* __restrict__ rec, size_t rstride,
+                      float* __restrict__ bwt, size_t bstride, int B, int heads, int NC) {
+  constexpr int C = CPL * 32;
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= 2 * B) return;
+  const int b = r >> 1, d = r & 1;
+  const Fus2Off O(C, heads);
+  const Fus2Rec R(C, heads);
+  const Fus2Bwt T(C, heads);
+  const float* st = fwd + (size_t)r * fstride;
+  float* rc = rec + (size_t)r * rstride;
+  float* bt = bwt + (size_t)r * bstride;
+  float de[CPL], df0[CPL], ch[CPL], g[CPL];
+  load_row<CPL>(ch, st + O.chat, lane);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = col_of<CPL>(i, lane);
+    float a = 0.f, v = 0.f;
+    for (int n = 0; n < NC; ++n) {
+      a += __ldg(prm.head_w[d] + (size_t)n * C + c) * d_fused[(size_t)b * NC + n];
+      if (d_x && prm.vhead_w[d]) v += __ldg(prm.vhead_w[d] + (size_t)n * C + c) * d_x[((size_t)d * B + b) * NC + n];
+    }
+    de[i] = a;
+    df0[i] = a + v;
+    g[i] = a * __ldg(prm.ln2_w[d] + c);
+    s1 += g[i];
+    s2 += g[i] * ch[i];
+  }
+  constexpr float invC = 1.0f / C;
+  const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+  const float rstd = st[O.misc + 1];
+  float dy[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    dy[i] = rstd * (g[i] - c1 - ch[i] * c2);
+    df0[i] += dy[i];
+  }
+  store_row<CPL>(de, rc + R.dz, lane);
+  store_row<CPL>(dy, rc + R.dy, lane);
+  store_row<CPL>(df0, bt + T.df0, lane);
+}
+
+// Streaming pass of the backward for one instance: gradients of every row of the other branch, dt, the CLS-row stash.
+template <int CPL>
+__global__ void __launch_bounds__(FUS_THREADS, 1)
+fus2_stream_bwd_kernel(const float* __restrict__ tok, const mfv_fusion_params prm, const float* __restrict__ fwd,
+                       size_t fstride, float* __restrict__ rec, size_t rstride, float* __restrict__ bwt, size_t bstride,
+                       float* __restrict__ dtok, int B, int S, int heads, float scale) {
+  constexpr int C = CPL * 32;
+  extern __shared__ __align__(16) float fsm[];
+  griddep_wait();
+  griddep_launch();
+  const int d = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = b * 2 + d;
+  const Fus2Off O(C, heads);
+  const Fus2Rec R(C, heads);
+  const Fus2Bwt T(C, heads);
+  const float* st = fwd + (size_t)r * fstride;
+  float* rc = rec + (size_t)r * rstride;
+  float* bt = bwt + (size_t)r * bstride;
+  float* s_g1 = fsm; float* s_b1 = s_g1 + C; float* s_f0 = s_b1 + C; float* s_t = s_f0 + C;
+  float* s_du = s_t + heads * C;
+  float* s_merge = s_du + heads * C;                         // [FUS_WARPS][max(heads, 2)][C]
+  float* s_lse = s_merge + (size_t)FUS_WARPS * MAX_HEADS * C;
+  float* s_D = s_lse + MAX_HEADS;
+  const float* other = tok + ((size_t)(1 - d) * B + b) * S * C;
+  for (int c = tid; c < C; c += FUS_THREADS) {
+    s_g1[c] = prm.ln1_w[d][c];
+    s_b1[c] = prm.ln1_b[d][c];
+    s_f0[c] = st[O.f0 + c];
+    for (int h = 0; h < heads; ++h) {
+      s_t[h * C + c] = st[O.t + (size_t)h * C + c];
+      s_du[h * C + c] = bt[T.du + (size_t)h * C + c];
+    }
+  }
+  if (tid < heads) s_lse[tid] = st[O.misc + 4 + tid];
+  __syncthreads();
+  if (warp < heads) {  // D_h = du_h . u_h
+    float v[CPL];
+    load_row<CPL>(v, s_du + warp * C, lane);
+    const float dd = dot_row<CPL>(v, st + O.u + (size_t)warp * C, lane);
+    if (lane == 0) s_D[warp] = dd;
+  }
+  __syncthreads();
+  float dg1[CPL], db1[CPL];
+  {
+    float dtacc[MAX_HEADS][CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) dg1[i] = db1[i] = 0.f;
+#pragma unroll
+    for (int h = 0; h < MAX_HEADS; ++h)
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) dtacc[h][i] = 0.f;
+    float* drows = dtok + ((size_t)(1 - d) * B + b) * S * C;
+    float vn[CPL];
+    if (warp < S) load_row<CPL>(vn, warp == 0 ? s_f0 : other + (size_t)warp * C, lane);
+    for (int j = warp; j < S; j += FUS_WARPS) {
+      float v[CPL], n[CPL], xh[CPL], dxh[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[i] = vn[i];
+      if (j + FUS_WARPS < S) load_row<CPL>(vn, other + (size_t)(j + FUS_WARPS) * C, lane);
+      float rstd;
+      ln_stats<CPL>(v, n, 1e-5f, rstd);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int c = col_of<CPL>(i, lane);
+        xh[i] = n[i] * s_g1[c] + s_b1[c];
+        dxh[i] = 0.f;
+      }
+#pragma unroll
+      for (int h = 0; h < MAX_HEADS; ++h) {
+        if (h < heads) {
+          const float s = scale * dot_row<CPL>(xh, s_t + h * C, lane);
+          const float p = __expf(s - s_lse[h]);
+          const float dp = dot_row<CPL>(xh, s_du + h * C, lane);
+          const float dss = p * (dp - s_D[h]) * scale;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const int c = col_of<CPL>(i, lane);
+            dtacc[h][i] += dss * xh[i];
+            dxh[i] += p * s_du[h * C + c] + dss * s_t[h * C + c];
+          }
+        }
+      }
+      if (j == 0) {
+        store_row<CPL>(dxh, bt + T.dxh0, lane);  // the CLS row still needs the query-path gradient (Wq^T dq)
+      } else {
+        float s1 = 0.f, s2 = 0.f, g[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int c = col_of<CPL>(i, lane);
+          dg1[i] += dxh[i] * n[i];
+          db1[i] += dxh[i];
+          g[i] = dxh[i] * s_g1[c];
+          s1 += g[i];
+          s2 += g[i] * n[i];
+        }
+        constexpr float invC = 1.0f / C;
+        const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) g[i] = rstd * (g[i] - c1 - n[i] * c2);
+        store_row<CPL>(g, drows + (size_t)j * C, lane);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < MAX_HEADS; ++h)
+      if (h < heads) store_row<CPL>(dtacc[h], s_merge + ((size_t)warp * MAX_HEADS + h) * C, lane);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += FUS_THREADS) {
+    for (int h = 0; h < heads; ++h) {
+      float acc = 0.f;
+      for (int w = 0; w < FUS_WARPS; ++w) acc += s_merge[((size_t)w * MAX_HEADS + h) * C + c];
+      rc[R.dt + (size_t)h * C + c] = acc;
+    }
+  }
+  __syncthreads();
+  store_row<CPL>(dg1, s_merge + ((size_t)warp * MAX_HEADS) * C, lane);
+  store_row<CPL>(db1, s_merge + ((size_t)warp * MAX_HEADS + 1) * C, lane);
+  __syncthreads();
+  for (int c = tid; c < C; c += FUS_THREADS) {  // rows j >= 1; the CLS row's share is added by fus2_bwd_row0_kernel
+    float ag = 0.f, ab = 0.f;
+    for (int w = 0; w < FUS_WARPS; ++w) {
+      ag += s_merge[((size_t)w * MAX_HEADS) * C + c];
+      ab += s_merge[((size_t)w * MAX_HEADS + 1) * C + c];
+    }
+    rc[R.dg1 + c] = ag;
+    rc[R.db1 + c] = ab;
+  }
+}
+
+// LN1 backward of the CLS row (now that dxh0 is complete) -> its dtok row; completes the record for the weight gradients.
+template <int CPL>
+__global__ void __launch_bounds__(128)
+fus2_bwd_row0_kernel(const mfv_fusion_params prm, const float* __restrict__ fwd, size_t fstride, float* __restrict__ rec,
+                     size_t rstride, const float* __restrict__ bwt, size_t bstride, float* __restrict__ dtok, int B, int S,
+                     int heads) {
+  constexpr int C = CPL * 32;
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= 2 * B) return;
+  const int b = r >> 1, d = r & 1;
+  const Fus2Off O(C, heads);
+  const Fus2Rec R(C, heads);
+  const Fus2Bwt T(C, heads);
+  const float* st = fwd + (size_t)r * fstride;
+  float* rc = rec + (size_t)r * rstride;
+  const float* bt = bwt + (size_t)r * bstride;
+  float n[CPL], dxh[CPL], g[CPL], df0[CPL], dg1[CPL], db1[CPL];
+  load_row<CPL>(n, st + O.n0, lane);
+  load_row<CPL>(dxh, bt + T.dxh0, lane);
+  load_row<CPL>(df0, bt + T.df0, lane);
+  load_row<CPL>(dg1, rc + R.dg1, lane);
+  load_row<CPL>(db1, rc + R.db1, lane);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = col_of<CPL>(i, lane);
+    g[i] = dxh[i] * __ldg(prm.ln1_w[d] + c);
+    s1 += g[i];
+    s2 += g[i] * n[i];
+    dg1[i] += dxh[i] * n[i];
+    db1[i] += dxh[i];
+  }
+  constexpr float invC = 1.0f / C;
+  const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+  const float rstd = st[O.misc];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) g[i] = df0[i] + rstd * (g[i] - c1 - n[i] * c2);
+  store_row<CPL>(g, dtok + ((size_t)d * B + b) * S * C, lane);
+  store_row<CPL>(dg1, rc + R.dg1, lane);
+  store_row<CPL>(db1, rc + R.db1, lane);
+  // forward vectors the weight-gradient contraction reads
+  float v[CPL];
+  load_row<CPL>(v, st + O.xh0, lane); store_row<CPL>(v, rc + R.xh0, lane);
+  load_row<CPL>(v, st + O.q, lane); store_row<CPL>(v, rc + R.q, lane);
+  load_row<CPL>(v, st + O.o, lane); store_row<CPL>(v, rc + R.o, lane);
+  load_row<CPL>(v, st + O.chat, lane); store_row<CPL>(v, rc + R.chat, lane);
+  load_row<CPL>(v, st + O.e, lane); store_row<CPL>(v, rc + R.e, lane);
+  load_row<CPL>(v, st + O.f0, lane); store_row<CPL>(v, rc + R.f0, lane);
+  for (int h = 0; h < heads; ++h) {
+    load_row<CPL>(v, st + O.u + (size_t)h * C, lane);
+    store_row<CPL>(v, rc + R.u + (size_t)h * C, lane);
+  }
+}
+
 }  // namespace mfv
 
 extern "C" size_t mfv_fusion_saved_floats(int64_t B, int64_t S, int64_t C, int64_t heads) {
   (void)S;
-  return (size_t)B * 2 * mfv::fus_rec_floats((int)C, (int)heads);
+  return (size_t)B * 2 * (mfv::fus_rec_floats((int)C, (int)heads) + mfv::fus2_fwd_floats((int)C, (int)heads) +
+                          mfv::fus2_bwt_floats((int)C, (int)heads));
 }
+
+namespace mfv {
+// Which forward the state inside a `saved` buffer belongs to (host-side bookkeeping: the executor entry points are
+// driven from one host thread).  mfv_fusion_bwd reuses the state only when it is called with the same buffer, tokens
+// and shape as the most recent batched forward; otherwise it recomputes the forward into the buffer first.
+struct Fus2Last { const float* tok; const float* saved; long long B, S, heads; };
+static Fus2Last g_fus2_last = {nullptr, nullptr, 0, 0, 0};
+
+struct Fus2Ws {
+  float *rec, *fwd, *bwt;
+  size_t rstride, fstride, bstride;
+  Fus2Ws(float* saved, long long B, int C, int heads) {
+    rstride = fus_rec_floats(C, heads);
+    fstride = fus2_fwd_floats(C, heads);
+    bstride = fus2_bwt_floats(C, heads);
+    rec = saved;
+    fwd = rec + (size_t)B * 2 * rstride;
+    bwt = fwd + (size_t)B * 2 * fstride;
+  }
+};
+
+static bool batched_fusion_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFVIT_FUSION_BATCHED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+constexpr size_t FUS2_ROW_SMEM = (size_t)FUS2_RB * 384 * sizeof(float);
+constexpr size_t FUS2_COL_SMEM = ((size_t)384 * 32 + (size_t)FUS2_CB * 384) * sizeof(float);
+
+static int fus2_set_attrs() {  // opt-in dynamic shared memory of the batched kernels, once per process
+  static bool done = false;
+  if (done) return MFV_OK;
+  MFV_CUDA_CHECK(cudaFuncSetAttribute(fus2_stream_fwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  MFV_CUDA_CHECK(cudaFuncSetAttribute(fus2_stream_bwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+  MFV_CUDA_CHECK(cudaFuncSetAttribute(fus2_rowdot_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUS2_ROW_SMEM));
+  MFV_CUDA_CHECK(cudaFuncSetAttribute(fus2_coldot_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUS2_COL_SMEM));
+  done = true;
+  return MFV_OK;
+}
+#define RC_ATTRS()                \
+  do {                            \
+    int _rc = fus2_set_attrs();   \
+    if (_rc) return _rc;          \
+  } while (0)
+
+static int fus2_forward(const float* tok, const mfv_fusion_params* p, float* out_fused, float* out_x, float* saved,
+                        long long B, long long S, int heads, int NC, cudaStream_t st) {
+  constexpr int CPL = 12, C = 384;
+  const Fus2Ws ws(saved, B, C, heads);
+  const Fus2Off O(C, heads);
+  const int hd = C / heads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const unsigned inst_blocks = (unsigned)((2 * B + 3) / 4);
+  const size_t smem_s = ((size_t)C * (3 + heads) + (size_t)FUS_WARPS * heads * C + FUS_WARPS * MAX_HEADS * 2 + MAX_HEADS) *
+                        sizeof(float);
+  RC_ATTRS();
+  const unsigned rz = (unsigned)((B + FUS2_RB - 1) / FUS2_RB), cz = (unsigned)((B + FUS2_CB - 1) / FUS2_CB);
+  MFV_CUDA_CHECK(launch_pdl(fus2_ln0_kernel<CPL>, dim3(inst_blocks), dim3(128), 0, st, tok, *p, ws.fwd, ws.fstride, (int)B,
+                            (int)S, heads));
+  MFV_LAUNCH_CHECK();
+  // q = Wq xh0
+  MFV_CUDA_CHECK(launch_pdl(fus2_rowdot_kernel<CPL>, dim3(C / 8, 2, rz), dim3(256), FUS2_ROW_SMEM, st, p->wq[0], p->wq[1],
+                            (const float*)nullptr, (const float*)nullptr, (const float*)(ws.fwd + O.xh0), ws.fstride,
+                            ws.fwd + O.q, ws.fstride, (int)B, 1, hd));
+  MFV_LAUNCH_CHECK();
+  // t_h = Wk_h^T q_h
+  MFV_CUDA_CHECK(launch_pdl(fus2_coldot_kernel<CPL>, dim3(C / 32, 2, cz), dim3(256), FUS2_COL_SMEM, st, p->wk[0],
+                            p->wk[1], (const float*)(ws.fwd + O.q), ws.fstride, ws.fwd + O.t, ws.fstride, (int)B, heads, 0));
+  MFV_LAUNCH_CHECK();
+  MFV_CUDA_CHECK(launch_pdl(fus2_stream_fwd_kernel<CPL>, dim3(2, (unsigned)B), dim3(FUS_THREADS), smem_s, st, tok, *p, ws.fwd,
+                            ws.fstride, (int)B, (int)S, heads, scale));
+  MFV_LAUNCH_CHECK();
+  // o = Wv u_h
+  MFV_CUDA_CHECK(launch_pdl(fus2_rowdot_kernel<CPL>, dim3(C / 8, 2, rz), dim3(256), FUS2_ROW_SMEM, st, p->wv[0], p->wv[1],
+                            (const float*)nullptr, (const float*)nullptr, (const float*)(ws.fwd + O.u), ws.fstride,
+                            ws.fwd + O.o, ws.fstride, (int)B, heads, hd));
+  MFV_LAUNCH_CHECK();
+  // y = Wp o + bp
+  MFV_CUDA_CHECK(launch_pdl(fus2_rowdot_kernel<CPL>, dim3(C / 8, 2, rz), dim3(256), FUS2_ROW_SMEM, st, p->proj_w[0], p->proj_w[1], p->proj_b[0],
+                            p->proj_b[1], (const float*)(ws.fwd + O.o), ws.fstride, ws.fwd + O.y, ws.fstride, (int)B, 1, hd));
+  MFV_LAUNCH_CHECK();
+  MFV_CUDA_CHECK(launch_pdl(fus2_ln2_heads_kernel<CPL>, dim3((unsigned)B), dim3(64), 0, st, *p, ws.fwd, ws.fstride, out_fused,
+                            out_x, (int)B, heads, NC));
+  MFV_LAUNCH_CHECK();
+  g_fus2_last = {tok, saved, B, S, heads};
+  return MFV_OK;
+}
+
+static int fus2_backward_main(const float* tok, const mfv_fusion_params* p, float* saved, const float* d_fused,
+                              const float* d_x, float* dtok, long long B, long long S, int heads, int NC, cudaStream_t st) {
+  constexpr int CPL = 12, C = 384;
+  const Fus2Ws ws(saved, B, C, heads);
+  const Fus2Rec R(C, heads);
+  const Fus2Bwt T(C, heads);
+  const int hd = C / heads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const unsigned inst_blocks = (unsigned)((2 * B + 3) / 4);
+  const unsigned bz = (unsigned)((B + FUS2_CB - 1) / FUS2_CB), rz = (unsigned)((B + FUS2_RB - 1) / FUS2_RB);
+  const size_t smem_s = ((size_t)C * (3 + 2 * heads) + (size_t)FUS_WARPS * MAX_HEADS * C + 2 * MAX_HEADS) * sizeof(float);
+  RC_ATTRS();
+  MFV_CUDA_CHECK(launch_pdl(fus2_bwd_heads_kernel<CPL>, dim3(inst_blocks), dim3(128), 0, st, *p, d_fused, d_x,
+                            (const float*)ws.fwd, ws.fstride, ws.rec, ws.rstride, ws.bwt, ws.bstride, (int)B, heads, NC));
+  MFV_LAUNCH_CHECK();
+  // do = Wp^T dy
+  MFV_CUDA_CHECK(launch_pdl(fus2_coldot_kernel<CPL>, dim3(C / 32, 2, bz), dim3(256), FUS2_COL_SMEM, st, p->proj_w[0], p->proj_w[1],
+                            (const float*)(ws.rec + R.dy), ws.rstride, ws.rec + R.d_o, ws.rstride, (int)B, 1, 0));
+  MFV_LAUNCH_CHECK();
+  // du_h = Wv_h^T do_h
+  MFV_CUDA_CHECK(launch_pdl(fus2_coldot_kernel<CPL>, dim3(C / 32, 2, bz), dim3(256), FUS2_COL_SMEM, st, p->wv[0], p->wv[1],
+                            (const float*)(ws.rec + R.d_o), ws.rstride, ws.bwt + T.du, ws.bstride, (int)B, heads, 0));
+  MFV_LAUNCH_CHECK();
+  MFV_CUDA_CHECK(launch_pdl(fus2_stream_bwd_kernel<CPL>, dim3(2, (unsigned)B), dim3(FUS_THREADS), smem_s, st, tok, *p,
+                            (const float*)ws.fwd, ws.fstride, ws.rec, ws.rstride, ws.bwt, ws.bstride, dtok, (int)B, (int)S,
+                            heads, scale));
+  MFV_LAUNCH_CHECK();
+  // dq = Wk dt_h
+  MFV_CUDA_CHECK(launch_pdl(fus2_rowdot_kernel<CPL>, dim3(C / 8, 2, rz), dim3(256), FUS2_ROW_SMEM, st, p->wk[0], p->wk[1],
+                            (const float*)nullptr, (const float*)nullptr, (const float*)(ws.rec + R.dt), ws.rstride,
+                            ws.rec + R.dq, ws.rstride, (int)B, heads, hd));
+  MFV_LAUNCH_CHECK();
+  // dxh0 += Wq^T dq
+  MFV_CUDA_CHECK(launch_pdl(fus2_coldot_kernel<CPL>, dim3(C / 32, 2, bz), dim3(256), FUS2_COL_SMEM, st, p->wq[0], p->wq[1],
+                            (const float*)(ws.rec + R.dq), ws.rstride, ws.bwt + T.dxh0, ws.bstride, (int)B, 1, 1));
+  MFV_LAUNCH_CHECK();
+  MFV_CUDA_CHECK(launch_pdl(fus2_bwd_row0_kernel<CPL>, dim3(inst_blocks), dim3(128), 0, st, *p, (const float*)ws.fwd, ws.fstride,
+                            ws.rec, ws.rstride, (const float*)ws.bwt, ws.bstride, dtok, (int)B, (int)S, heads));
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+}  // namespace mfv
 
 extern "C" int mfv_fusion_fwd(const float* tok, const mfv_fusion_params* p, float* out_fused, float* out_x,
                               float* saved, int64_t B, int64_t S, int64_t C, int64_t heads, int64_t NC, void* stream) {
   using namespace mfv;
-  (void)saved;
   if (!p || B <= 0 || S < 2 || heads <= 0 || heads > MAX_HEADS || NC <= 0 || NC > MAX_NC) return MFV_ERR_SHAPE;
   if (C != 384 || C % heads) return MFV_ERR_SHAPE;
   if (B > 65535) return MFV_ERR_SHAPE;
+  if (saved && batched_fusion_enabled())  // batched path: every weight matrix read once per launch, state kept for the backward
+    return fus2_forward(tok, p, out_fused, out_x, saved, B, S, (int)heads, (int)NC, reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = fus_smem_floats<12>((int)heads) * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -695,17 +1361,30 @@ static int fusion_bwd_impl(const float* tok, const mfv_fusion_params* p, const f
   if (C != 384 || C % heads) return MFV_ERR_SHAPE;
   if (B > 65535) return MFV_ERR_SHAPE;
   float* scratch = const_cast<float*>(saved);
-  const size_t smem = (fus_smem_floats<12>((int)heads) + (size_t)C * (6 + 2 * heads) + MAX_HEADS + 2 * MAX_NC) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    MFV_CUDA_CHECK(cudaFuncSetAttribute(fusion_bwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const float scale = 1.0f / sqrtf((float)(C / heads));
-  fusion_bwd_kernel<12><<<dim3(2, (unsigned)B), FUS_THREADS, smem, st>>>(tok, *p, d_fused, d_x, dtok, scratch, (int)B,
-                                                                          (int)S, (int)heads, (int)NC, scale);
-  MFV_LAUNCH_CHECK();
+  if (batched_fusion_enabled()) {
+    const bool have_fwd = g_fus2_last.tok == tok && g_fus2_last.saved == saved && g_fus2_last.B == B &&
+                          g_fus2_last.S == S && g_fus2_last.heads == heads;
+    if (!have_fwd) {  // the forward ran without this buffer (or something ran in between): rebuild its state here
+      float* tmp_out = scratch;  // logits are not needed: park them in the record area, which the backward overwrites
+      int rc = fus2_forward(tok, p, tmp_out, tmp_out + B * NC, scratch, B, S, (int)heads, (int)NC, st);
+      if (rc) return rc;
+    }
+    g_fus2_last.tok = nullptr;  // consumed: a later backward on the same buffer must not trust it blindly
+    int rc = fus2_backward_main(tok, p, scratch, d_fused, d_x, dtok, B, S, (int)heads, (int)NC, st);
+    if (rc) return rc;
+  } else {
+    const size_t smem = (fus_smem_floats<12>((int)heads) + (size_t)C * (6 + 2 * heads) + MAX_HEADS + 2 * MAX_NC) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(fusion_bwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    const float scale = 1.0f / sqrtf((float)(C / heads));
+    fusion_bwd_kernel<12><<<dim3(2, (unsigned)B), FUS_THREADS, smem, st>>>(tok, *p, d_fused, d_x, dtok, scratch, (int)B,
+                                                                            (int)S, (int)heads, (int)NC, scale);
+    MFV_LAUNCH_CHECK();
+  }
   // The contraction of the per-sample records into the parameter gradients feeds only the optimizer: deferred, it runs
   // on the side stream beside the encoder backward that consumes dtok.
   SideStream* ss = defer ? side_stream() : nullptr;

@@ -710,7 +710,11 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
     const long long pairs = num_sms() / 2;
     const long long t128 = ((p.M + 255) / 256) * p.tiles_n * p.G, t96 = ((p.M + 191) / 192) * p.tiles_n * p.G;
     const bool fits = (t96 + pairs - 1) / pairs <= (t128 + pairs - 1) / pairs;
-    if (a->rows_per_cta == 96 || (a->rows_per_cta == 0 && fits && EPI == MFV_EPI_RESID_F32 && rows96_enabled())) p.rows_cta = 96;
+    // MFVIT_ROWS96: 1 = forward residual GEMMs (proj / fc2, with or without the fused LayerNorm), 2 = also the bf16 dgrads
+    const int r96 = rows96_mode();
+    const bool fwd_res = (EPI == MFV_EPI_RESID_F32 || EPI == MFV_EPI_RESID_LN);
+    if (a->rows_per_cta == 96 || (a->rows_per_cta == 0 && fits && ((fwd_res && r96 >= 1) || (EPI == MFV_EPI_BF16 && r96 >= 2))))
+      p.rows_cta = 96;
   }
   p.tiles_m = (p.M + p.rows_cta * CG - 1) / (p.rows_cta * CG);
   p.kb_total = (p.K + BK - 1) / BK;

@@ -13,7 +13,8 @@ int num_sms();
 bool pdl_enabled();
 bool fuse_ln_enabled();  // MFVIT_FUSE_LN=0: standalone LayerNorm launches instead of the fused proj / fc2 epilogue
 bool dx32_stream_enabled();  // MFVIT_DX32=1: fp32 residual-gradient stream through the LayerNorm backward (default: bf16)
-bool rows96_enabled();  // MFVIT_ROWS96=1: 96 rows per CTA in the 384-wide pair tiles of the forward (off by default)
+bool patch_tma_enabled();  // MFVIT_PATCH_TMA=0: patchify -> GEMM -> embed_finish instead of the im2col-free TMA kernel
+int rows96_mode();  // MFVIT_ROWS96: 96 rows per CTA in the 384-wide pair tiles: 1 = forward residual GEMMs, 2 = + bf16 dgrads
 // Side stream of mfv_vit_backward: weight-gradient GEMMs and bias column sums are off the critical path (nothing in
 // the backward consumes them), so they run beside the dgrad / attention / LayerNorm chain and fill the SMs those
 // kernels leave idle (dgrad grids are 100 CTAs on 148 SMs at 32 pairs).  MFVIT_SIDE_STREAM=0 serialises everything.

@@ -40,7 +40,7 @@ static int g_device = -1;
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
 // Runtime switches (defaults from the environment, overridable through mfv_set_option): -1 = not read yet
-static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1, g_opt_fuse_ln = -1, g_opt_dx32 = -1;
+static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1, g_opt_fuse_ln = -1, g_opt_dx32 = -1, g_opt_patch_tma = -1;
 static int env_flag(const char* name, int dflt, char off_char) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
@@ -70,9 +70,12 @@ bool legacy_attention() {
   if (g_opt_legacy_attn < 0) g_opt_legacy_attn = env_flag("MFVIT_ATTN", 0, 'l');
   return g_opt_legacy_attn == 1;
 }
-bool rows96_enabled() {
-  if (g_opt_rows96 < 0) g_opt_rows96 = env_flag("MFVIT_ROWS96", 0, '1');
-  return g_opt_rows96 == 1;
+int rows96_mode() {
+  if (g_opt_rows96 < 0) {
+    const char* e = getenv("MFVIT_ROWS96");
+    g_opt_rows96 = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;
+  }
+  return g_opt_rows96;
 }
 bool fuse_ln_enabled() {
   if (g_opt_fuse_ln < 0) g_opt_fuse_ln = env_flag("MFVIT_FUSE_LN", 1, '0');
@@ -81,6 +84,10 @@ bool fuse_ln_enabled() {
 bool dx32_stream_enabled() {
   if (g_opt_dx32 < 0) g_opt_dx32 = env_flag("MFVIT_DX32", 0, '1');
   return g_opt_dx32 == 1;
+}
+bool patch_tma_enabled() {
+  if (g_opt_patch_tma < 0) g_opt_patch_tma = env_flag("MFVIT_PATCH_TMA", 1, '0');
+  return g_opt_patch_tma == 1;
 }
 bool pdl_enabled() {
   if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
@@ -102,9 +109,10 @@ extern "C" int mfv_set_option(const char* key, int value) {
   if (k == "pdl") g_opt_pdl = value ? 1 : 0;
   else if (k == "side_stream") g_opt_side = value ? 1 : 0;
   else if (k == "legacy_attention") g_opt_legacy_attn = value ? 1 : 0;
-  else if (k == "rows96") g_opt_rows96 = value ? 1 : 0;
+  else if (k == "rows96") g_opt_rows96 = value < 0 ? 0 : value;
   else if (k == "fuse_ln") g_opt_fuse_ln = value ? 1 : 0;
   else if (k == "dx32") g_opt_dx32 = value ? 1 : 0;
+  else if (k == "patch_tma") g_opt_patch_tma = value ? 1 : 0;
   else return MFV_ERR_ARG;
   return MFV_OK;
 }

@@ -198,23 +198,32 @@ extern "C" int mfv_vit_forward(const mfv_vit_plan* p, void* stream) {
   const long long D = C / p->H;
   const float scale = 1.0f / sqrtf((float)D);
   const long long rows_pe = p->B * p->np;
-  // patch embedding: patchify (per group: images are separate caller tensors) -> GEMM(+bias) -> +cls, +pos
-  for (int g = 0; g < G; ++g)
-    RCP(PROF_PATCHIFY, mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768,
-                    p->fwd_f16,
-                    v.dual() ? reinterpret_cast<__nv_bfloat16*>(p->patches_bf) + (long long)g * rows_pe * 768 : nullptr,
-                    p->B, p->img, st));
-  {
-    mfv_gemm_args a = {};
-    a.A = p->patches; a.B = v.wf(p->off_pe_w); a.C = p->acc; a.bias = v.w32(p->off_pe_b);
-    a.dtype_flags = p->fwd_f16 ? 3 : 0;
-    a.M = rows_pe; a.N = C; a.K = 768; a.G = G;
-    a.lda = 768; a.ldb = 768; a.ldc = C;
-    a.a_gstride = rows_pe * 768; a.b_gstride = p->P; a.c_gstride = rows_pe * C; a.bias_gstride = p->P;
-    a.epilogue = MFV_EPI_F32;
-    RCP(PROF_GEMM_FWD, mfv_gemm(&a, st));
+  // patch embedding.  Default (C == 384): ONE im2col-free GEMM - TMA tiles straight from the NCHW fp32 images, bias +
+  // position embedding + class token in the epilogue (patch_embed.cu).  Otherwise patchify (per group: the images are
+  // separate caller tensors) -> GEMM(+bias) -> +cls, +pos.
+  const bool pe_tma = patch_tma_enabled() && C == 384 && p->img / 16 <= 128;
+  if (pe_tma) {
+    RCP(PROF_GEMM_FWD, mfv_patch_embed_tma(p->images[0], G > 1 ? p->images[1] : nullptr, v.wf(p->off_pe_w), p->fwd_f16,
+                                           v.w32(p->off_pe_b), v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->img,
+                                           C, p->P, st));
+  } else {
+    for (int g = 0; g < G; ++g)
+      RCP(PROF_PATCHIFY, mfv_patchify(p->images[g], reinterpret_cast<__nv_bfloat16*>(p->patches) + (long long)g * rows_pe * 768,
+                      p->fwd_f16,
+                      v.dual() ? reinterpret_cast<__nv_bfloat16*>(p->patches_bf) + (long long)g * rows_pe * 768 : nullptr,
+                      p->B, p->img, st));
+    {
+      mfv_gemm_args a = {};
+      a.A = p->patches; a.B = v.wf(p->off_pe_w); a.C = p->acc; a.bias = v.w32(p->off_pe_b);
+      a.dtype_flags = p->fwd_f16 ? 3 : 0;
+      a.M = rows_pe; a.N = C; a.K = 768; a.G = G;
+      a.lda = 768; a.ldb = 768; a.ldc = C;
+      a.a_gstride = rows_pe * 768; a.b_gstride = p->P; a.c_gstride = rows_pe * C; a.bias_gstride = p->P;
+      a.epilogue = MFV_EPI_F32;
+      RCP(PROF_GEMM_FWD, mfv_gemm(&a, st));
+    }
+    RCP(PROF_EMBED, mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
   }
-  RCP(PROF_EMBED, mfv_embed_finish(p->acc, nullptr, v.w32(p->off_cls), v.w32(p->off_pos), v.x(0), G, p->B, p->np, C, p->P, st));
 
   // LayerNorm placement: with C == 384 the proj / fc2 GEMMs own whole rows (256 x 384 pair tiles) and normalise what
   // they just wrote (MFV_EPI_RESID_LN) - only the first LayerNorm of block 0 (input: the embedding) is a launch of its
@@ -360,7 +369,18 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
   const long long rows_pe = p->B * p->np;
   RCP(PROF_EMBED_BWD, mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
                           p->B, p->np, C, p->P, st));
-  if (!p->stop_grad_conv1)
+  if (!p->stop_grad_conv1) {
+    if (patch_tma_enabled() && C == 384 && p->img / 16 <= 128) {
+      // the forward never wrote a patch matrix: build the bf16 one the weight-gradient GEMM reads, here, off the
+      // critical path of the step (nothing later in the backward depends on it)
+      for (int g = 0; g < G; ++g) {
+        if (!p->images[g]) return MFV_ERR_ARG;
+        RCP(PROF_PATCHIFY, mfv_patchify(p->images[g],
+                                        reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(v.patches_b())) + (long long)g * rows_pe * 768,
+                                        0, nullptr, p->B, p->img, st));
+      }
+    }
     RC(linear_wgrad(v, p->dacc, C, v.patches_b(), 768, rows_pe, p->off_pe_w, -1, st));
+  }
   return MFV_OK;
 }

@@ -87,6 +87,8 @@ SIGNATURES = {
     "mfv_attn_bwd_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),
     "mfv_attn_bwd_ws": (C.c_int, [c_vp, C.c_int] + [c_vp] * 6 + [i64, i64, i64, i64, f32, c_vp]),
     "mfv_patchify": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, i64, i64, c_vp]),
+    "mfv_debug_patch_tma_probe": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, i64, c_vp]),
+    "mfv_patch_embed_tma": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, i64, c_vp]),
     "mfv_embed_finish": (C.c_int, [c_vp] * 5 + [i64] * 5 + [c_vp]),
     "mfv_embed_finish_bwd": (C.c_int, [c_vp] * 4 + [i64] * 5 + [c_vp]),
     "mfv_colsum_bf16": (C.c_int, [c_vp, c_vp, i64, i64, i64, i64, c_vp]),
@@ -114,6 +116,7 @@ SIGNATURES = {
     "mfv_vit_backward": (C.c_int, [C.POINTER(VitPlan), c_vp]),
     "mfv_vit_backward_range": (C.c_int, [C.POINTER(VitPlan), c_vp, C.c_int, C.c_int, C.c_int]),
     "mfv_cast_shadow": (C.c_int, [c_vp, c_vp, c_vp, i64, c_vp]),
+    "mfv_cast_bf16_f32": (C.c_int, [c_vp, c_vp, i64, c_vp]),
     "mfv_fill_f32": (C.c_int, [c_vp, f32, i64, c_vp]),
     "mfv_sgd_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, i64, f32, f32, f32, C.c_int, c_vp]),
     "mfv_adam_step": (C.c_int, [c_vp] * 6 + [i64, f32, f32, f32, f32, f32, C.c_int, i64, c_vp]),

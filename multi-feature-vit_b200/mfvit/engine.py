@@ -381,6 +381,7 @@ class ViTEngine:
         check(lib.mfv_vit_forward(C.byref(plan), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "mfv_vit_forward")
         lease = _Lease(ws) if save else None
+        ws.images = imgs if save else None  # the backward rebuilds the bf16 patch matrix from them (conv weight gradient)
         self._last_images = imgs  # keep inputs alive until the stream has consumed them
         return tokens, lease
 
@@ -421,7 +422,7 @@ class ViTEngine:
             ops.fill_(grad.view(-1), 0.0)
         dtokens = dtokens.contiguous()
         stop = not self._params[0][2][1].requires_grad  # patch_embed.proj.weight frozen (stop_grad_conv1)
-        plan = self._plan(ws, None, None, dtokens=dtokens, grad=grad, stop_grad_conv1=stop)
+        plan = self._plan(ws, getattr(ws, "images", None), None, dtokens=dtokens, grad=grad, stop_grad_conv1=stop)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if not segments:
             check(lib.mfv_vit_backward(C.byref(plan), stream), "mfv_vit_backward")

@@ -43,7 +43,9 @@ class FusionFn(torch.autograd.Function):
         ps = [None if p is None else p.detach().contiguous() for p in params]
         NC = ps[FUSION_FIELDS.index("head_w") * 2].shape[0]
         struct = ops.fusion_param_struct({n: (ps[2 * i], ps[2 * i + 1]) for i, n in enumerate(FUSION_FIELDS)})
-        fused, x = ops.fusion_fwd(tok, struct, B, S, Cd, heads, NC)
+        scratch = ops.fusion_scratch(tok, B, S, Cd, heads)  # forward state for the backward + its own records
+        fused, x = ops.fusion_fwd(tok, struct, B, S, Cd, heads, NC, saved=scratch)
+        ctx.scratch = scratch
         ctx.save_for_backward(tok, *[p for p in ps if p is not None])
         ctx.mask = [p is not None for p in ps]
         ctx.heads, ctx.NC = heads, NC
@@ -69,7 +71,8 @@ class FusionFn(torch.autograd.Function):
         if d_fused is None:
             d_fused = torch.zeros(B, ctx.NC, device=tok.device)
         dxc = None if d_x is None else d_x.contiguous()
-        dtok = ops.fusion_bwd(tok, struct, gstruct, d_fused.contiguous(), dxc, B, S, Cd, ctx.heads, ctx.NC)
+        dtok = ops.fusion_bwd(tok, struct, gstruct, d_fused.contiguous(), dxc, B, S, Cd, ctx.heads, ctx.NC,
+                              scratch=ctx.scratch)
         return (dtok, None) + tuple(gs)
 
 

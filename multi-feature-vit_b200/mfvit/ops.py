@@ -184,6 +184,36 @@ def cast_shadow(src, dst_bf16=None, dst_f16=None):
     check(_lib_for(src).mfv_cast_shadow(_p(src), _p(dst_bf16), _p(dst_f16), src.numel(), _stream()), "mfv_cast_shadow")
 
 
+def patch_embed_tma(imgs, w, bias, cls, pos, f16=True):
+    """imgs: list of G f32 [B,3,HW,HW]; w f32 [G,C,768] (rounded here to the 16-bit operand format), bias / cls f32 [G,C],
+    pos f32 [G,S,C] -> x f32 [G,B,S,C].  The G parameter sets must sit at one stride inside a common buffer (as the
+    engine's flat master / shadow do): here they are packed into one."""
+    G, B, HW = len(imgs), imgs[0].shape[0], imgs[0].shape[-1]
+    Cd, S = w.shape[1], pos.shape[1]
+    n = [Cd * 768, Cd, Cd, S * Cd]
+    P = (sum(n) + 7) // 8 * 8
+    flat = torch.zeros(G, P, device=w.device, dtype=torch.float32)
+    offs, o = [], 0
+    for k in n:
+        offs.append(o)
+        o += k
+    for g in range(G):
+        for t, off, k in zip((w[g], bias[g], cls[g], pos[g]), offs, n):
+            flat[g, off:off + k] = t.reshape(-1)
+    flat16 = flat.to(torch.float16 if f16 else torch.bfloat16)
+    x = torch.empty(G, B, S, Cd, device=w.device, dtype=torch.float32)
+    im = [t.contiguous() for t in imgs]
+    check(_lib_for(w).mfv_patch_embed_tma(_p(im[0]), _p(im[1]) if G > 1 else None, _p(flat16[0, offs[0]:]), int(f16),
+                                          _p(flat[0, offs[1]:]), _p(flat[0, offs[2]:]), _p(flat[0, offs[3]:]), _p(x), G, B,
+                                          HW, Cd, P, _stream()), "mfv_patch_embed_tma")
+    return x
+
+
+def cast_bf16_f32_(src_bf16, dst_f32):
+    check(_lib_for(src_bf16).mfv_cast_bf16_f32(_p(src_bf16), _p(dst_f32), src_bf16.numel(), _stream()), "mfv_cast_bf16_f32")
+    return dst_f32
+
+
 def fill_(t, value=0.0):
     check(_lib_for(t).mfv_fill_f32(_p(t), float(value), t.numel(), _stream()), "mfv_fill_f32")
     return t
@@ -224,11 +254,13 @@ def fusion_param_struct(tensors, cls=FusionParams):
     return s
 
 
-def fusion_fwd(tok, params, B, S, Cd, heads, NC):
+def fusion_fwd(tok, params, B, S, Cd, heads, NC, saved=None):
+    """saved (fusion_scratch): runs the batched stage kernels and keeps the forward state there for fusion_bwd; without
+    it the single-kernel forward runs and a later backward recomputes what it needs."""
     lib = _lib_for(tok)
     fused = torch.empty(B, NC, device=tok.device, dtype=torch.float32)
     x = torch.empty(2, B, NC, device=tok.device, dtype=torch.float32)
-    check(lib.mfv_fusion_fwd(_p(tok), C.byref(params), _p(fused), _p(x), None, B, S, Cd, heads, NC, _stream()),
+    check(lib.mfv_fusion_fwd(_p(tok), C.byref(params), _p(fused), _p(x), _p(saved), B, S, Cd, heads, NC, _stream()),
           "mfv_fusion_fwd")
     return fused, x
 

@@ -17,10 +17,10 @@ for seed in range(int(sys.argv[2]) if len(sys.argv) > 2 else 6):
         tok_r = torch.stack([r_c.features3D(img_c), r_e.features3D(img_e)])
         row = []
         for fuse in (0, 1):
-            lib.mfv_set_option(b"fuse_ln", fuse)
+            lib.mfv_set_option(b"patch_tma", fuse)
             fo, oc, oe = o_f(o_c, o_e, img_c, img_e)
             from mfvit.engine import encode, engine_for
             tok_o = encode(engine_for(o_c, o_e), [img_c, img_e])
             row.append((float((fo - fr).abs().max()), float((oc - xc).abs().max()), float((oe - xe).abs().max()),
                         float((tok_o - tok_r).abs().max()), float((tok_o[:, :, 0] - tok_r[:, :, 0]).pow(2).mean().sqrt())))
-    print("seed %d  " % seed + "   ".join("fuse_ln=%d fused %.2e cxr %.2e enh %.2e tok max %.2e cls rms %.2e" % ((i,) + r) for i, r in enumerate(row)), flush=True)
+    print("seed %d  " % seed + "   ".join("patch_tma=%d fused %.2e cxr %.2e enh %.2e tok max %.2e cls rms %.2e" % ((i,) + r) for i, r in enumerate(row)), flush=True)

@@ -38,5 +38,15 @@ def timeit(fn, reps=10):
 
 
 print(torch.cuda.get_device_name(0), "B", B)
-print("fusion fwd: %.1f us" % (timeit(lambda: ops.fusion_fwd(tok, ps, B, S, C, heads, NC)) * 1e3))
+print("fusion fwd (single kernel): %.1f us" % (timeit(lambda: ops.fusion_fwd(tok, ps, B, S, C, heads, NC)) * 1e3))
+scr = ops.fusion_scratch(tok, B, S, C, heads)
+print("fusion fwd (batched stages): %.1f us" % (timeit(lambda: ops.fusion_fwd(tok, ps, B, S, C, heads, NC, saved=scr)) * 1e3))
+
+
+def fwd_bwd():
+    ops.fusion_fwd(tok, ps, B, S, C, heads, NC, saved=scr)
+    ops.fusion_bwd(tok, ps, gs, dlog, dx, B, S, C, heads, NC, dtok=dtok, scratch=scr)
+
+
+print("fusion fwd + bwd (+wgrad), batched, state reused: %.1f us" % (timeit(fwd_bwd) * 1e3))
 print("fusion bwd (+wgrad): %.1f us" % (timeit(lambda: ops.fusion_bwd(tok, ps, gs, dlog, dx, B, S, C, heads, NC, dtok=dtok)) * 1e3))

@@ -107,6 +107,47 @@ def t_gemm_resid_ln():
         report("gemm resid+LN y f32 " + tag, y32, yr, 2e-5, rel=True)
 
 
+def t_patch_embed_tma():
+    """im2col-free patch embedding (5-D TMA tiles from NCHW fp32, 16-bit conversion in shared memory, tcgen05) vs Conv2d +
+    flatten + cls + pos on the same 16-bit-rounded operands; and the raw TMA box layout the converter warps rely on."""
+    import ctypes as C
+    from mfvit import _lib
+    lib = _lib.init(0)
+    HW, Bp = 224, 2
+    img = torch.arange(Bp * 3 * HW * HW, device=dev, dtype=torch.float32).view(Bp, 3, HW, HW)
+    raw = torch.zeros(8192, device=dev)
+    kb, ph0, cb = 6, 9, 4  # channel 1 of image 1, pixel rows 8..11 of the patches, second band (5 real patch rows)
+    rc = lib.mfv_debug_patch_tma_probe(C.c_void_p(img.data_ptr()), C.c_void_p(raw.data_ptr()), Bp, HW, kb, ph0, cb,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+    gw, PH = 14, 9
+    exp = torch.zeros(128, 4, 16, device=dev)
+    exp[gw * PH:] = -777.0
+    for ph in range(min(PH, gw - ph0)):
+        for pw in range(gw):
+            exp[ph * gw + pw] = img[1, 1, (ph0 + ph) * 16 + 8:(ph0 + ph) * 16 + 12, pw * 16:pw * 16 + 16]
+    report("patch embed TMA box layout [patch][i][j] (+ zero fill past the image)", raw.view(128, 4, 16), exp, 0.0)
+    for B, HW, G, f16 in ((3, 224, 2, True), (2, 384, 1, True), (5, 224, 1, False)):
+        torch.manual_seed(8)
+        gw = HW // 16
+        S = 1 + gw * gw
+        dt = torch.float16 if f16 else torch.bfloat16
+        imgs = [torch.randn(B, 3, HW, HW, device=dev) * 1.5 + 0.3 for _ in range(G)]
+        w = torch.randn(G, 384, 768, device=dev) * 0.05
+        bias = torch.randn(G, 384, device=dev) * 0.1
+        cls = torch.randn(G, 384, device=dev)
+        pos = torch.randn(G, S, 384, device=dev)
+        x = ops.patch_embed_tma(imgs, w, bias, cls, pos, f16=f16)
+        ref = torch.empty_like(x)
+        for g in range(G):
+            t = F.conv2d(imgs[g].to(dt).float(), w[g].to(dt).float().view(384, 3, 16, 16), bias[g], stride=16)
+            ref[g, :, 1:] = t.flatten(2).transpose(1, 2) + pos[g, 1:]
+            ref[g, :, 0] = cls[g] + pos[g, 0]
+        tag = "B%d %dpx G%d %s" % (B, HW, G, "f16" if f16 else "bf16")
+        report("patch embed TMA cls row " + tag, x[:, :, 0], ref[:, :, 0], 1e-6)
+        report("patch embed TMA tokens " + tag, x[:, :, 1:], ref[:, :, 1:], 2e-5, rel=True)
+
+
 def t_gemm_epilogues():
     torch.manual_seed(1)
     G, M, N, K = 2, 1000, 384, 256
@@ -256,6 +297,27 @@ def t_fusion():
     for k, v in names.items():
         for d in range(2):
             report("fusion bwd d%s[%d]" % (k, d), gt[k][d], v[d].grad, 2e-3, rel=True)
+    # batched stage kernels: forward with a saved buffer, backward reusing its state (what the trainer / autograd do)
+    for Bb in (B, 33):
+        tk = (torch.randn(2, Bb, S, C, device=dev) * 1.5).requires_grad_(True)
+        f_ref = fus.fuse(tk[0], tk[1])
+        x_r = torch.stack([vh[0](tk[0][:, 0]), vh[1](tk[1][:, 0])])
+        for v in names.values():
+            for t in v:
+                t.grad = None
+        dfu, dxx = torch.randn(Bb, NC, device=dev), torch.randn(2, Bb, NC, device=dev)
+        (f_ref * dfu).sum().add((x_r * dxx).sum()).backward()
+        scratch = ops.fusion_scratch(tk, Bb, S, C, heads)
+        fused_b, x_b = ops.fusion_fwd(tk.detach(), prm, Bb, S, C, heads, NC, saved=scratch)
+        report("fusion batched fwd fused B%d" % Bb, fused_b, f_ref, 1e-4)
+        report("fusion batched fwd x B%d" % Bb, x_b, x_r, 1e-4)
+        gt2 = {k: tuple(torch.zeros_like(t) for t in v) for k, v in names.items()}
+        grads2 = ops.fusion_param_struct(gt2, cls=FusionGrads)
+        dtok2 = ops.fusion_bwd(tk.detach(), prm, grads2, dfu, dxx, Bb, S, C, heads, NC, scratch=scratch)
+        report("fusion batched bwd dtok B%d" % Bb, dtok2, tk.grad, 1e-3, rel=True)
+        worst = max(float((gt2[k][d] - v[d].grad).abs().max() / v[d].grad.abs().max().clamp_min(1e-20))
+                    for k, v in names.items() for d in range(2))
+        report("fusion batched bwd all 26 parameter grads B%d (worst rel)" % Bb, torch.tensor([worst]), torch.zeros(1), 2e-3)
 
 
 # ------------------------------------------------------------------------------------------------------------ misc
@@ -404,6 +466,7 @@ def main():
     run("gemm epilogues", t_gemm_epilogues, flt)
     run("gemm rows96", t_gemm_rows96, flt)
     run("gemm resid+LN", t_gemm_resid_ln, flt)
+    run("patch embed TMA", t_patch_embed_tma, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
     run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
     run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)
