@@ -481,6 +481,15 @@ def main():
     barrier()
     u8_nosync_ms = u_start.elapsed_time(u_end)
 
+    # ---- data-parallel correctness on this hardware (N > 1): all-reduced gradient == one rank on the concatenated batch.
+    # Runs while the replicas are still identical (the same-work leg below steps every rank on its own, unsynchronised).
+    dp_check = None
+    if world > 1:
+        try:
+            dp_check = dp_gradient_check(trainer, device, rank, world, img)
+        except Exception as exc:  # noqa: BLE001 - a failed self-check must not lose the measured line
+            dp_check = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- data-parallel runs only: the same per-GPU work with the gradient all-reduce switched off (every rank steps its
     # own replica), i.e. the single-GPU rate at THIS batch size - the denominator a weak-scaling efficiency needs
     # (N = 1 of this benchmark runs configs[1], 32 pairs, not the 64 pairs per GPU of configs[2])
@@ -526,13 +535,6 @@ def main():
         elapsed_ms, e2e_ms, u8_ms, u8_nosync_ms, local_ms = (float(v) for v in t)
 
     graph_launches = trainer.graph_launches
-    # ---- data-parallel correctness on this hardware (N > 1): all-reduced gradient == one rank on the concatenated batch
-    dp_check = None
-    if world > 1:
-        try:
-            dp_check = dp_gradient_check(trainer, device, rank, world, img)
-        except Exception as exc:  # noqa: BLE001 - a failed self-check must not lose the measured line
-            dp_check = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---- BASELINE configs[3]: the MoCo-v3-structure / v2-loss pretraining step under SyncBatchNorm + DDP over NCCL
     # (MAIN_PRE:297,312), 128 images per GPU, K = 65 536, with its self-checks (tests/moco_dp_common.py).  N = 1 runs it

@@ -100,6 +100,10 @@ typedef struct {
   int32_t ln_out_f32;
 } mfv_gemm_args;
 int mfv_gemm(const mfv_gemm_args* args, void* stream);
+/* Two split-K weight-gradient GEMMs (MFV_EPI_ATOMIC_F32, N % 384 == 0, M > 128; same K, G, splits, majorness, formats,
+ * bias_gstride) as ONE grid of 256 x 384 pair tiles: the four weight gradients of a transformer block (autograd of the
+ * four nn.Linear, absent timm Block) take two launches instead of four.                                              */
+int mfv_gemm_wgrad_pair(const mfv_gemm_args* a, const mfv_gemm_args* b, void* stream);
 
 /* ---- LayerNorm ------------------------------------------------------------------------------------------------------
  * Replaces nn.LayerNorm(384, eps=1e-6) x25 per branch in the absent timm ViT, PreNorm's LayerNorm (MOD:15-21).

@@ -41,6 +41,11 @@ struct GemmParams {
   int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
   int rows_cta;           // rows of the output tile each CTA owns: 128, or 96 (K-major A only; see launch_gemm_epi)
   float* row_sum;         // BN == 384, fp32 reduce-add epilogue: += row sums of A (bias gradient of a wgrad GEMM)
+  // Second problem of a paired launch (mfv_gemm_wgrad_pair: two weight-gradient GEMMs that share the reduction length,
+  // split count, groups and operand formats run as ONE grid; tiles [0, tiles0) belong to problem 0, the rest to problem
+  // 1, whose operand / output maps ride in the tmC2 / tmC3 / tmAux slots).  tiles0 = INT_MAX for ordinary launches.
+  int tiles0, M1, N1, tiles_m1, tiles_n1;
+  float* row_sum1;
   long long bias_gstride;
   const float* bias;
   // MFV_EPI_RESID_LN: LayerNorm of the finished row, fused into the epilogue (gamma / beta share bias_gstride)
@@ -107,6 +112,19 @@ __device__ __forceinline__ void bulk_wait_read_n(int n) {
 // address bits [7,9) = (r >> 1) & 3); a warp's 32 x 16 B store then covers every bank exactly 4 times (conflict-free)
 __device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
+struct TileInfo { int prob, n_tile, split, m_tile, g; };
+__device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t) {
+  TileInfo ti;
+  ti.prob = 0;
+  int tm = p.tiles_m, tn = p.tiles_n;
+  if (t >= p.tiles0) { t -= p.tiles0; ti.prob = 1; tm = p.tiles_m1; tn = p.tiles_n1; }
+  ti.n_tile = t % tn; t /= tn;
+  ti.split = t % p.splits; t /= p.splits;
+  ti.m_tile = t % tm;
+  ti.g = t / tm;
+  return ti;
+}
+
 // EPI is a template parameter (MFV_EPI_ATOMIC_F32 shares the MFV_EPI_F32 instance): the epilogue is the issue-bound
 // part of these kernels, and a specialised instruction stream keeps it small (I-cache) and spill-free.
 template <int BN, int CG, int EPI>
@@ -155,7 +173,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
   }
-  if (BN == 384 && warp == 2 && p.row_sum) {  // bf16 1.0 everywhere: the swizzle is irrelevant for a constant tile
+  if (BN == 384 && warp == 2 && (p.row_sum || p.row_sum1)) {  // bf16 1.0 everywhere: the swizzle is irrelevant for a constant tile
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       reinterpret_cast<uint4*>(ones_tile)[lane + 32 * i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -167,8 +185,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();
 
-  const int tiles_per_group = p.tiles_m * p.tiles_n * p.splits;
-  const int total_tiles = tiles_per_group * p.G;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits * p.G +
+                          (p.tiles0 == 0x7fffffff ? 0 : p.tiles_m1 * p.tiles_n1 * p.splits * p.G);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -180,11 +198,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (CG == 2) tma_load_3d_cg2(dst, map, bar, c0, c1, c2); else tma_load_3d(dst, map, bar, c0, c1, c2);
       };
       for (int t = cta_id; t < total_tiles; t += num_ctas) {
-        int r = t;
-        const int n_tile = r % p.tiles_n; r /= p.tiles_n;
-        const int split = r % p.splits;   r /= p.splits;
-        const int m_tile = r % p.tiles_m;
-        const int g = r / p.tiles_m;
+        const TileInfo ti = decode_tile(p, t);
+        const int n_tile = ti.n_tile, split = ti.split, m_tile = ti.m_tile, g = ti.g;
+        const CUtensorMap* mapA = ti.prob ? &tmC2 : &tmA;
+        const CUtensorMap* mapB = ti.prob ? &tmC3 : &tmB;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         const int m0 = (m_tile * CG + (int)rank) * p.rows_cta;       // this CTA's rows of A
@@ -197,24 +214,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (rank == 0)
             mbar_arrive_expect_tx(&full_bar[stage], (S::STAGE_BYTES - S::A_BYTES + p.rows_cta * BK * 2) * CG);
           if (!p.a_mn) {
-            load(sa, &tmA, &full_bar[stage], kb * BK, m0, g);
+            load(sa, mapA, &full_bar[stage], kb * BK, m0, g);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK, g);
+            for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, mapA, &full_bar[stage], m0 + j * 64, kb * BK, g);
           }
           if (BN == 384) {
             // pair tile = UMMA N=256 (each CTA supplies rows [rank*128, +128) of it) + UMMA N=128 (rows 256 + rank*64)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               const int nn = n_tile * BN + (j < 2 ? (int)rank * 128 + j * 64 : 256 + (int)rank * 64);
-              if (!p.b_mn) load(sb + j * 8192, &tmB, &full_bar[stage], kb * BK, nn, g);
-              else load(sb + j * 8192, &tmB, &full_bar[stage], nn, kb * BK, g);
+              if (!p.b_mn) load(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g);
+              else load(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g);
             }
           } else if (!p.b_mn) {
-            load(sb, &tmB, &full_bar[stage], kb * BK, n0, g);
+            load(sb, mapB, &full_bar[stage], kb * BK, n0, g);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK, g);
+            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, mapB, &full_bar[stage], n0 + j * 64, kb * BK, g);
           }
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -235,8 +252,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int it = 0;
       for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
-        int r = t / p.tiles_n;
-        const int split = r % p.splits;
+        const TileInfo ti = decode_tile(p, t);
+        const int split = ti.split;
+        const bool want_rs = (ti.prob ? p.row_sum1 : p.row_sum) != nullptr;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         const int as = it % NACC;
@@ -258,7 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (BN == 384) {
               const uint64_t db2 = make_smem_desc_sw128(sb + 16384u + k * b_kadv, b_lbo, 1024u);
               umma_bf16_cg2(tmem_d + 256u, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
-              if (p.row_sum)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
+              if (want_rs)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
                 umma_bf16_cg2(tmem_d + 384u, da, make_smem_desc_sw128(smem_u32(ones_tile), 8192u, 1024u), idesc3,
                               (kb > kb0 || k > 0) ? 1u : 0u);
             }
@@ -321,11 +339,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
     int it = 0;
     for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
-      int r = t;
-      const int n_tile = r % p.tiles_n; r /= p.tiles_n;
-      r /= p.splits;
-      const int m_tile = r % p.tiles_m;
-      const int g = r / p.tiles_m;
+      const TileInfo ti = decode_tile(p, t);
+      const int n_tile = ti.n_tile, m_tile = ti.m_tile, g = ti.g;
+      const int pM = ti.prob ? p.M1 : p.M, pN = ti.prob ? p.N1 : p.N;
+      const CUtensorMap* mapC = ti.prob ? &tmAux : &tmC;   // paired launches only exist for the fp32 reduce-add epilogue
+      float* const row_sum = ti.prob ? p.row_sum1 : p.row_sum;
       const int as = it % NACC;
       const uint32_t aphase = (it / NACC) & 1;
       const int row0 = (m_tile * CG + (int)rank) * p.rows_cta + q * 32;  // first row of this warp's 32-row slice
@@ -333,8 +351,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
       // pieces owned by this warp that hold real output (slices past M / N are skipped; TMA clips partial ones)
       int n_my = 0;
-      if (row0 < p.M && q * 32 < p.rows_cta)  // 96-row CTAs: TMEM lanes 96..127 hold rows the neighbour tile owns
-        for (int c = h; c < npieces && ncol0 + c * PW < p.N; c += 4) ++n_my;
+      if (row0 < pM && q * 32 < p.rows_cta)  // 96-row CTAs: TMEM lanes 96..127 hold rows the neighbour tile owns
+        for (int c = h; c < npieces && ncol0 + c * PW < pN; c += 4) ++n_my;
       // The aux operand (fp32 residual / bf16 pre-GELU u) of piece i arrives by TMA in the ring slot where the result
       // of piece i is then computed in place.  AUX_AHEAD pieces are in flight: the load of piece i+AUX_AHEAD is issued
       // right after the first store of piece i, into the slot whose previous store is then the second-newest bulk group
@@ -370,11 +388,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         continue;
       }
-      if (BN == 384 && epi == MFV_EPI_F32 && p.row_sum && h == 0 && n_tile == 0) {
+      if (BN == 384 && epi == MFV_EPI_F32 && row_sum && h == 0 && n_tile == 0) {
         uint32_t rs;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(trow + 384u) : "memory");
         tmem_ld_wait();
-        if (row0 + lane < p.M) atomicAdd(p.row_sum + (long long)g * p.bias_gstride + row0 + lane, __uint_as_float(rs));
+        if (row0 + lane < pM) atomicAdd(row_sum + (long long)g * p.bias_gstride + row0 + lane, __uint_as_float(rs));
       }
       [[maybe_unused]] float ln_m = 0.f, ln_s = 0.f;  // MFV_EPI_RESID_LN: mean and sum of squared deviations so far
 #pragma unroll 1
@@ -539,7 +557,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<float4*>(st0 + stage_off(lane, j)) =
                   make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            publish(&tmC, st0, n0, row0, g, p.epi == MFV_EPI_ATOMIC_F32);
+            publish(mapC, st0, n0, row0, g, p.epi == MFV_EPI_ATOMIC_F32);
           }
         }
       }
@@ -740,9 +758,10 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   }
   p.row_sum = nullptr;
   if (a->row_sum) {
-    if (BN != 384 || a->epilogue != MFV_EPI_ATOMIC_F32 || a->N != 384) return MFV_ERR_ARG;
+    if (BN != 384 || a->epilogue != MFV_EPI_ATOMIC_F32 || a->N % 384 != 0) return MFV_ERR_ARG;
     p.row_sum = a->row_sum;
   }
+  p.tiles0 = 0x7fffffff; p.M1 = p.N1 = p.tiles_m1 = p.tiles_n1 = 0; p.row_sum1 = nullptr;
 
   CUtensorMap tmA, tmB, tmC, tmC2, tmC3, tmAux;
   int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G,
@@ -826,6 +845,72 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
   }
 }
 
+// Two weight-gradient GEMMs as ONE grid of 256 x 384 pair tiles (fp32 reduce-add epilogue): same reduction length K,
+// split count, groups and operand formats; problem 1's operand / output maps ride in the tmC2 / tmC3 / tmAux slots.
+static int launch_wgrad_pair(const mfv_gemm_args* a, const mfv_gemm_args* b, cudaStream_t stream) {
+  constexpr int BN = 384, CG = 2;
+  using S = GemmSmem<BN, CG, epi_nbuf(MFV_EPI_F32)>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MFV_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        S::TOTAL));
+    attr_set = true;
+  }
+  GemmParams p = {};
+  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.G = (int)a->G;
+  p.M1 = (int)b->M; p.N1 = (int)b->N;
+  p.rows_cta = BM;
+  p.tiles_n = p.N / BN; p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
+  p.tiles_n1 = p.N1 / BN; p.tiles_m1 = (p.M1 + BM * CG - 1) / (BM * CG);
+  p.kb_total = (p.K + BK - 1) / BK;
+  int splits = a->splits > 0 ? a->splits : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.a_mn = a->a_mn_major; p.b_mn = a->b_mn_major; p.epi = MFV_EPI_ATOMIC_F32;
+  p.a_f16 = a->dtype_flags & 1; p.b_f16 = (a->dtype_flags >> 1) & 1; p.out_f16 = 0;
+  if (p.a_f16 != p.b_f16) return MFV_ERR_ARG;
+  p.bias_gstride = a->bias_gstride;
+  p.row_sum = a->row_sum; p.row_sum1 = b->row_sum;
+  p.tiles0 = p.tiles_m * p.tiles_n * p.splits * p.G;
+  CUtensorMap tmA, tmB, tmC, tmA1, tmB1, tmC1;
+  int rc = encode_operand_map(&tmA, a->A, a->a_mn_major, a->M, a->K, a->lda, a->a_gstride, p.G, BM, p.a_f16);
+  if (rc) return rc;
+  rc = encode_operand_map(&tmB, a->B, a->b_mn_major, a->N, a->K, a->ldb, a->b_gstride, p.G, 64, p.b_f16);
+  if (rc) return rc;
+  rc = encode_tile_map(&tmC, a->C, 4, 0, a->M, a->N, a->ldc, a->c_gstride, p.G);
+  if (rc) return rc;
+  rc = encode_operand_map(&tmA1, b->A, b->a_mn_major, b->M, b->K, b->lda, b->a_gstride, p.G, BM, p.a_f16);
+  if (rc) return rc;
+  rc = encode_operand_map(&tmB1, b->B, b->b_mn_major, b->N, b->K, b->ldb, b->b_gstride, p.G, 64, p.b_f16);
+  if (rc) return rc;
+  rc = encode_tile_map(&tmC1, b->C, 4, 0, b->M, b->N, b->ldc, b->c_gstride, p.G);
+  if (rc) return rc;
+  const int total = p.tiles0 + p.tiles_m1 * p.tiles_n1 * p.splits * p.G;
+  int clusters = num_sms() / CG;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, MFV_EPI_F32>, tmA, tmB, tmC, tmA1, tmB1, tmC1, p));
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
 }  // namespace mfv
 
 extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
@@ -874,4 +959,21 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
     case 256: return launch_gemm<256, 1>(a, s);
     default: return MFV_ERR_ARG;
   }
+}
+
+// Two split-K weight-gradient GEMMs (MFV_EPI_ATOMIC_F32) in ONE launch: the four weight gradients of a block are two
+// launches instead of four, each long enough to fill the machine without slicing the reduction into short pieces.  Both
+// problems must have N % 384 == 0 (256 x 384 pair tiles), M > 128, the same K, G, splits, operand majorness and formats,
+// and the same bias_gstride for their row_sum outputs.
+extern "C" int mfv_gemm_wgrad_pair(const mfv_gemm_args* a, const mfv_gemm_args* b, void* stream) {
+  using namespace mfv;
+  if (!a || !b) return MFV_ERR_ARG;
+  for (const mfv_gemm_args* x : {a, b}) {
+    if (x->M <= 128 || x->N <= 0 || x->N % 384 != 0 || x->K <= 0 || x->G <= 0) return MFV_ERR_SHAPE;
+    if (x->epilogue != MFV_EPI_ATOMIC_F32 || x->ldc % 8 != 0) return MFV_ERR_ARG;
+  }
+  if (a->K != b->K || a->G != b->G || a->splits != b->splits || a->a_mn_major != b->a_mn_major ||
+      a->b_mn_major != b->b_mn_major || (a->dtype_flags & 3) != (b->dtype_flags & 3) || a->bias_gstride != b->bias_gstride)
+    return MFV_ERR_ARG;
+  return launch_wgrad_pair(a, b, reinterpret_cast<cudaStream_t>(stream));
 }

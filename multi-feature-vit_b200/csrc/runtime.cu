@@ -38,7 +38,19 @@ static int g_num_sms = 0;
 static int g_device = -1;
 
 PFN_encodeTiled get_encode_tiled() { return g_encode; }
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+// SMs the persistent kernels size their grids for.  "reserve_sms" (MFVIT_RESERVE_SMS, set by the data-parallel trainer)
+// leaves that many SMs free for the NCCL all-reduce kernels that run beside the backward: a one-CTA-per-SM GEMM grid
+// otherwise makes every collective CTA wait for a tile to finish.
+static int g_opt_reserve = -1;
+int num_sms() {
+  if (g_opt_reserve < 0) {
+    const char* e = getenv("MFVIT_RESERVE_SMS");
+    g_opt_reserve = e ? atoi(e) : 0;
+  }
+  const int n = g_num_sms > 0 ? g_num_sms : 148;
+  const int r = g_opt_reserve < 0 ? 0 : (g_opt_reserve > n / 2 ? n / 2 : g_opt_reserve);
+  return (n - r) & ~1;  // even: CTA pairs
+}
 // Runtime switches (defaults from the environment, overridable through mfv_set_option): -1 = not read yet
 static int g_opt_pdl = -1, g_opt_side = -1, g_opt_legacy_attn = -1, g_opt_rows96 = -1, g_opt_fuse_ln = -1, g_opt_dx32 = -1, g_opt_patch_tma = -1;
 static int env_flag(const char* name, int dflt, char off_char) {
@@ -113,6 +125,7 @@ extern "C" int mfv_set_option(const char* key, int value) {
   else if (k == "fuse_ln") g_opt_fuse_ln = value ? 1 : 0;
   else if (k == "dx32") g_opt_dx32 = value ? 1 : 0;
   else if (k == "patch_tma") g_opt_patch_tma = value ? 1 : 0;
+  else if (k == "reserve_sms") g_opt_reserve = value < 0 ? 0 : value;
   else return MFV_ERR_ARG;
   return MFV_OK;
 }

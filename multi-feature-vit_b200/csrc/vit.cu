@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "mfvit_internal.h"
 
+#include <stdlib.h>
+
 namespace mfv {
 
 struct PlanView {
@@ -158,6 +160,61 @@ static int linear_wgrad(const PlanView& v, const void* dY, long long N, const vo
     rc = mfv_colsum_bf16(dY, v.gr(b_off), v.p->G, rows, N, v.p->P, st);
   }
   return rc;
+}
+
+// Two weight gradients that become ready together (fc2 + fc1 after the fc2 dgrad, proj + qkv after the attention backward)
+// as ONE launch of 256 x 384 pair tiles (mfv_gemm_wgrad_pair): half the launches, and enough tiles per launch that the
+// split count - chosen here so the units fill whole waves of the 74 CTA pairs - leaves long reduction slices.
+// Measured at 32 pairs: the weight-gradient class time drops from 1.24 to 0.93 ms per step, but the STEP gets slower
+// (4.577 -> 4.631 ms): the four short kernels slip into the SMs the 100-CTA dgrad kernels leave idle, the two long ones
+// hold all 148 SMs and push the critical chain back.  Opt-in therefore (MFVIT_WGRAD_PAIR=1).
+struct WgradSpec { const void* dY; long long N; const void* X; long long K; long long w_off, b_off; };
+static bool wgrad_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFVIT_WGRAD_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static int linear_wgrad_pair(const PlanView& v, const WgradSpec& s0, const WgradSpec& s1, long long rows, cudaStream_t st) {
+  const bool ok = wgrad_pair_enabled() && s0.K % 384 == 0 && s1.K % 384 == 0 && s0.N > 128 && s1.N > 128;
+  if (!ok) {
+    int rc = linear_wgrad(v, s0.dY, s0.N, s0.X, s0.K, rows, s0.w_off, s0.b_off, st);
+    if (rc) return rc;
+    return linear_wgrad(v, s1.dY, s1.N, s1.X, s1.K, rows, s1.w_off, s1.b_off, st);
+  }
+  mfv_gemm_args a[2] = {};
+  long long tiles = 0;
+  const WgradSpec* sp[2] = {&s0, &s1};
+  for (int i = 0; i < 2; ++i) {
+    const WgradSpec& s = *sp[i];
+    a[i].A = s.dY; a[i].B = s.X; a[i].C = v.gr(s.w_off);
+    a[i].M = s.N; a[i].N = s.K; a[i].K = rows; a[i].G = v.p->G;
+    a[i].lda = s.N; a[i].ldb = s.K; a[i].ldc = s.K;
+    a[i].a_gstride = rows * s.N; a[i].b_gstride = rows * s.K; a[i].c_gstride = v.p->P;
+    a[i].a_mn_major = 1; a[i].b_mn_major = 1;
+    a[i].epilogue = MFV_EPI_ATOMIC_F32;
+    a[i].bias_gstride = v.p->P;
+    if (s.b_off >= 0) a[i].row_sum = v.gr(s.b_off);  // bias gradient folded into the tile (one N=16 UMMA against ones)
+    tiles += ((s.N + 255) / 256) * (s.K / 384) * v.p->G;
+  }
+  const long long kb = (rows + 63) / 64;
+  const long long pairs = num_sms() / 2;
+  long long splits = 1;
+  double best = -1.0;
+  for (long long spl = 1; spl <= 32 && spl <= kb; ++spl) {
+    if (kb / spl < 8 && spl > 1) break;
+    const long long per = (kb + spl - 1) / spl;
+    const long long eff_sp = (kb + per - 1) / per;
+    const long long units = tiles * eff_sp;
+    const long long waves = (units + pairs - 1) / pairs;
+    const double eff = (double)units / (double)(waves * pairs) - 0.002 * (double)spl;
+    if (waves <= 3 && eff > best) { best = eff; splits = spl; }
+  }
+  a[0].splits = a[1].splits = (int)splits;
+  ProfScope ps(PROF_GEMM_WGRAD, st);
+  return mfv_gemm_wgrad_pair(&a[0], &a[1], st);
 }
 
 #define RC(expr)            \
@@ -336,8 +393,11 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     RC(linear_dgrad(v, p->dx16[cur], C, v.boff(l, p->r_fc2_w), Hd, MFV_EPI_DGELU, p->dhid,
                     p->fwd_f16 ? v.g_b(l) : nullptr, v.u(l), Hd, st));
     RC(fork(0));
-    RC(linear_wgrad(v, p->dx16[cur], C, v.g_b(l), Hd, M, v.boff(l, p->r_fc2_w), -1, sw));  // bias: LN backward above
-    RC(linear_wgrad(v, p->dhid, Hd, v.xn_b(2 * l + 1), C, M, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b), sw));
+    {  // fc2 (bias: LN backward above) + fc1 weight gradients, one launch
+      const WgradSpec w_fc2 = {p->dx16[cur], C, v.g_b(l), Hd, v.boff(l, p->r_fc2_w), -1};
+      const WgradSpec w_fc1 = {p->dhid, Hd, v.xn_b(2 * l + 1), C, v.boff(l, p->r_fc1_w), v.boff(l, p->r_fc1_b)};
+      RC(linear_wgrad_pair(v, w_fc2, w_fc1, M, sw));
+    }
     RC(side_done(0));
     RC(linear_dgrad(v, p->dhid, Hd, v.boff(l, p->r_fc1_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RC(join(1));  // the previous block's attention-half weight gradients still read dx16[cur ^ 1]
@@ -350,8 +410,11 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
     RCP(PROF_ATTN_BWD, mfv_attn_bwd_ws(v.qkv(l), p->fwd_f16, v.ao_b(l), p->d_o, v.lse(l), p->delta, p->dqkv, p->attn_ws,
                                        G * p->B, p->S, p->H, D, scale, st));
     RC(fork(1));
-    RC(linear_wgrad(v, p->dx16[cur], C, v.ao_b(l), C, M, v.boff(l, p->r_proj_w), -1, sw));  // bias: LN2 backward above
-    RC(linear_wgrad(v, p->dqkv, 3 * C, v.xn_b(2 * l), C, M, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b), sw));
+    {  // proj (bias: LN2 backward above) + qkv weight gradients, one launch
+      const WgradSpec w_proj = {p->dx16[cur], C, v.ao_b(l), C, v.boff(l, p->r_proj_w), -1};
+      const WgradSpec w_qkv = {p->dqkv, 3 * C, v.xn_b(2 * l), C, v.boff(l, p->r_qkv_w), v.boff(l, p->r_qkv_b)};
+      RC(linear_wgrad_pair(v, w_proj, w_qkv, M, sw));
+    }
     RC(side_done(1));
     RC(linear_dgrad(v, p->dqkv, 3 * C, v.boff(l, p->r_qkv_w), C, MFV_EPI_BF16, p->dxn, nullptr, nullptr, 0, st));
     RC(join(0));  // fc2's weight gradient of this block reads dx16[cur ^ 1], which the LayerNorm backward below rewrites

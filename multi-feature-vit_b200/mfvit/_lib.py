@@ -80,6 +80,7 @@ SIGNATURES = {
     "mfv_prof_label_name": (C.c_char_p, [C.c_int]),
     "mfv_prof_read": (C.c_int, [c_vp, c_vp, C.c_int]),
     "mfv_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
+    "mfv_gemm_wgrad_pair": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(GemmArgs), c_vp]),
     "mfv_layernorm_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),
     "mfv_layernorm_bwd": (C.c_int, [c_vp] * 13 + [i64, i64, i64, i64, c_vp]),
     "mfv_attn_fwd": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, i64, i64, i64, i64, f32, c_vp]),

@@ -104,6 +104,27 @@ def linear_wgrad(dy16, x16, dw, splits=8, block_n=0, cta_group=0, db=None):
                 cta_group=cta_group, row_sum=db, bias_gstride=N if db is not None else 0)
 
 
+def linear_wgrad_pair(dy0, x0, dw0, db0, dy1, x1, dw1, db1, splits=4):
+    """Two weight gradients in one launch (mfv_gemm_wgrad_pair): dw_i [G,N_i,K_i] += dy_i^T x_i, db_i += colsum(dy_i)."""
+    lib = _lib_for(dy0)
+    args = []
+    for dy, x, dw, db in ((dy0, x0, dw0, db0), (dy1, x1, dw1, db1)):
+        G, M, N = dy.shape
+        K = x.shape[2]
+        a = GemmArgs()
+        a.A, a.B, a.C = dy.data_ptr(), x.data_ptr(), dw.data_ptr()
+        a.M, a.N, a.K, a.G = N, K, M, G
+        a.lda, a.ldb, a.ldc = N, K, K
+        a.a_gstride, a.b_gstride, a.c_gstride = M * N, M * K, N * K
+        a.a_mn_major, a.b_mn_major, a.epilogue, a.splits = 1, 1, EPI_ATOMIC_F32, splits
+        a.bias_gstride = N if db is not None else 0
+        a.row_sum = db.data_ptr() if db is not None else None
+        args.append(a)
+    if args[0].bias_gstride != args[1].bias_gstride:  # one stride for both bias outputs: the caller packs them alike
+        raise MfvError("linear_wgrad_pair: both bias gradients must use the same group stride")
+    check(lib.mfv_gemm_wgrad_pair(C.byref(args[0]), C.byref(args[1]), _stream()), "mfv_gemm_wgrad_pair")
+
+
 def layernorm_fwd(x, gamma, beta, eps, want_bf16=True, want_f32=False, f16=False, bf16_copy=False):
     G, rows, Cd = x.shape
     lib = _lib_for(x)

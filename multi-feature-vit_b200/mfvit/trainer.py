@@ -407,7 +407,11 @@ class MFViTCATrainer:
         self._g_inputs = [torch.empty_like(t) for t in (img_cxr, img_enh, target)]
         for dst, src in zip(self._g_inputs, (img_cxr, img_enh, target)):
             dst.copy_(src)
-        side = torch.cuda.Stream(device=device)
+        # (Capturing on a high-priority stream - so that pending CTAs of the critical chain are placed before those of the
+        # weight-gradient side stream - was measured and is worse: 4.85 against 4.58 ms per step; the starved side stream
+        # piles its GEMMs up behind the backward.  MFVIT_MAIN_PRIORITY=1 reproduces it.)
+        prio = -1 if os.environ.get("MFVIT_MAIN_PRIORITY", "0") == "1" else 0
+        side = torch.cuda.Stream(device=device, priority=prio)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):  # allocations, cudaFuncSetAttribute, side-stream / event creation happen here
@@ -416,7 +420,7 @@ class MFViTCATrainer:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = lib.mfv_launch_count()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             self._g_loss = self._step_eager(*self._g_inputs)
         self.graph_launches = int(lib.mfv_launch_count() - n0)
         # undo the warm-up steps (capture itself executes nothing); the 16-bit GEMM shadows are rebuilt from the master

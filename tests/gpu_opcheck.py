@@ -107,6 +107,53 @@ def t_gemm_resid_ln():
         report("gemm resid+LN y f32 " + tag, y32, yr, 2e-5, rel=True)
 
 
+def t_wgrad_pair():
+    """mfv_gemm_wgrad_pair: two split-K weight gradients (+ folded bias gradients) as one grid, vs fp32 einsum."""
+    for M, splits in ((6304, 5), (197 * 3, 2), (1000, 1)):
+        torch.manual_seed(9)
+        G = 2
+        dy0 = bf(torch.randn(G, M, 384, device=dev)); x0 = bf(torch.randn(G, M, 1536, device=dev))      # fc2-like: dW [384][1536]
+        dy1 = bf(torch.randn(G, M, 1536, device=dev)); x1 = bf(torch.randn(G, M, 384, device=dev))      # fc1-like: dW [1536][384]
+        dw0 = torch.zeros(G, 384, 1536, device=dev); dw1 = torch.zeros(G, 1536, 384, device=dev)
+        # both bias gradients live at one group stride inside a common buffer, as in the engine's flat gradient buffer
+        dbuf = torch.zeros(G, 4096, device=dev)
+        db1 = dbuf[:, :1536]
+        ops.linear_wgrad_pair(dy0, x0, dw0, None, dy1, x1, dw1, None, splits=splits)
+        report("wgrad pair dW0 M%d s%d" % (M, splits), dw0, torch.einsum("gmn,gmk->gnk", dy0.float(), x0.float()), 2e-3, rel=True)
+        report("wgrad pair dW1 M%d s%d" % (M, splits), dw1, torch.einsum("gmn,gmk->gnk", dy1.float(), x1.float()), 2e-3, rel=True)
+    # with the bias gradient of problem 1 folded in (row sums of dY through the ones-UMMA): strided view into a flat buffer
+    from mfvit._lib import GemmArgs  # noqa: F401
+    import ctypes as C
+    M, G = 1379, 2
+    dy0 = bf(torch.randn(G, M, 384, device=dev)); x0 = bf(torch.randn(G, M, 384, device=dev))          # proj-like
+    dy1 = bf(torch.randn(G, M, 1152, device=dev)); x1 = bf(torch.randn(G, M, 384, device=dev))         # qkv-like
+    flat = torch.zeros(G, 1152 * 384 + 384 * 384 + 1152 + 8, device=dev)
+    P = flat.shape[1]
+    o_w0, o_w1, o_b1 = 0, 384 * 384, 384 * 384 + 1152 * 384
+
+    def args(dy, x, w_off, b_off):
+        Gg, Mm, N = dy.shape
+        K = x.shape[2]
+        a = GemmArgs()
+        a.A, a.B, a.C = dy.data_ptr(), x.data_ptr(), flat.data_ptr() + 4 * w_off
+        a.M, a.N, a.K, a.G = N, K, Mm, Gg
+        a.lda, a.ldb, a.ldc = N, K, K
+        a.a_gstride, a.b_gstride, a.c_gstride = Mm * N, Mm * K, P
+        a.a_mn_major, a.b_mn_major, a.epilogue, a.splits = 1, 1, 5, 4
+        a.bias_gstride = P
+        a.row_sum = flat.data_ptr() + 4 * b_off if b_off is not None else None
+        return a
+    from mfvit import _lib
+    a0, a1 = args(dy0, x0, o_w0, None), args(dy1, x1, o_w1, o_b1)
+    _lib.check(_lib.init(0).mfv_gemm_wgrad_pair(C.byref(a0), C.byref(a1), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "mfv_gemm_wgrad_pair")
+    report("wgrad pair (flat buffer) dW proj", flat[:, o_w0:o_w0 + 384 * 384].reshape(G, 384, 384),
+           torch.einsum("gmn,gmk->gnk", dy0.float(), x0.float()), 2e-3, rel=True)
+    report("wgrad pair (flat buffer) dW qkv", flat[:, o_w1:o_w1 + 1152 * 384].reshape(G, 1152, 384),
+           torch.einsum("gmn,gmk->gnk", dy1.float(), x1.float()), 2e-3, rel=True)
+    report("wgrad pair (flat buffer) db qkv (folded)", flat[:, o_b1:o_b1 + 1152], dy1.float().sum(1), 2e-3, rel=True)
+
+
 def t_patch_embed_tma():
     """im2col-free patch embedding (5-D TMA tiles from NCHW fp32, 16-bit conversion in shared memory, tcgen05) vs Conv2d +
     flatten + cls + pos on the same 16-bit-rounded operands; and the raw TMA box layout the converter warps rely on."""
@@ -467,6 +514,7 @@ def main():
     run("gemm rows96", t_gemm_rows96, flt)
     run("gemm resid+LN", t_gemm_resid_ln, flt)
     run("patch embed TMA", t_patch_embed_tma, flt)
+    run("wgrad pair", t_wgrad_pair, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
     run("gemm wgrad", t_gemm_wgrad(2, 6304, 1152, 384, 8), flt)
     run("gemm wgrad fc", t_gemm_wgrad(2, 1970, 384, 1536, 5), flt)
