@@ -465,11 +465,20 @@ extern "C" int mfv_attn_fwd(const void* qkv, int qkv_is_f16, void* o, int o_is_f
   if (D == 64 && (o_is_f16 != 0) == (qkv_is_f16 != 0) && !legacy_attention()) {
     // The flash-style kernel (64-key blocks, S double-buffered in TMEM, one TMEM read per score) is also the faster
     // one at S = 197 (23.5 vs 28.7 us in fp16 mode); MFVIT_ATTN_FLASH=0 selects the single-shot kernel for S <= 256.
-    static int flash_all = -1;
+    static int flash_all = -1, p2 = -1;
     if (flash_all < 0) {
       const char* e = getenv("MFVIT_ATTN_FLASH");
       flash_all = (e && e[0] == '0') ? 0 : 1;
+      const char* e2 = getenv("MFVIT_ATTN_P2");
+      p2 = (e2 && e2[0] == '1') ? 1 : 0;
     }
+    // MFVIT_ATTN_P2=1: the persistent single-shot kernel for S <= 256 (both query tiles of a head in flight on one SM,
+    // K / V read once per head).  Correct (tests/gpu_opcheck.py attn) but not faster: 22.1 us (bf16) / 29.3 us (fp16 +
+    // bf16 copy) against 22.4 / 23.4 us for the flash-style kernel at 64 images x 6 heads - its two passes read every
+    // score out of TMEM twice, and TMEM reads (64 B/clk/SM) cost as much as the exponentials (profiles/r02_summary.md).
+    if (S <= 256 && p2)
+      return attn_fwd_tc_p2(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
+                            reinterpret_cast<cudaStream_t>(stream));
     if (S <= 256 && !flash_all)
       return attn_fwd_tc(qkv, qkv_is_f16, o, o_is_f16, o_bf16_copy, lse, NB, S, H, scale,
                          reinterpret_cast<cudaStream_t>(stream));

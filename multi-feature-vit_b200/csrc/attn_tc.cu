@@ -1185,6 +1185,286 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+// =====================================================================================================================
+// Forward for S <= 256, persistent: one CTA per SM walks over (image, head) items; the two 128-query tiles of an item
+// are softmaxed by two independent warpgroups (warps 0..3 / 4..7), each with its own 256-column TMEM slot, so the Q K^T /
+// P V MMAs of one tile run under the exp of the other.  K, V and both Q tiles of the NEXT item are prefetched by TMA into
+// the second smem buffer while this one is being worked on; K / V are read once per head (the flash-style kernel reads
+// them once per query tile).  The MMA warp is an event loop over the two slots (whichever tile has its operands ready
+// is issued), the softmax is the single-shot two-pass form (scores never leave TMEM; P packed over S; O inside the spent
+// S columns).  Warps whose 32 query rows all lie past S (the last quarter of the second tile at S = 197) skip the math.
+constexpr int FP_THREADS = 320;     // warps 0..3: tile 0, 4..7: tile 1, 8: MMA issue, 9: TMA producer
+constexpr uint32_t FP_SLOT = 256;   // TMEM columns per tile slot
+constexpr uint32_t FP_O_COL = 128;
+
+template <bool F16>
+__global__ void __launch_bounds__(FP_THREADS, 1)
+attn_fwd_tc_p2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+                      float* __restrict__ lse, int S, int H, int NK, int items, float scale_log2, int has_o2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int KV = NK * 128;                 // bytes of K (or V) of a head: [NK][64] 16-bit, 128B-swizzled
+  const int BUF = 32768 + 2 * KV;          // Q tile 0 | Q tile 1 | K | V
+  uint8_t* sO2 = smem + 2 * BUF;           // 8 warps x 4 KB staging of the optional bf16 copy of O
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO2 + 32768);
+  uint64_t* qk_full = bars;                // [2] Q (both tiles) + K landed
+  uint64_t* v_full = bars + 2;             // [2]
+  uint64_t* buf_free = bars + 4;           // [2] every softmax warp is done with the buffer (O staged out of the Q
+                                           //     tiles included) and both tiles' MMAs have retired
+  uint64_t* s_full = bars + 6;             // [2 slots]
+  uint64_t* p_full = bars + 8;             // [2] 4 warp arrivals
+  uint64_t* o_full = bars + 10;            // [2]
+  uint64_t* o_free = bars + 12;            // [2] 4 warp arrivals: O read out, the slot may take the next S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mt = (S + 127) >> 7;
+  const int n_local = items > (int)blockIdx.x ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmO2);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qk_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&buf_free[i], (uint32_t)(5 * n_mt));
+        mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int k = 0; k < n_local; ++k) {
+        const int buf = k & 1;
+        const int bh = (int)blockIdx.x + k * (int)gridDim.x;
+        const int b = bh / H, h = bh % H;
+        if (k >= 2) mbar_wait(&buf_free[buf], (uint32_t)(((k >> 1) - 1) & 1));
+        uint8_t* base = smem + buf * BUF;
+        mbar_arrive_expect_tx(&qk_full[buf], (uint32_t)(n_mt * 16384 + KV));
+        for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(base + mt * 16384, &tmQ, &qk_full[buf], h * 64, mt * 128, b);
+        tma_load_3d(base + 32768, &tmKV, &qk_full[buf], (H + h) * 64, 0, b);
+        mbar_arrive_expect_tx(&v_full[buf], (uint32_t)KV);
+        tma_load_3d(base + 32768 + KV, &tmKV, &v_full[buf], (2 * H + h) * 64, 0, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------------------------------ MMA issue: event loop
+    if (lane == 0) {
+      const uint32_t fmt = F16 ? 0u : 1u;
+      const uint32_t idesc_s = make_idesc2(fmt, fmt, 128, (uint32_t)NK, 0, 0);
+      const uint32_t idesc_o = make_idesc2(fmt, fmt, 128, 64, 0, 1);
+      int ks[2] = {0, n_mt > 1 ? 0 : n_local};
+      int st[2] = {0, 0};
+      const long long t_start = clock64();
+      while (ks[0] < n_local || ks[1] < n_local) {
+        if (clock64() - t_start > 4000000000LL) {  // a protocol bug must trap instead of hanging the GPU box
+          printf("mfvit: attention MMA loop timeout (block %d)\n", blockIdx.x);
+          __trap();
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int k = ks[t];
+          if (k >= n_local) continue;
+          const int buf = k & 1;
+          const uint32_t use_ph = (uint32_t)((k >> 1) & 1);
+          uint8_t* base = smem + buf * BUF;
+          const uint32_t slot = tmem_base + (uint32_t)t * FP_SLOT;
+          if (st[t] == 0) {
+            if (!mbar_test_wait(&qk_full[buf], use_ph)) continue;
+            if (k > 0 && !mbar_test_wait(&o_free[t], (uint32_t)((k - 1) & 1))) continue;
+            tc_fence_after();
+            const uint32_t qa = smem_u32(base + t * 16384), ka = smem_u32(base + 32768);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(slot, make_smem_desc_sw128(qa + kk * 32, 0u, 1024u), make_smem_desc_sw128(ka + kk * 32, 0u, 1024u),
+                        idesc_s, kk > 0 ? 1u : 0u);
+            umma_commit(&s_full[t]);
+            st[t] = 1;
+          } else {
+            if (!mbar_test_wait(&p_full[t], (uint32_t)(k & 1))) continue;
+            if (!mbar_test_wait(&v_full[buf], use_ph)) continue;
+            tc_fence_after();
+            const uint32_t va = smem_u32(base + 32768 + KV);
+            for (int kk = 0; kk < NK / 16; ++kk)
+              umma_f16_ts(slot + FP_O_COL, slot + (uint32_t)(kk * 8), make_smem_desc_sw128(va + kk * 2048, 8192u, 1024u),
+                          idesc_o, kk > 0 ? 1u : 0u);
+            umma_commit(&o_full[t]);
+            umma_commit(&buf_free[buf]);
+            st[t] = 0;
+            ks[t] = k + 1;
+          }
+        }
+      }
+    }
+  } else if ((warp >> 2) < n_mt) {
+    // ------------------------------------------------------------------------------------------ softmax + epilogue
+    const int t = warp >> 2, w = warp & 3;
+    const uint32_t trow = tmem_base + (uint32_t)t * FP_SLOT + ((uint32_t)(w * 32) << 16);
+    const bool skip = t * 128 + w * 32 >= S;  // warp-uniform: no valid query row in this warp's quarter
+    uint8_t* st2 = sO2 + warp * 4096;
+    const int nch = (NK + 31) >> 5;
+    auto ld_chunk = [&](int c, uint32_t (&v)[32]) {
+      if (c * 32 + 32 <= NK) tmem_ld32(trow + (uint32_t)(c * 32), v); else tmem_ld16(trow + (uint32_t)(c * 32), v);
+    };
+    for (int k = 0; k < n_local; ++k) {
+      const int buf = k & 1;
+      const uint32_t ph = (uint32_t)(k & 1);
+      const int bh = (int)blockIdx.x + k * (int)gridDim.x;
+      const int b = bh / H, h = bh % H;
+      mbar_wait(&s_full[t], ph);
+      tc_fence_after();
+      if (k > 0) {
+        // the stores of the previous item have long finished reading their staging (its Q tiles, sO2): hand that buffer
+        // back to the producer
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&buf_free[buf ^ 1]);
+        }
+        __syncwarp();
+      }
+      float inv = 0.f;
+      if (!skip) {
+        // ---- pass 1: row maximum (columns >= S are padding)
+        float mx = -INFINITY;
+        {
+          uint32_t va[32], vb[32];
+          ld_chunk(0, va);
+          auto red = [&](int c, const uint32_t (&v)[32]) {
+            const int c0 = c * 32;
+            if (c0 + 32 <= S) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else {
+              const bool full = c0 + 32 <= NK;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < S && (full || j < 16)) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+          };
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) ld_chunk(c + 1, vb);
+            red(c, va);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) ld_chunk(c + 2, va);
+              red(c + 1, vb);
+            }
+          }
+        }
+        const float mc = mx * scale_log2;
+        // ---- pass 2: p = exp2(s * c - max * c), row sum, packed 16-bit P written back over S
+        float sum = 0.f;
+        {
+          uint32_t va[32], vb[32];
+          ld_chunk(0, va);
+          auto proc = [&](int c, const uint32_t (&v)[32]) {
+            const int c0 = c * 32;
+            const bool full = c0 + 32 <= NK;
+            float pr[32];
+            if (c0 + 32 <= S) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pr[j] = fast_exp2(fmaf(__uint_as_float(v[j]), scale_log2, -mc));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                pr[j] = (c0 + j < S && (full || j < 16)) ? fast_exp2(fmaf(__uint_as_float(v[j]), scale_log2, -mc)) : 0.f;
+            }
+            uint32_t pk[16];
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s4[j & 3] += pr[2 * j] + pr[2 * j + 1];
+              pk[j] = F16 ? pack_f16(pr[2 * j], pr[2 * j + 1]) : pack_bf16(pr[2 * j], pr[2 * j + 1]);
+            }
+            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            if (full) tmem_st16(trow + (uint32_t)(c0 >> 1), pk); else tmem_st8(trow + (uint32_t)(c0 >> 1), pk);
+          };
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) ld_chunk(c + 1, vb);
+            proc(c, va);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) ld_chunk(c + 2, va);
+              proc(c + 1, vb);
+            }
+          }
+        }
+        tmem_st_wait();
+        const int row = t * 128 + w * 32 + lane;
+        if (row < S) lse[(long long)bh * S + row] = (mc + log2f(sum)) * FA_LN2;
+        inv = 1.f / sum;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      // ---- epilogue: O / sum -> 16-bit -> swizzled smem (this tile's spent Q rows) -> TMA store
+      mbar_wait(&o_full[t], ph);
+      tc_fence_after();
+      if (skip) {
+        if (lane == 0) mbar_arrive(&o_free[t]);
+        continue;
+      }
+      float o[64];
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(trow + FP_O_COL, v0);
+        tmem_ld32(trow + FP_O_COL + 32u, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { o[j] = __uint_as_float(v0[j]) * inv; o[32 + j] = __uint_as_float(v1[j]) * inv; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      uint8_t* stg = smem + buf * BUF + t * 16384 + w * 4096;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 wv;
+        if (F16)
+          wv = make_uint4(pack_f16(o[8 * j], o[8 * j + 1]), pack_f16(o[8 * j + 2], o[8 * j + 3]),
+                          pack_f16(o[8 * j + 4], o[8 * j + 5]), pack_f16(o[8 * j + 6], o[8 * j + 7]));
+        else
+          wv = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                          pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = wv;
+      }
+      if (has_o2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(st2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                         pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        fa_tma_store_3d(&tmO, stg, h * 64, t * 128 + w * 32, b);
+        if (has_o2) fa_tma_store_3d(&tmO2, st2, h * 64, t * 128 + w * 32, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int fa_encode(CUtensorMap* map, const void* base, int is_f16, long long inner, long long rows, long long images,
                      int box_rows, int box_cols = 64) {
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)images};
@@ -1246,6 +1526,57 @@ int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_
     }
     MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<false>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, NK, sl2,
                                       has_o2));
+  }
+  MFV_LAUNCH_CHECK();
+  return MFV_OK;
+}
+
+// Host entry for S <= 256: the persistent two-warpgroup kernel (one CTA per SM).
+int attn_fwd_tc_p2(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
+                   long long S, long long H, float scale, cudaStream_t st) {
+  if (o_is_f16 != qkv_is_f16) return MFV_ERR_ARG;
+  const int NK = ((int)S + 15) & ~15;
+  CUtensorMap tmQ, tmKV, tmO, tmO2;
+  int rc;
+  if ((rc = fa_encode(&tmQ, qkv, qkv_is_f16, 3 * H * 64, S, NB, 128))) return rc;
+  if ((rc = fa_encode(&tmKV, qkv, qkv_is_f16, 3 * H * 64, S, NB, NK))) return rc;
+  if ((rc = fa_encode(&tmO, o, o_is_f16, H * 64, S, NB, 32))) return rc;
+  tmO2 = tmO;
+  if (o_bf16_copy && (rc = fa_encode(&tmO2, o_bf16_copy, 0, H * 64, S, NB, 32))) return rc;
+  const size_t smem = 1024 + 2 * (32768 + 2 * (size_t)NK * 128) + 32768 + 256;
+  const long long items = NB * H;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min<long long>(items, num_sms()));
+  cfg.blockDim = dim3(FP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const float sl2 = scale * FA_LOG2E;
+  const int has_o2 = o_bf16_copy != nullptr;
+  if (qkv_is_f16) {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_p2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_p2_kernel<true>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, NK,
+                                      (int)items, sl2, has_o2));
+  } else {
+    static bool set = false;
+    if (!set) {
+      MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_p2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_fwd_tc_p2_kernel<false>, tmQ, tmKV, tmO, tmO2, lse, (int)S, (int)H, NK,
+                                      (int)items, sl2, has_o2));
   }
   MFV_LAUNCH_CHECK();
   return MFV_OK;

@@ -29,6 +29,8 @@ bool legacy_attention();  // MFVIT_ATTN=legacy forces the mma.sync attention ker
 // tcgen05 attention (attn_tc.cu); head_dim 64, S <= 256
 int attn_fwd_tc(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
                 long long S, long long H, float scale, cudaStream_t st);
+int attn_fwd_tc_p2(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
+                long long S, long long H, float scale, cudaStream_t st);
 int attn_fwd_tc_mb(const void* qkv, int qkv_is_f16, void* o, int o_is_f16, void* o_bf16_copy, float* lse, long long NB,
                    long long S, long long H, float scale, cudaStream_t st);  // S > 256
 int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o, const float* lse, void* dqkv,

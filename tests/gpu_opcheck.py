@@ -528,6 +528,13 @@ def main():
     run("attn 577/32 f16", t_attn(1, 577, 12, 32, True), flt)
     run("attn 577/64 f16", t_attn(2, 577, 6, 64, True), flt)
     run("attn 300/64", t_attn(2, 300, 3, 64), flt)
+    # persistent forward: several items per CTA (64 x 6 = 384 items on 148 CTAs), tile-edge token counts
+    run("attn 197/64 f16 NB64", t_attn(64, 197, 6, 64, True), flt)
+    run("attn 197/64 NB50", t_attn(50, 197, 6, 64), flt)
+    run("attn 256/64 f16", t_attn(30, 256, 6, 64, True), flt)
+    run("attn 128/64", t_attn(70, 128, 3, 64), flt)
+    run("attn 129/64 f16", t_attn(70, 129, 3, 64, True), flt)
+    run("attn 17/64", t_attn(200, 17, 2, 64), flt)
     run("fusion", t_fusion, flt)
     run("ema", t_ema, flt)
     run("infonce", t_infonce, flt)
