@@ -55,6 +55,15 @@ struct GemmParams {
   float* ln_rstd;
   float ln_eps;
   int ln_out_f32;
+  // Stream-K (sk_units > 0): the (tile, k-block) space is cut into equal ranges of sk_units k-blocks per CTA pair
+  // instead of whole tiles, so a 50-tile GEMM keeps all 74 pairs busy for 0.68 tile times (and a 100-tile one for 1.35
+  // instead of 2).  Only the FIRST fragment of a pair's range can start inside a tile (k-blocks [x, ..) with x > 0): the
+  // pair dumps that partial accumulator into its workspace slot and raises its counter, before anything else it does.
+  // Only the LAST fragment can be the head of a tile it does not finish (k-blocks [0, y)): the pair owns that tile - it
+  // adds the partials of the pairs behind it that cover the rest of the tile, then runs the normal epilogue.
+  int sk_units;
+  float* sk_ws;        // [pairs * CG][16 warps][BN / 4 * 32] fp32
+  unsigned* sk_flags;  // [pairs * CG][2]: partial written (16 warp arrivals) / partial consumed (16)
 };
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) computes 256 x BN; each CTA stages its own
@@ -124,6 +133,38 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int t) {
   ti.g = t / tm;
   return ti;
 }
+
+// One unit of work of a CTA pair: k-blocks [kb0, kb1) of tile t.  role 0 = the whole reduction range of the tile (or of
+// its split), 1 = stream-K tail (dump the partial), 2 = stream-K head (add the next pair's partial, then the epilogue).
+struct Frag { int t, kb0, kb1, role, contrib; };  // contrib: pairs behind this one that hold the rest of the tile (role 2)
+struct FragCursor {
+  int u, u1, step;
+  __device__ __forceinline__ void init(const GemmParams& p, int cta_id, int num_ctas, int total_tiles) {
+    if (p.sk_units > 0) {
+      u = cta_id * p.sk_units;
+      u1 = min(u + p.sk_units, total_tiles * p.kb_total);
+      step = 0;
+    } else {
+      u = cta_id; u1 = total_tiles; step = num_ctas;
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmParams& p, Frag& f) {
+    if (u >= u1) return false;
+    if (p.sk_units > 0) {
+      f.t = u / p.kb_total;
+      f.kb0 = u - f.t * p.kb_total;
+      f.kb1 = min(p.kb_total, f.kb0 + (u1 - u));
+      f.role = f.kb0 > 0 ? 1 : (f.kb1 < p.kb_total ? 2 : 0);
+      u += f.kb1 - f.kb0;
+      // role 2: this fragment ends at u == u1 (the end of this pair's range); the tile ends at (t + 1) * kb_total
+      f.contrib = f.role == 2 ? ((f.t + 1) * p.kb_total - 1) / p.sk_units - (u1 - 1) / p.sk_units : 0;
+    } else {
+      f.t = u; f.role = 0; f.kb0 = -1; f.kb1 = -1; f.contrib = 0;  // k range from the tile's split index
+      u += step;
+    }
+    return true;
+  }
+};
 
 // EPI is a template parameter (MFV_EPI_ATOMIC_F32 shares the MFV_EPI_F32 instance): the epilogue is the issue-bound
 // part of these kernels, and a specialised instruction stream keeps it small (I-cache) and spill-free.
@@ -197,13 +238,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
         if (CG == 2) tma_load_3d_cg2(dst, map, bar, c0, c1, c2); else tma_load_3d(dst, map, bar, c0, c1, c2);
       };
-      for (int t = cta_id; t < total_tiles; t += num_ctas) {
-        const TileInfo ti = decode_tile(p, t);
+      FragCursor cur;
+      cur.init(p, cta_id, num_ctas, total_tiles);
+      Frag fr;
+      while (cur.next(p, fr)) {
+        const TileInfo ti = decode_tile(p, fr.t);
         const int n_tile = ti.n_tile, split = ti.split, m_tile = ti.m_tile, g = ti.g;
         const CUtensorMap* mapA = ti.prob ? &tmC2 : &tmA;
         const CUtensorMap* mapB = ti.prob ? &tmC3 : &tmB;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int kb0 = fr.kb0 >= 0 ? fr.kb0 : split * p.kb_per_split;
+        const int kb1 = fr.kb0 >= 0 ? fr.kb1 : min(kb0 + p.kb_per_split, p.kb_total);
         const int m0 = (m_tile * CG + (int)rank) * p.rows_cta;       // this CTA's rows of A
         const int n0 = n_tile * BN + (int)rank * (BN / CG);          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -251,12 +295,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
-        const TileInfo ti = decode_tile(p, t);
+      FragCursor cur;
+      cur.init(p, cta_id, num_ctas, total_tiles);
+      Frag fr;
+      for (; cur.next(p, fr); ++it) {
+        const TileInfo ti = decode_tile(p, fr.t);
         const int split = ti.split;
         const bool want_rs = (ti.prob ? p.row_sum1 : p.row_sum) != nullptr;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int kb0 = fr.kb0 >= 0 ? fr.kb0 : split * p.kb_per_split;
+        const int kb1 = fr.kb0 >= 0 ? fr.kb1 : min(kb0 + p.kb_per_split, p.kb_total);
         const int as = it % NACC;
         const uint32_t aphase = (it / NACC) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -338,8 +385,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto pack16 = [&](float a, float b) { return p.out_f16 ? pack_f16(a, b) : pack_bf16(a, b); };
     griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
     int it = 0;
-    for (int t = cta_id; t < total_tiles; t += num_ctas, ++it) {
-      const TileInfo ti = decode_tile(p, t);
+    FragCursor cur;
+    cur.init(p, cta_id, num_ctas, total_tiles);
+    Frag fr;
+    // stream-K workspace of this warp: [slot = pair * CG + rank][16 warps][BN / 4 * 32 fp32], piece i at i * 32 * PW,
+    // lane's PW values contiguous (a warp reads / writes 32 x 64 B or 32 x 128 B in one piece: fully coalesced)
+    constexpr int SK_WARP_FLOATS = BN / 4 * 32;
+    auto sk_slot = [&](int pair) {
+      return p.sk_ws + ((size_t)(pair * CG + (int)rank) * NUM_EPI_WARPS + ew) * SK_WARP_FLOATS;
+    };
+    auto sk_flag = [&](int pair) { return p.sk_flags + (size_t)(pair * CG + (int)rank) * 2; };
+    for (; cur.next(p, fr); ++it) {
+      const TileInfo ti = decode_tile(p, fr.t);
       const int n_tile = ti.n_tile, m_tile = ti.m_tile, g = ti.g;
       const int pM = ti.prob ? p.M1 : p.M, pN = ti.prob ? p.N1 : p.N;
       const CUtensorMap* mapC = ti.prob ? &tmAux : &tmC;   // paired launches only exist for the fp32 reduce-add epilogue
@@ -366,19 +423,79 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_3d(slot_ptr(use0 + (uint32_t)(i * upc)), &tmAux, &abar[i & 1], ncol0 + (h + 4 * i) * PW, row0, g);
       };
       if constexpr (has_aux) {
-        if (lane == 0)
+        if (lane == 0 && fr.role != 1)
           for (int j = 0; j < aux_ahead && j < n_my; ++j) issue_aux(j, (int)EPI_NBUF - 1 - j * upc);
       }
       // pull this warp's bias lines into L1 while the MMAs of the tile are still running
-      if (bias && lane < n_my) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
+      if (bias && lane < n_my && fr.role != 1) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (fr.role == 1) {
+        // ---- stream-K tail: this pair's partial sums of a tile the previous pair finishes.  Dump, raise the counter.
+        if (!(p.dbg_skip_epilogue & 1) && !(p.dbg_skip_epilogue & 8)) {
+          float* ws = sk_slot(cta_id) + lane * PW;
+#pragma unroll 1
+          for (int i = 0; i < n_my; ++i) {
+            const int c = h + 4 * i;
+            uint32_t v[32];
+            if constexpr (!out32) tmem_ld32(trow + (uint32_t)(c * PW), v); else tmem_ld16(trow + (uint32_t)(c * PW), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < PW; k += 4)
+              __stcg(reinterpret_cast<float4*>(ws + i * 32 * PW + k),
+                     make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
+                                 __uint_as_float(v[k + 3])));
+          }
+        }
+        release_accumulator(as);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(sk_flag(cta_id), 1u);
+        continue;
+      }
+      const float* sk_part = nullptr;
+      if (fr.role == 2) {
+        // ---- stream-K head: the rest of this tile was the FIRST thing the pairs behind this one did; their partials are
+        // (almost always) there already.  All 16 warps of a contributing CTA have arrived when its counter reads 16.
+        if (lane == 0) {
+          const long long t0 = clock64();
+          for (int j = 1; j <= fr.contrib; ++j) {
+            unsigned* fl = sk_flag(cta_id + j);
+            while (*reinterpret_cast<volatile unsigned*>(fl) < (unsigned)NUM_EPI_WARPS) {
+              if (clock64() - t0 > 4000000000LL) {
+                printf("mfvit: stream-K partial never arrived (block %d warp %d)\n", blockIdx.x, warp);
+                __trap();
+              }
+            }
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        sk_part = sk_slot(cta_id + 1) + lane * PW;
+      }
+      // every warp of a head fragment counts itself out, whatever path it leaves by; the last one re-arms the slot
+      auto sk_consumed = [&]() {
+        if (fr.role != 2) return;
+        __syncwarp();
+        if (lane == 0) {
+          for (int j = 1; j <= fr.contrib; ++j) {
+            unsigned* fl = sk_flag(cta_id + j);
+            if (atomicAdd(fl + 1, 1u) == (unsigned)NUM_EPI_WARPS - 1u) {
+              fl[1] = 0u;
+              __threadfence();
+              fl[0] = 0u;
+            }
+          }
+        }
+      };
       if (n_my == 0) {
         release_accumulator(as);
+        sk_consumed();
         continue;
       }
       if (p.dbg_skip_epilogue & 1) {  // measurement aid: drain the aux loads already issued, touch nothing else
+        sk_consumed();
         release_accumulator(as);
         if constexpr (has_aux) {
           for (int j = 0; j < aux_ahead && j < n_my; ++j) {
@@ -412,6 +529,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+        }
+        if (sk_part) {  // stream-K head: + the partial sums of the pairs that hold the rest of this tile
+          for (int j = 0; j < ((p.dbg_skip_epilogue & 4) ? 0 : fr.contrib); ++j) {
+            const float* wp = sk_part + (size_t)j * (CG * NUM_EPI_WARPS * SK_WARP_FLOATS) + i * 32 * PW;
+#pragma unroll
+            for (int k = 0; k < PW; k += 4) {
+              const float4 w4 = __ldcg(reinterpret_cast<const float4*>(wp + k));
+              f[k] += w4.x; f[k + 1] += w4.y; f[k + 2] += w4.z; f[k + 3] += w4.w;
+            }
+          }
+          if (i == n_my - 1) sk_consumed();
         }
         if (epi != MFV_EPI_RESID_LN && i == n_my - 1)
           release_accumulator(as);  // last TMEM read of the tile: the MMA warp may reuse the buffer
@@ -746,7 +874,7 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   if (p.a_f16 != p.b_f16) return MFV_ERR_ARG;  // tcgen05 kind::f16 traps on mixed fp16 x bf16 operands
   p.has_c2 = a->C2 != nullptr;
   p.has_c3 = a->C3 != nullptr;
-  p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 3;  // bit0: skip everything, bit1: skip the bulk stores
+  p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 15;  // bit0: skip everything, bit1: skip the bulk stores
   p.bias_gstride = a->bias_gstride;
   p.bias = (const float*)a->bias;
   p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_mean = a->ln_mean; p.ln_rstd = a->ln_rstd;
@@ -805,6 +933,28 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   const int total = p.tiles_m * p.tiles_n * p.splits * p.G;
   int clusters = num_sms() / CG;
   if (total < clusters) clusters = total;
+  // Stream-K: where whole tiles leave pairs idle (fewer tiles than pairs, or a ragged last round), for the epilogues that
+  // write each output element once, for the families MFVIT_STREAMK selects, and only when the reduction is long enough
+  // (>= streamk_min_kb k-blocks per tile) for the shorter mainloop to pay for the partial dump + add.
+  p.sk_units = 0; p.sk_ws = nullptr; p.sk_flags = nullptr;
+  {
+    const int mask = streamk_mask();
+    const bool family = (BN == 384 && (mask & 1) && (EPI == MFV_EPI_BF16 || EPI == MFV_EPI_RESID_F32 || EPI == MFV_EPI_RESID_LN)) ||
+                        (BN == 256 && (mask & 2) && EPI == MFV_EPI_BF16) || (BN == 256 && (mask & 4) && EPI == MFV_EPI_GELU) ||
+                        (BN == 256 && (mask & 8) && EPI == MFV_EPI_DGELU);
+    const int pairs = num_sms() / CG;
+    if (CG == 2 && family && p.splits == 1 && a->epilogue != MFV_EPI_ATOMIC_F32 && total % pairs != 0 &&
+        p.kb_total >= streamk_min_kb() && streamk_workspace()) {
+      const long long units = (long long)total * p.kb_total;
+      const int per = (int)((units + pairs - 1) / pairs);
+      if (per >= 2) {
+        p.sk_units = per;
+        p.sk_ws = streamk_workspace();
+        p.sk_flags = streamk_flags();
+        clusters = (int)((units + per - 1) / per);  // every pair that has a range (<= pairs)
+      }
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
   cfg.blockDim = dim3(GEMM_THREADS);

@@ -14,6 +14,10 @@ bool pdl_enabled();
 bool fuse_ln_enabled();  // MFVIT_FUSE_LN=0: standalone LayerNorm launches instead of the fused proj / fc2 epilogue
 bool dx32_stream_enabled();  // MFVIT_DX32=1: fp32 residual-gradient stream through the LayerNorm backward (default: bf16)
 bool patch_tma_enabled();  // MFVIT_PATCH_TMA=0: patchify -> GEMM -> embed_finish instead of the im2col-free TMA kernel
+int streamk_mask();           // MFVIT_STREAMK bit mask (runtime.cu)
+int streamk_min_kb();         // MFVIT_STREAMK_MINKB: shortest reduction (64-wide k-blocks per tile) stream-K is used for
+float* streamk_workspace();   // partial-accumulator slots of the stream-K GEMMs (nullptr before mfv_init)
+unsigned* streamk_flags();
 int rows96_mode();  // MFVIT_ROWS96: 96 rows per CTA in the 384-wide pair tiles: 1 = forward residual GEMMs, 2 = + bf16 dgrads
 // Side stream of mfv_vit_backward: weight-gradient GEMMs and bias column sums are off the critical path (nothing in
 // the backward consumes them), so they run beside the dgrad / attention / LayerNorm chain and fill the SMs those

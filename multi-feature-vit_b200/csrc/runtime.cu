@@ -105,6 +105,43 @@ bool pdl_enabled() {
   if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
   return g_opt_pdl == 1;
 }
+// Stream-K (gemm.cu): bit mask of the GEMM families whose tile lists are cut into equal k-block ranges per CTA pair.
+// 1 = 384-wide pair tiles (proj / fc2 forward, every dgrad), 2 = 256-wide bf16 (qkv), 4 = GELU (fc1), 8 = GELU' (fc2 dgrad)
+// Default 0.  Measured (profiles/r02_summary.md, fc2-shaped bf16 GEMM, graph-timed): the mainloop is bound by operand
+// bytes out of L2 (~6-7 TB/s whatever the number of busy pairs), so spreading 50 tiles over 74 pairs does not shorten it
+// (17.5 -> 17.3 us) and 100 tiles only by 15 % (30.9 -> 26.3 us), while the partial dump + add through L2 costs 10 + 23 us
+// as written (20.2 -> 52.9 us in total).  Step: 4.70 ms off, 5.80 ms with mask 1.
+static int g_opt_streamk = -1;
+int streamk_mask() {
+  if (g_opt_streamk < 0) {
+    const char* e = getenv("MFVIT_STREAMK");
+    g_opt_streamk = e ? atoi(e) : 0;
+  }
+  return g_opt_streamk;
+}
+static int g_opt_streamk_min_kb = -1;
+int streamk_min_kb() {
+  if (g_opt_streamk_min_kb < 0) {
+    const char* e = getenv("MFVIT_STREAMK_MINKB");
+    g_opt_streamk_min_kb = e ? atoi(e) : 12;
+  }
+  return g_opt_streamk_min_kb;
+}
+// Partial-accumulator workspace of the stream-K GEMMs: one slot per CTA (fp32 [16 warps][BN / 4 x 32 values], BN <= 384)
+// + two counters per CTA.  Allocated at mfv_init (never inside a stream capture), zeroed once; the kernels leave the
+// counters at zero.
+static float* g_sk_ws = nullptr;
+static unsigned* g_sk_flags = nullptr;
+float* streamk_workspace() { return g_sk_ws; }
+unsigned* streamk_flags() { return g_sk_flags; }
+static int streamk_alloc(int sms) {
+  if (g_sk_ws) return MFV_OK;
+  const size_t per_cta = (size_t)16 * (384 / 4 * 32) * sizeof(float);
+  MFV_CUDA_CHECK(cudaMalloc(&g_sk_ws, per_cta * (size_t)sms));
+  MFV_CUDA_CHECK(cudaMalloc(&g_sk_flags, sizeof(unsigned) * 2 * (size_t)sms));
+  MFV_CUDA_CHECK(cudaMemset(g_sk_flags, 0, sizeof(unsigned) * 2 * (size_t)sms));
+  return MFV_OK;
+}
 }  // namespace mfv
 
 // Source location and expression of the last CUDA runtime failure seen by this thread ("" if none).
@@ -126,6 +163,8 @@ extern "C" int mfv_set_option(const char* key, int value) {
   else if (k == "dx32") g_opt_dx32 = value ? 1 : 0;
   else if (k == "patch_tma") g_opt_patch_tma = value ? 1 : 0;
   else if (k == "reserve_sms") g_opt_reserve = value < 0 ? 0 : value;
+  else if (k == "streamk") g_opt_streamk = value < 0 ? 0 : value;
+  else if (k == "streamk_min_kb") g_opt_streamk_min_kb = value < 1 ? 1 : value;
   else return MFV_ERR_ARG;
   return MFV_OK;
 }
@@ -177,6 +216,10 @@ extern "C" int mfv_init(int device) {
   MFV_CUDA_CHECK(cudaSetDevice(device));
   g_num_sms = prop.multiProcessorCount;
   g_device = device;
+  {
+    const int rc = streamk_alloc(g_num_sms);
+    if (rc) return rc;
+  }
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

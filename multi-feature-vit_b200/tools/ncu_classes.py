@@ -5,7 +5,7 @@
     python multi-feature-vit_b200/tools/ncu_classes.py launches.csv profiles/r01_kernel_traffic.json
 
 GEMM launches are classed by position (before / after the fusion forward kernel) and epilogue: forward = every GEMM
-before `fusion_fwd_kernel`; in the backward the fp32 reduce-add instance is a weight gradient, the rest are dgrads.
+before the fusion forward (`fusion_fwd_kernel` / `fus2_ln0_kernel`); in the backward the fp32 reduce-add instance is a weight gradient, the rest are dgrads.
 """
 import csv
 import json
@@ -29,7 +29,7 @@ def classify(launches):
     seen_fusion = False
     for l in launches:
         n = l["name"]
-        if "fusion_fwd_kernel" in n:
+        if "fusion_fwd_kernel" in n or "fus2_ln0_kernel" in n:  # single-kernel / batched fusion forward
             seen_fusion = True
         if "gemm_bf16_kernel" in n:
             m = re.search(r"gemm_bf16_kernel<\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+)>", n)
@@ -44,7 +44,7 @@ def classify(launches):
             l["cls"], l["kernel"] = "ln_fwd", "ln_fwd"
         elif "ln_bwd" in n:
             l["cls"], l["kernel"] = "ln_bwd", "ln_bwd"
-        elif "fusion_" in n:
+        elif "fusion_" in n or "fus2_" in n:
             l["cls"], l["kernel"] = "fusion", n.split("(")[0].split("::")[-1].split("<")[0]
         elif "sgd_kernel" in n or "adam_kernel" in n:
             l["cls"], l["kernel"] = "sgd", "sgd"

@@ -81,6 +81,58 @@ def t_gemm_rows96():
         report("gemm rows96 dgrad M%d" % M, out, torch.einsum("gmn,gnk->gmk", dy.float(), w2.float()), 2e-2, rel=True)
 
 
+def t_gemm_streamk():
+    """opt-in stream-K (mfv_set_option("streamk", mask)): the (tile, k-block) space cut into equal ranges per CTA pair,
+    partial accumulators of a shared tile exchanged through the workspace.  Every family, against the whole-tile launch."""
+    from mfvit import _lib
+    lib = _lib.load()
+    M = 6304
+    default_mask = int(os.environ.get("MFVIT_STREAMK", "0"))
+
+    def both(fn):
+        assert lib.mfv_set_option(b"streamk", 0) == 0
+        a = fn()
+        assert lib.mfv_set_option(b"streamk", 15) == 0 and lib.mfv_set_option(b"streamk_min_kb", 2) == 0
+        try:
+            b = fn()
+        finally:
+            assert lib.mfv_set_option(b"streamk", default_mask) == 0 and lib.mfv_set_option(b"streamk_min_kb", 12) == 0
+        return a, b
+
+    torch.manual_seed(11)
+    x = bf(torch.randn(2, M, 1536, device=dev)); w = bf(torch.randn(2, 384, 1536, device=dev) * 0.05)
+    b = torch.randn(2, 384, device=dev); res = torch.randn(2, M, 384, device=dev)
+    o0, o1 = both(lambda: ops.linear_fwd(x, w, b, EPI_RESID_F32, aux=res, block_n=384))
+    report("stream-K resid fc2 (50 tiles on 74 pairs) vs whole tiles", o1, o0, 2e-5, rel=True)
+    assert float((o1 - o0).abs().max()) > 0.0, "stream-K did not engage (bit-identical to the whole-tile launch)"
+    x2 = bf(torch.randn(2, 2 * M, 1536, device=dev)); res2 = torch.randn(2, 2 * M, 384, device=dev)
+    p0, p1 = both(lambda: ops.linear_fwd(x2, w, b, EPI_RESID_F32, aux=res2, block_n=384))
+    report("stream-K resid fc2 (100 tiles) vs whole tiles", p1, p0, 2e-5, rel=True)
+    x3 = bf(torch.randn(2, 197 * 7, 1536, device=dev)); res3 = torch.randn(2, 197 * 7, 384, device=dev)
+    s0, s1 = both(lambda: ops.linear_fwd(x3, w, b, EPI_RESID_F32, aux=res3, block_n=384))
+    report("stream-K resid fc2 (12 tiles, ragged rows) vs whole tiles", s1, s0, 2e-5, rel=True)
+    report("stream-K resid fc2 vs fp32", o1, torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :] + res, 1e-4, rel=True)
+    gam = 1 + 0.1 * torch.randn(2, 384, device=dev); bet = 0.1 * torch.randn(2, 384, device=dev)
+    r0, r1 = both(lambda: ops.linear_fwd_ln(x, w, b, res, gam, bet))
+    for nm, t0, t1 in zip(("x", "ln", "copy", "mean", "rstd"), r0, r1):
+        if t0 is not None and torch.is_tensor(t0):
+            report("stream-K resid+LN %s vs whole tiles" % nm, t1.float(), t0.float(), 4e-3 if t0.dtype != torch.float32 else 2e-5, rel=True)
+    dy = bf(torch.randn(2, M, 1152, device=dev)); w2 = bf(torch.randn(2, 1152, 384, device=dev) * 0.05)
+    d0, d1 = both(lambda: ops.linear_dgrad(dy, w2, EPI_BF16, block_n=384))
+    report("stream-K bf16 dgrad qkv vs whole tiles", d1.float(), d0.float(), 8e-3, rel=True)
+    xs = bf(torch.randn(2, M, 384, device=dev)); w3 = bf(torch.randn(2, 1152, 384, device=dev) * 0.05); b3 = torch.randn(2, 1152, device=dev)
+    q0, q1 = both(lambda: ops.linear_fwd(xs, w3, b3, EPI_BF16))
+    report("stream-K bf16 qkv (250 tiles) vs whole tiles", q1.float(), q0.float(), 8e-3, rel=True)
+    w4 = bf(torch.randn(2, 1536, 384, device=dev) * 0.05); b4 = torch.randn(2, 1536, device=dev)
+    def fc1():
+        u = torch.empty(2, M, 1536, device=dev, dtype=torch.bfloat16); g = torch.empty_like(u)
+        ops.linear_fwd(xs, w4, b4, EPI_GELU, out=u, out2=g)
+        return u, g
+    g0, g1 = both(fc1)
+    for nm, t0, t1 in zip(("u", "gelu"), g0, g1):
+        report("stream-K fc1 GELU %s vs whole tiles" % nm, t1.float(), t0.float(), 8e-3, rel=True)
+
+
 def t_gemm_resid_ln():
     """MFV_EPI_RESID_LN: residual add + LayerNorm of the finished row inside the proj / fc2 epilogue."""
     for M, K, f16, rows in ((6304, 384, True, 0), (197 * 3, 1536, False, 0), (1379, 384, True, 96), (200, 256, False, 0)):
@@ -513,6 +565,7 @@ def main():
     run("gemm epilogues", t_gemm_epilogues, flt)
     run("gemm rows96", t_gemm_rows96, flt)
     run("gemm resid+LN", t_gemm_resid_ln, flt)
+    run("gemm stream-K", t_gemm_streamk, flt)
     run("patch embed TMA", t_patch_embed_tma, flt)
     run("wgrad pair", t_wgrad_pair, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
