@@ -248,6 +248,16 @@ __device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// The same load delivered to the same smem offset of every CTA in cta_mask (cluster ranks); each destination CTA's share
+// of the bytes is signalled on the barrier of ITS pair's leader (cute::SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma_load_3d_cg2_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                   int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
                "r"(ncols)

@@ -168,7 +168,12 @@ struct FragCursor {
 
 // EPI is a template parameter (MFV_EPI_ATOMIC_F32 shares the MFV_EPI_F32 instance): the epilogue is the issue-bound
 // part of these kernels, and a specialised instruction stream keeps it small (I-cache) and spill-free.
-template <int BN, int CG, int EPI>
+// MC = 1 (BN = 384 pair tiles only): clusters of FOUR CTAs = two pairs that work on two adjacent row tiles of the same
+// column tile in lockstep and share its B operand - each CTA loads half of its pair's B half and TMA-multicasts it to
+// the CTA of the same pair rank in the other pair, so the weights are read from L2 once per two row tiles.  (These
+// mainloops are bound by operand bytes out of L2: profiles/r02_summary.md.)  Stage release then needs both pairs: every
+// MMA commit arrives on the empty barrier of all four CTAs, which count two arrivals.
+template <int BN, int CG, int EPI, int MC = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
@@ -191,8 +196,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair (issues the MMAs)
-  const int cta_id = blockIdx.x / CG, num_ctas = gridDim.x / CG;  // persistent schedule runs over clusters
+  static_assert(MC == 0 || (BN == 384 && CG == 2), "B multicast is built for the 384-wide pair tiles");
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;  // rank in the cluster: 0..1, or 0..3 with MC
+  const uint32_t rank = crank & 1u;                           // 0 = leader of the pair (issues the MMAs)
+  const uint32_t pq = MC ? (crank >> 1) : 0u;                 // which pair of the cluster
+  // persistent schedule runs over clusters (with MC a cluster takes a pair of row tiles per step)
+  const int cta_id = blockIdx.x / (CG * (MC ? 2 : 1)), num_ctas = gridDim.x / (CG * (MC ? 2 : 1));
   constexpr int NACC = S::NACC;
   constexpr uint32_t TMEM_COLS = (NACC * BN <= 32) ? 32 : (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
 
@@ -202,7 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -243,12 +252,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       Frag fr;
       while (cur.next(p, fr)) {
         const TileInfo ti = decode_tile(p, fr.t);
-        const int n_tile = ti.n_tile, split = ti.split, m_tile = ti.m_tile, g = ti.g;
+        const int n_tile = ti.n_tile, split = ti.split, g = ti.g;
         const CUtensorMap* mapA = ti.prob ? &tmC2 : &tmA;
         const CUtensorMap* mapB = ti.prob ? &tmC3 : &tmB;
         const int kb0 = fr.kb0 >= 0 ? fr.kb0 : split * p.kb_per_split;
         const int kb1 = fr.kb0 >= 0 ? fr.kb1 : min(kb0 + p.kb_per_split, p.kb_total);
-        const int m0 = (m_tile * CG + (int)rank) * p.rows_cta;       // this CTA's rows of A
+        const int m_tile = MC ? ti.m_tile * 2 + (int)pq : ti.m_tile;  // MC: p.tiles_m counts PAIRS of row tiles
+        const int m0 = (m_tile * CG + (int)rank) * p.rows_cta;       // this CTA's rows of A (past M: TMA zero-fills)
         const int n0 = n_tile * BN + (int)rank * (BN / CG);          // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -268,8 +278,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               const int nn = n_tile * BN + (j < 2 ? (int)rank * 128 + j * 64 : 256 + (int)rank * 64);
-              if (!p.b_mn) load(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g);
-              else load(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g);
+              if constexpr (MC) {
+                // pair 0 fetches boxes 0 and 1, pair 1 box 2; every box goes to this CTA and to the CTA of the same
+                // pair rank in the other pair (cluster ranks rank and rank + 2)
+                if ((j < 2) != (pq == 0)) continue;
+                const uint16_t mask = (uint16_t)(0x5u << rank);
+                if (!p.b_mn) tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g, mask);
+                else tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g, mask);
+              } else {
+                if (!p.b_mn) load(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g);
+                else load(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g);
+              }
             }
           } else if (!p.b_mn) {
             load(sb, mapB, &full_bar[stage], kb * BK, n0, g);
@@ -329,10 +348,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
-          if (CG == 2) umma_commit_cg2(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
+          if (CG == 2) umma_commit_cg2(&empty_bar[stage], MC ? 0xF : 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) umma_commit_cg2(&tfull_bar[as], 0x3); else umma_commit(&tfull_bar[as]);
+        if (CG == 2) umma_commit_cg2(&tfull_bar[as], (uint16_t)(0x3u << (2 * pq))); else umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -379,7 +398,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster_relaxed(&tempty_bar[as], 0); else mbar_arrive_relaxed(&tempty_bar[as]);
+        if (CG == 2) mbar_arrive_cluster_relaxed(&tempty_bar[as], 2 * pq); else mbar_arrive_relaxed(&tempty_bar[as]);
       }
     };
     auto pack16 = [&](float a, float b) { return p.out_f16 ? pack_f16(a, b) : pack_bf16(a, b); };
@@ -397,7 +416,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto sk_flag = [&](int pair) { return p.sk_flags + (size_t)(pair * CG + (int)rank) * 2; };
     for (; cur.next(p, fr); ++it) {
       const TileInfo ti = decode_tile(p, fr.t);
-      const int n_tile = ti.n_tile, m_tile = ti.m_tile, g = ti.g;
+      const int n_tile = ti.n_tile, m_tile = MC ? ti.m_tile * 2 + (int)pq : ti.m_tile, g = ti.g;
       const int pM = ti.prob ? p.M1 : p.M, pN = ti.prob ? p.N1 : p.N;
       const CUtensorMap* mapC = ti.prob ? &tmAux : &tmC;   // paired launches only exist for the fp32 reduce-add epilogue
       float* const row_sum = ti.prob ? p.row_sum1 : p.row_sum;
@@ -930,6 +949,14 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
 
+  // B multicast between two pairs (MC kernel): the 384-wide bf16 / residual / residual + LayerNorm GEMMs with K-major A
+  constexpr bool mc_family = BN == 384 && CG == 2 && (EPI == MFV_EPI_BF16 || EPI == MFV_EPI_RESID_F32 || EPI == MFV_EPI_RESID_LN);
+  bool use_mc = false;
+  if constexpr (mc_family) {
+    use_mc = gemm_multicast_enabled() && !a->a_mn_major && p.splits == 1 && p.rows_cta == BM && p.tiles_m >= 2 &&
+             !p.dbg_skip_epilogue;
+    if (use_mc) p.tiles_m = (p.tiles_m + 1) / 2;  // the schedule walks PAIRS of row tiles
+  }
   const int total = p.tiles_m * p.tiles_n * p.splits * p.G;
   int clusters = num_sms() / CG;
   if (total < clusters) clusters = total;
@@ -943,7 +970,7 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
                         (BN == 256 && (mask & 2) && EPI == MFV_EPI_BF16) || (BN == 256 && (mask & 4) && EPI == MFV_EPI_GELU) ||
                         (BN == 256 && (mask & 8) && EPI == MFV_EPI_DGELU);
     const int pairs = num_sms() / CG;
-    if (CG == 2 && family && p.splits == 1 && a->epilogue != MFV_EPI_ATOMIC_F32 && total % pairs != 0 &&
+    if (CG == 2 && family && !use_mc && p.splits == 1 && a->epilogue != MFV_EPI_ATOMIC_F32 && total % pairs != 0 &&
         p.kb_total >= streamk_min_kb() && streamk_workspace()) {
       const long long units = (long long)total * p.kb_total;
       const int per = (int)((units + pairs - 1) / pairs);
@@ -974,6 +1001,28 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if constexpr (mc_family) {
+    if (use_mc) {
+      static bool mc_attr_set = false;
+      static int mc_max_clusters = 0;
+      attr[na - 1].val.clusterDim.x = 4;  // the cluster attribute is the last one written above (CG == 2)
+      if (!mc_attr_set) {
+        MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            S::TOTAL));
+        cfg.gridDim = dim3((unsigned)(num_sms() / 4 * 4));
+        MFV_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&mc_max_clusters, gemm_bf16_kernel<BN, CG, EPI, 1>, &cfg));
+        if (mc_max_clusters < 1) mc_max_clusters = 1;
+        mc_attr_set = true;
+      }
+      int cl4 = mc_max_clusters;  // clusters of four CTAs that can be resident at once (GPC boundaries cost a few SMs)
+      if (cl4 > num_sms() / 4) cl4 = num_sms() / 4;
+      if (total < cl4) cl4 = total;
+      cfg.gridDim = dim3((unsigned)(cl4 * 4));
+      MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, EPI, 1>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
+      MFV_LAUNCH_CHECK();
+      return MFV_OK;
+    }
+  }
   MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG, EPI>, tmA, tmB, tmC, tmC2, tmC3, tmAux, p));
   MFV_LAUNCH_CHECK();
   return MFV_OK;

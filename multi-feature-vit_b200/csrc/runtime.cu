@@ -119,6 +119,14 @@ int streamk_mask() {
   }
   return g_opt_streamk;
 }
+// B-operand multicast between two CTA pairs in the 384-wide GEMMs (gemm.cu, MC kernels): MFVIT_GEMM_MC=1.  Off by
+// default: it takes 13 % off the L2 traffic of an fc2-shaped GEMM (152 -> 132 MB, ncu lts__t_bytes) and nothing off its
+// duration (25.9 us cold either way; step 4.71 vs 4.74 ms) - what bounds these mainloops is per SM, not L2 bytes.
+static int g_opt_gemm_mc = -1;
+bool gemm_multicast_enabled() {
+  if (g_opt_gemm_mc < 0) g_opt_gemm_mc = env_flag("MFVIT_GEMM_MC", 0, '1');
+  return g_opt_gemm_mc == 1;
+}
 static int g_opt_streamk_min_kb = -1;
 int streamk_min_kb() {
   if (g_opt_streamk_min_kb < 0) {
@@ -163,6 +171,7 @@ extern "C" int mfv_set_option(const char* key, int value) {
   else if (k == "dx32") g_opt_dx32 = value ? 1 : 0;
   else if (k == "patch_tma") g_opt_patch_tma = value ? 1 : 0;
   else if (k == "reserve_sms") g_opt_reserve = value < 0 ? 0 : value;
+  else if (k == "gemm_mc") g_opt_gemm_mc = value ? 1 : 0;
   else if (k == "streamk") g_opt_streamk = value < 0 ? 0 : value;
   else if (k == "streamk_min_kb") g_opt_streamk_min_kb = value < 1 ? 1 : value;
   else return MFV_ERR_ARG;

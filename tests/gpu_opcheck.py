@@ -133,6 +133,39 @@ def t_gemm_streamk():
         report("stream-K fc1 GELU %s vs whole tiles" % nm, t1.float(), t0.float(), 8e-3, rel=True)
 
 
+def t_gemm_multicast():
+    """opt-in clusters of four CTAs (mfv_set_option("gemm_mc", 1)): two pairs on adjacent row tiles share the B operand by
+    TMA multicast.  Same arithmetic in the same order: bit-identical to the plain pair kernel, odd row-tile counts included."""
+    from mfvit import _lib
+    lib = _lib.load()
+
+    def both(fn):
+        assert lib.mfv_set_option(b"gemm_mc", 0) == 0
+        a = fn()
+        assert lib.mfv_set_option(b"gemm_mc", 1) == 0
+        try:
+            b = fn()
+        finally:
+            assert lib.mfv_set_option(b"gemm_mc", 0) == 0
+        return a, b
+
+    for M in (6304, 197 * 3, 2 * 6304 + 77):
+        torch.manual_seed(13)
+        x = bf(torch.randn(2, M, 1536, device=dev)); w = bf(torch.randn(2, 384, 1536, device=dev) * 0.05)
+        b = torch.randn(2, 384, device=dev); res = torch.randn(2, M, 384, device=dev)
+        o0, o1 = both(lambda: ops.linear_fwd(x, w, b, EPI_RESID_F32, aux=res, block_n=384))
+        report("multicast resid M%d vs pair kernel" % M, o1, o0, 0.0)
+        report("multicast resid M%d vs fp32" % M, o1, torch.einsum("gmk,gnk->gmn", x.float(), w.float()) + b[:, None, :] + res, 1e-4, rel=True)
+        gam = 1 + 0.1 * torch.randn(2, 384, device=dev); bet = 0.1 * torch.randn(2, 384, device=dev)
+        r0, r1 = both(lambda: ops.linear_fwd_ln(x, w, b, res, gam, bet))
+        for nm, t0, t1 in zip(("x", "ln", "copy", "mean", "rstd"), r0, r1):
+            if torch.is_tensor(t0):
+                report("multicast resid+LN %s M%d vs pair kernel" % (nm, M), t1.float(), t0.float(), 0.0)
+        dy = bf(torch.randn(2, M, 1152, device=dev)); w2 = bf(torch.randn(2, 1152, 384, device=dev) * 0.05)
+        d0, d1 = both(lambda: ops.linear_dgrad(dy, w2, EPI_BF16, block_n=384))
+        report("multicast bf16 dgrad (B MN-major) M%d vs pair kernel" % M, d1.float(), d0.float(), 0.0)
+
+
 def t_gemm_resid_ln():
     """MFV_EPI_RESID_LN: residual add + LayerNorm of the finished row inside the proj / fc2 epilogue."""
     for M, K, f16, rows in ((6304, 384, True, 0), (197 * 3, 1536, False, 0), (1379, 384, True, 96), (200, 256, False, 0)):
@@ -566,6 +599,7 @@ def main():
     run("gemm rows96", t_gemm_rows96, flt)
     run("gemm resid+LN", t_gemm_resid_ln, flt)
     run("gemm stream-K", t_gemm_streamk, flt)
+    run("gemm multicast", t_gemm_multicast, flt)
     run("patch embed TMA", t_patch_embed_tma, flt)
     run("wgrad pair", t_wgrad_pair, flt)
     run("gemm wgrad small", t_gemm_wgrad(1, 256, 128, 128, 1), flt)
