@@ -136,8 +136,8 @@ int streamk_min_kb() {
   return g_opt_streamk_min_kb;
 }
 // Partial-accumulator workspace of the stream-K GEMMs: one slot per CTA (fp32 [16 warps][BN / 4 x 32 values], BN <= 384)
-// + two counters per CTA.  Allocated at mfv_init (never inside a stream capture), zeroed once; the kernels leave the
-// counters at zero.
+// + two counters per CTA.  Allocated when the option is switched on (mfv_init with MFVIT_STREAMK set, or mfv_set_option -
+// never inside a stream capture), zeroed once; the kernels leave the counters at zero.
 static float* g_sk_ws = nullptr;
 static unsigned* g_sk_flags = nullptr;
 float* streamk_workspace() { return g_sk_ws; }
@@ -172,7 +172,13 @@ extern "C" int mfv_set_option(const char* key, int value) {
   else if (k == "patch_tma") g_opt_patch_tma = value ? 1 : 0;
   else if (k == "reserve_sms") g_opt_reserve = value < 0 ? 0 : value;
   else if (k == "gemm_mc") g_opt_gemm_mc = value ? 1 : 0;
-  else if (k == "streamk") g_opt_streamk = value < 0 ? 0 : value;
+  else if (k == "streamk") {  // not inside a stream capture: switching it on allocates the partial-sum workspace
+    g_opt_streamk = value < 0 ? 0 : value;
+    if (g_opt_streamk && g_num_sms > 0) {
+      const int rc = streamk_alloc(g_num_sms);
+      if (rc) return rc;
+    }
+  }
   else if (k == "streamk_min_kb") g_opt_streamk_min_kb = value < 1 ? 1 : value;
   else return MFV_ERR_ARG;
   return MFV_OK;
@@ -225,7 +231,7 @@ extern "C" int mfv_init(int device) {
   MFV_CUDA_CHECK(cudaSetDevice(device));
   g_num_sms = prop.multiProcessorCount;
   g_device = device;
-  {
+  if (streamk_mask() != 0) {  // opt-in experiment: its 29 MB workspace exists only when it is switched on
     const int rc = streamk_alloc(g_num_sms);
     if (rc) return rc;
   }
