@@ -30,7 +30,13 @@ from .trainer import FlatParams
 
 class MoCoPretrainer:
     def __init__(self, model, lr, weight_decay=0.1, betas=(0.9, 0.999), eps=1e-8, epochs=100, warmup_epochs=0,
-                 moco_m=0.99, moco_m_cos=True, cos=True, schedule=(), autocast_dtype=torch.bfloat16):
+                 moco_m=0.99, moco_m_cos=True, cos=True, schedule=(), autocast_dtype=torch.bfloat16, fast_syncbn=True):
+        # nn.SyncBatchNorm (MAIN_PRE:297) -> the lean implementation sharing its tensors (mfvit/syncbn.py): same numbers,
+        # one collective per call, a tenth of the host time; fast_syncbn=False keeps the stock modules
+        self.swapped_syncbn = 0
+        if fast_syncbn:
+            from .syncbn import swap_sync_batchnorm
+            self.swapped_syncbn = swap_sync_batchnorm(model)
         self.wrapped = model
         self.moco = model.module if hasattr(model, "module") else model
         self.lr, self.wd, self.betas, self.eps = float(lr), float(weight_decay), tuple(betas), float(eps)

@@ -137,6 +137,8 @@ def run(device, rank, world, batch=128, steps=10, warmup=3, check_batch=None, hw
     norms = q[:, ptr0:ptr0 + world * batch].norm(dim=0)
     out["enqueued_keys_unit_norm"] = bool(((norms - 1).abs() < 1e-4).all())
     out["optimizer"] = "fused AdamW on flat buffers (mfv_adam_step_dev), bf16 autocast heads, no GradScaler"
+    out["sync_batchnorm"] = ("%d nn.SyncBatchNorm modules replaced by mfvit.syncbn.FastSyncBatchNorm (same tensors; one "
+                             "collective per call)" % pre.swapped_syncbn) if pre.swapped_syncbn else "torch.nn.SyncBatchNorm"
     out["ok"] = bool(out["queues_identical_on_all_ranks"] and out["queue_ptr"] == expect and out["loss_finite"]
                      and out["enqueued_keys_unit_norm"] and out["parity_queue_max_abs"] <= 1e-4
                      and out["parity_logits_max_abs"] <= 2e-3 and out["parity_grad_cos_min"] >= 0.999)

@@ -62,6 +62,41 @@ def _worker(rank, world, port, out_dir):
     c1, _, _ = E.synthetic_pair(2, 32, rank=rank)
     res["shard_reproducible"] = bool(torch.equal(c0, c1))
     res["shard_sum"] = float(c0.sum())
+    # (5) FastSyncBatchNorm (mfvit/syncbn.py): two ranks with UNEQUAL batches reproduce nn.BatchNorm1d on the concatenated
+    # batch - output, running statistics, input gradient; parameter gradients are local sums that add up to the global one
+    from mfvit.syncbn import FastSyncBatchNorm, swap_sync_batchnorm
+    import torch.nn as nn
+    Fdim = 6
+    gen = torch.Generator().manual_seed(7)
+    full = torch.randn(7, Fdim, generator=gen) * 3 + 50.0            # large mean: E[x^2] - mean^2 would lose digits
+    wts = torch.randn(7, Fdim, generator=gen)
+    lo, hi = (0, 3) if rank == 0 else (3, 7)
+    ref_bn = nn.BatchNorm1d(Fdim)
+    with torch.no_grad():
+        ref_bn.weight.copy_(torch.linspace(0.5, 1.5, Fdim)); ref_bn.bias.copy_(torch.linspace(-1, 1, Fdim))
+    stock = nn.SyncBatchNorm(Fdim)
+    stock.load_state_dict(ref_bn.state_dict())
+    holder = nn.Sequential(stock)
+    res["bn_swapped"] = swap_sync_batchnorm(holder)
+    fast = holder[0]
+    res["bn_shares_tensors"] = bool(fast.weight is stock.weight and fast.running_mean is stock.running_mean)
+    xr = full.clone().requires_grad_(True)
+    (ref_bn(xr) * wts).sum().backward()
+    xl = full[lo:hi].clone().requires_grad_(True)
+    yl = fast(xl)
+    (yl * wts[lo:hi]).sum().backward()
+    want = nn.functional.batch_norm(full, None, None, ref_bn.weight, ref_bn.bias, True, 0.0, ref_bn.eps)  # no side effects
+    res["bn_out_err"] = float((yl.detach() - want[lo:hi]).abs().max())
+    res["bn_dx_err"] = float((xl.grad - xr.grad[lo:hi]).abs().max())
+    gw = fast.weight.grad.clone()
+    dist.all_reduce(gw)
+    res["bn_dw_err"] = float((gw - ref_bn.weight.grad).abs().max())
+    res["bn_rm_err"] = float((fast.running_mean - ref_bn.running_mean).abs().max())
+    res["bn_rv_err"] = float((fast.running_var - ref_bn.running_var).abs().max())
+    res["bn_tracked"] = int(fast.num_batches_tracked)
+    res["bn_keys"] = sorted(fast.state_dict().keys())
+    fast.eval()
+    res["bn_eval_err"] = float((fast(full[lo:hi]) - ref_bn.eval()(full)[lo:hi]).abs().max())
     torch.save(res, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
@@ -78,6 +113,10 @@ def test_two_rank_gloo(tmp_path):
         assert x["grad_mean_big"] == pytest.approx(15.0) and x["grad_mean_small"] == pytest.approx(1.5)
         assert x["local_only_untouched"]
         assert x["shard_reproducible"]
+        assert x["bn_swapped"] == 1 and x["bn_shares_tensors"] and x["bn_tracked"] == 1
+        assert x["bn_keys"] == ["bias", "num_batches_tracked", "running_mean", "running_var", "weight"]
+        assert x["bn_out_err"] < 2e-5 and x["bn_dx_err"] < 2e-5 and x["bn_dw_err"] < 1e-4
+        assert x["bn_rm_err"] < 1e-5 and x["bn_rv_err"] < 1e-5 and x["bn_eval_err"] < 2e-5
     # the queue holds rank 0's keys first, then rank 1's
     assert torch.allclose(torch.tensor(r[0]["queue_cols"][:2]), torch.tensor(r[0]["own_keys"]))
     assert torch.allclose(torch.tensor(r[0]["queue_cols"][2:]), torch.tensor(r[1]["own_keys"]))
