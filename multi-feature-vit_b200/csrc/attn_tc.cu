@@ -71,7 +71,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_free = bars + 5;       // O read out: TMEM may be overwritten by the next tile (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
   const int b = bh / H, h = bh % H;
   const int n_mt = (S + 127) >> 7;
@@ -95,13 +95,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   griddep_launch();
 
   if (warp == 4) {
-    if (lane == 0) {
+    {  // whole warp in uniform control flow, one elected lane issues (see elect_one() in common.cuh)
       griddep_wait();
-      mbar_arrive_expect_tx(bar_qk, (uint32_t)(n_mt * 16384 + NK * 128));
-      for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(sQ + mt * 16384, &tmQ, bar_qk, h * 64, mt * 128, b);
-      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * 64, 0, b);
-      mbar_arrive_expect_tx(bar_v, (uint32_t)(NK * 128));
-      tma_load_3d(sV, &tmKV, bar_v, (2 * H + h) * 64, 0, b);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_qk, (uint32_t)(n_mt * 16384 + NK * 128));
+        for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(sQ + mt * 16384, &tmQ, bar_qk, h * 64, mt * 128, b);
+        tma_load_3d(sK, &tmKV, bar_qk, (H + h) * 64, 0, b);
+        mbar_arrive_expect_tx(bar_v, (uint32_t)(NK * 128));
+        tma_load_3d(sV, &tmKV, bar_v, (2 * H + h) * 64, 0, b);
+      }
+      __syncwarp();
       const uint32_t fmt = F16 ? 0u : 1u;
       const uint32_t idesc_s = make_idesc2(fmt, fmt, 128, (uint32_t)NK, 0, 0);
       const uint32_t idesc_o = make_idesc2(fmt, fmt, 128, 64, 0, 1);
@@ -113,11 +116,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_after();
         }
         const uint32_t qa = smem_u32(sQ + mt * 16384), ka = smem_u32(sK);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, make_smem_desc_sw128(qa + k * 32, 0u, 1024u), make_smem_desc_sw128(ka + k * 32, 0u, 1024u),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, make_smem_desc_sw128(qa + k * 32, 0u, 1024u), make_smem_desc_sw128(ka + k * 32, 0u, 1024u),
+                      idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s);
+        }
+        __syncwarp();
         mbar_wait(bar_p, (uint32_t)(mt & 1));
         tc_fence_after();
         if (mt == 0) {
@@ -125,10 +131,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_after();
         }
         const uint32_t va = smem_u32(sV);
-        for (int k = 0; k < NK / 16; ++k)
-          umma_f16_ts(tmem_base + FA_O_COL, tmem_base + (uint32_t)(k * 8),
-                      make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(bar_o);
+        if (elect_one()) {
+          for (int k = 0; k < NK / 16; ++k)
+            umma_f16_ts(tmem_base + FA_O_COL, tmem_base + (uint32_t)(k * 8),
+                        make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(bar_o);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -321,7 +330,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint64_t* bar_conv2 = bars + 8;      // fp16 mode: V converted to bf16 (16 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int bh = blockIdx.x;
   const int b = bh / H, h = bh % H;
   const int n_t = (S + 127) >> 7;      // q-tiles == key-blocks
@@ -351,32 +360,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   if (warp == FB_CWARPS) {
     // ------------------------------------------------------------------------------------------ TMA + MMA issue
-    if (lane == 0) {
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one() in common.cuh)
+    {
       griddep_wait();
-      mbar_arrive_expect_tx(&bar_ld[0], (uint32_t)(2 * TILE));
-      tma_load_3d(sQ, &tmQKV, &bar_ld[0], h * 64, 0, b);
-      tma_load_3d(sK, &tmQKV, &bar_ld[0], (H + h) * 64, 0, b);
-      mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(2 * TILE));
-      tma_load_3d(sV, &tmQKV, &bar_ld[1], (2 * H + h) * 64, 0, b);
-      tma_load_3d(sdO, &tmDO, &bar_ld[1], h * 64, 0, b);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar_ld[0], (uint32_t)(2 * TILE));
+        tma_load_3d(sQ, &tmQKV, &bar_ld[0], h * 64, 0, b);
+        tma_load_3d(sK, &tmQKV, &bar_ld[0], (H + h) * 64, 0, b);
+        mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(2 * TILE));
+        tma_load_3d(sV, &tmQKV, &bar_ld[1], (2 * H + h) * 64, 0, b);
+        tma_load_3d(sdO, &tmDO, &bar_ld[1], h * 64, 0, b);
+      }
+      __syncwarp();
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
       auto issue_s = [&](int n) {
         const int j = n / n_t, i = n % n_t;
         const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FB_S_COL, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 0u, 1024u),
-                    make_smem_desc_sw128(aK + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + FB_S_COL, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aK + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+        }
+        __syncwarp();
       };
       auto issue_dp = [&](int n) {
         const int j = n / n_t, i = n % n_t;
         const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FB_DP_COL, make_smem_desc_sw128(adO + i * 16384 + k * 32, 0u, 1024u),
-                    make_smem_desc_sw128(aV + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
-        umma_commit(bar_sdp);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + FB_DP_COL, make_smem_desc_sw128(adO + i * 16384 + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aV + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+          umma_commit(bar_sdp);
+        }
+        __syncwarp();
       };
       auto issue_sdp = [&](int n) { issue_s(n); issue_dp(n); };
       // the first S = Q K^T starts as soon as Q and K are in shared memory (and converted, in fp16 mode) - it does not
@@ -405,22 +424,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tc_fence_after();
         }
         const int kq = r16(rows_of(i)) / 16;  // reduction over the q rows of tile i
-        for (int k = 0; k < kq; ++k) {
-          const uint64_t da_p = make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u);
-          const uint64_t da_s = make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u);
-          const uint64_t db_do = make_smem_desc_sw128(adO + i * 16384 + k * 2048, 8192u, 1024u);
-          const uint64_t db_q = make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192u, 1024u);
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base + FB_DV_COL, da_p, db_do, idesc_t, acc);
-          umma_bf16(tmem_base + FB_DK_COL, da_s, db_q, idesc_t, acc);
-        }
         const int kk = r16(rows_of(j)) / 16;  // reduction over the keys of block j
-        for (int k = 0; k < kk; ++k) {
-          const uint64_t da = make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u);
-          const uint64_t db = make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192u, 1024u);
-          umma_bf16(tmem_base + FB_DQ_COL + (uint32_t)(i * 64), da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        if (elect_one()) {
+          for (int k = 0; k < kq; ++k) {
+            const uint64_t da_p = make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u);
+            const uint64_t da_s = make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u);
+            const uint64_t db_do = make_smem_desc_sw128(adO + i * 16384 + k * 2048, 8192u, 1024u);
+            const uint64_t db_q = make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192u, 1024u);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base + FB_DV_COL, da_p, db_do, idesc_t, acc);
+            umma_bf16(tmem_base + FB_DK_COL, da_s, db_q, idesc_t, acc);
+          }
+          for (int k = 0; k < kk; ++k) {
+            const uint64_t da = make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u);
+            const uint64_t db = make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192u, 1024u);
+            umma_bf16(tmem_base + FB_DQ_COL + (uint32_t)(i * 64), da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_mma);
         }
-        umma_commit(bar_mma);
+        __syncwarp();
       }
     }
   } else {
@@ -678,7 +700,7 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   uint64_t* bar_dq_free = bars + 12;   // dQ read out of TMEM (16)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int bh = blockIdx.x, j = blockIdx.y;
   const int b = bh / H, h = bh % H;
   const int n_t = (S + 127) >> 7;
@@ -706,22 +728,27 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
   if (warp == FB_CWARPS + 1) {
     // ------------------------------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      griddep_wait();
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one() in common.cuh)
+    griddep_wait();
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_kv, 2 * 16384);
       tma_load_3d(sK, &tmQKV, bar_kv, (H + h) * 64, j * 128, b);
       tma_load_3d(sV, &tmQKV, bar_kv, (2 * H + h) * 64, j * 128, b);
-      for (int i = 0; i < n_t; ++i) {
-        const int s = i & 1;
-        if (i >= 2) mbar_wait(&bar_qfree[s], (uint32_t)(((i >> 1) - 1) & 1));
+    }
+    __syncwarp();
+    for (int i = 0; i < n_t; ++i) {
+      const int s = i & 1;
+      if (i >= 2) mbar_wait(&bar_qfree[s], (uint32_t)(((i >> 1) - 1) & 1));
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bar_q[s], 2 * 16384);
         tma_load_3d(sQ + s * 16384, &tmQKV, &bar_q[s], h * 64, i * 128, b);
         tma_load_3d(sdO + s * 16384, &tmDO, &bar_q[s], h * 64, i * 128, b);
       }
+      __syncwarp();
     }
   } else if (warp == FB_CWARPS) {
     // ------------------------------------------------------------------------------------------ MMA issue
-    if (lane == 0) {
+    {
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
       const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
       const uint32_t idesc_s = make_idesc2(1u, 1u, 128, (uint32_t)nk, 0, 0);
@@ -735,15 +762,18 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       };
       auto issue_sdp = [&](int i) {
         const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FM_S_COL, make_smem_desc_sw128(q + k * 32, 0u, 1024u),
-                    make_smem_desc_sw128(aK + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + FM_S_COL, make_smem_desc_sw128(q + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aK + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + FM_DP_COL, make_smem_desc_sw128(d + k * 32, 0u, 1024u),
-                    make_smem_desc_sw128(aV + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_sdp);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + FM_DP_COL, make_smem_desc_sw128(d + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aV + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_sdp);
+        }
+        __syncwarp();
       };
       mbar_wait(bar_kv, 0);
       if (QKV_F16) mbar_wait(bar_kvconv, 0);
@@ -760,18 +790,21 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tc_fence_after();
         const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
         const int kq = r16(rows_of(i)) / 16;
-        for (int k = 0; k < kq; ++k) {
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base + FM_DV_COL, make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u),
-                    make_smem_desc_sw128(d + k * 2048, 8192u, 1024u), idesc_t, acc);
-          umma_bf16(tmem_base + FM_DK_COL, make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u),
-                    make_smem_desc_sw128(q + k * 2048, 8192u, 1024u), idesc_t, acc);
+        if (elect_one()) {
+          for (int k = 0; k < kq; ++k) {
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base + FM_DV_COL, make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u),
+                      make_smem_desc_sw128(d + k * 2048, 8192u, 1024u), idesc_t, acc);
+            umma_bf16(tmem_base + FM_DK_COL, make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u),
+                      make_smem_desc_sw128(q + k * 2048, 8192u, 1024u), idesc_t, acc);
+          }
+          for (int k = 0; k < nk / 16; ++k)
+            umma_bf16(tmem_base + FM_DQ_COL, make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aK + k * 2048, 8192u, 1024u), idesc_q, k > 0 ? 1u : 0u);
+          umma_commit(&bar_qfree[i & 1]);  // the slot's Q / dO tiles are no longer needed
+          umma_commit(bar_mma);
         }
-        for (int k = 0; k < nk / 16; ++k)
-          umma_bf16(tmem_base + FM_DQ_COL, make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u),
-                    make_smem_desc_sw128(aK + k * 2048, 8192u, 1024u), idesc_q, k > 0 ? 1u : 0u);
-        umma_commit(&bar_qfree[i & 1]);  // the slot's Q / dO tiles are no longer needed
-        umma_commit(bar_mma);
+        __syncwarp();
       }
     }
   } else {
@@ -974,7 +1007,7 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bar_o = bar_p + 1;               // P.V of the block complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int bh = blockIdx.x, mt = blockIdx.y;
   const int b = bh / H, h = bh % H;
   const int n_kb = (S + 63) >> 6;
@@ -998,21 +1031,26 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (warp == 5) {
     // ------------------------------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      griddep_wait();
+    // (whole warp in uniform control flow, one elected lane issues: see elect_one() in common.cuh)
+    griddep_wait();
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_q, 16384);
       tma_load_3d(sQ, &tmQ, bar_q, h * 64, mt * 128, b);
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const int sl = kb % FL_RING;
-        if (kb >= FL_RING) mbar_wait(&ring_free[sl], (uint32_t)(((kb / FL_RING) - 1) & 1));
+    }
+    __syncwarp();
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int sl = kb % FL_RING;
+      if (kb >= FL_RING) mbar_wait(&ring_free[sl], (uint32_t)(((kb / FL_RING) - 1) & 1));
+      if (elect_one()) {
         mbar_arrive_expect_tx(&ring_full[sl], 16384);
         tma_load_3d(sRing + sl * 16384, &tmKV, &ring_full[sl], (H + h) * 64, kb * 64, b);
         tma_load_3d(sRing + sl * 16384 + 8192, &tmKV, &ring_full[sl], (2 * H + h) * 64, kb * 64, b);
       }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------------------------------ MMA issue
-    if (lane == 0) {
+    {
       const uint32_t fmt = F16 ? 0u : 1u;
       const uint32_t qa = smem_u32(sQ);
       auto keys_of = [&](int kb) { return min(64, S - 64 * kb); };
@@ -1022,11 +1060,14 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         const uint32_t ka = smem_u32(sRing + sl * 16384);
         const uint32_t idesc = make_idesc2(fmt, fmt, 128, (uint32_t)((keys_of(kb) + 15) & ~15), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + (uint32_t)((kb & 1) * 64), make_smem_desc_sw128(qa + k * 32, 0u, 1024u),
-                    make_smem_desc_sw128(ka + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
-        umma_commit(&bar_s[kb & 1]);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)((kb & 1) * 64), make_smem_desc_sw128(qa + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(ka + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[kb & 1]);
+        }
+        __syncwarp();
       };
       const uint32_t idesc_o = make_idesc2(fmt, fmt, 128, 64, 0, 1);
       mbar_wait(bar_q, 0);
@@ -1037,11 +1078,14 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         const uint32_t va = smem_u32(sRing + (kb % FL_RING) * 16384 + 8192);
         const int ksteps = ((keys_of(kb) + 15) & ~15) / 16;
-        for (int k = 0; k < ksteps; ++k)
-          umma_f16_ts(tmem_base + FL_O_COL, tmem_base + (uint32_t)((kb & 1) * 64 + k * 8),
-                      make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&ring_free[kb % FL_RING]);  // K (used by S) and V of this block are spent
-        umma_commit(bar_o);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ts(tmem_base + FL_O_COL, tmem_base + (uint32_t)((kb & 1) * 64 + k * 8),
+                        make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&ring_free[kb % FL_RING]);  // K (used by S) and V of this block are spent
+          umma_commit(bar_o);
+        }
+        __syncwarp();
         if (kb + 2 < n_kb) issue_s(kb + 2);     // reuses S buffer kb & 1: ordered behind the P.V just issued
       }
     }

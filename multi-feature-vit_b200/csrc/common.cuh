@@ -47,6 +47,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// Warp index as a value the compiler knows to be warp-uniform, and a one-lane election.  A role loop written as
+// `if (lane == 0) { ... tcgen05.mma / TMA ... }` is divergent code to the compiler: every operand of UTCHMMA / UTMALDG /
+// UTCBAR must be in a UNIFORM register, so each such instruction is wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY
+// "waterfall" loop - measured 180-310 clk per tcgen05.mma k-step in the GEMM mainloop (tests/gpu_ring_probe3.py), more
+// than the 64-128 clk the tensor pipe needs for it.  With the whole warp running the loop (uniform control flow, uniform
+// values) and only the asynchronous instruction itself under elect_one(), descriptors and coordinates live in uniform
+// registers and the instruction issues directly.
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

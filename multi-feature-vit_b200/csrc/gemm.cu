@@ -29,6 +29,7 @@ constexpr int EPI_BUF = 2048;                 // one staging slot: 32 rows x 64 
 // the pre-GELU tiles of BOTH pieces of a tile are requested at tile start - with three, the second one waited for the
 // previous tile's last store and its L2 latency was exposed, 12 % of the stall samples in profiles/r01_summary.md)
 constexpr int epi_nbuf(int epi) { return epi == MFV_EPI_DGELU ? 4 : 3; }
+constexpr int MAX_STAGES = 6;                 // barrier slots reserved per operand ring
 constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux (residual / pre-GELU) TMA loads: 2 in flight per epilogue warp
 
 struct GemmParams {
@@ -39,6 +40,10 @@ struct GemmParams {
   int epi;
   int has_c2, has_c3;
   int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
+  int dbg_mma;            // measurement aid (dtype_flags bits 16..19, epilogue skipped): 1 = no TMA loads (MMAs on stale smem),
+                          // 2 / 3 = + only the N=256 / only the N=128 UMMA of a 384-wide tile, 4 = + two N=192 UMMAs
+  int dbg_stages;         // measurement aid (dtype_flags bits 12..15, only with the epilogue skipped): operand ring depth;
+                          // stages past S::STAGES lie over the unused epilogue rings
   int rows_cta;           // rows of the output tile each CTA owns: 128, or 96 (K-major A only; see launch_gemm_epi)
   float* row_sum;         // BN == 384, fp32 reduce-add epilogue: += row sums of A (bias gradient of a wgrad GEMM)
   // Second problem of a paired launch (mfv_gemm_wgrad_pair: two weight-gradient GEMMs that share the reduction length,
@@ -186,16 +191,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* epi_base = smem + S::STAGES * S::STAGE_BYTES;
   uint8_t* bar_base = epi_base + S::EPI_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* tfull_bar = empty_bar + S::STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint8_t* ones_tile = bar_base + S::BAR_BYTES;  // BN == 384 only
   float2* ln_part = reinterpret_cast<float2*>(ones_tile + S::ONES_BYTES);  // BN == 384 only: [16 warps][32 lanes]
   uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + AUX_BARS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
+  const int nst = p.dbg_stages ? p.dbg_stages : S::STAGES;
   static_assert(MC == 0 || (BN == 384 && CG == 2), "B multicast is built for the 384-wide pair tiles");
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;  // rank in the cluster: 0..1, or 0..3 with MC
   const uint32_t rank = crank & 1u;                           // 0 = leader of the pair (issues the MMAs)
@@ -209,7 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < S::STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], MC ? 2 : 1);
     }
@@ -239,8 +245,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                           (p.tiles0 == 0x7fffffff ? 0 : p.tiles_m1 * p.tiles_n1 * p.splits * p.G);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       griddep_wait();  // PDL: operands may still be in flight in the previous kernel
       int stage = 0;
       uint32_t phase = 0;
@@ -264,6 +270,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
+          if (p.dbg_mma) {
+            if (rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
+            __syncwarp();
+            if (++stage == nst) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (elect_one()) {
           // the leader's barrier collects the bytes of both CTAs' loads
           if (rank == 0)
             mbar_arrive_expect_tx(&full_bar[stage], (S::STAGE_BYTES - S::A_BYTES + p.rows_cta * BK * 2) * CG);
@@ -296,17 +309,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, mapB, &full_bar[stage], n0 + j * 64, kb * BK, g);
           }
-          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+          }
+          __syncwarp();
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, BN == 384 ? 256 : BN,
-                                         (uint32_t)p.a_mn, (uint32_t)p.b_mn);
-      const uint32_t idesc2 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, 128, (uint32_t)p.a_mn,
-                                          (uint32_t)p.b_mn);  // second UMMA of a 384-wide tile
+    // ------------------------------------------------------------------ MMA issuer (whole warp of the leader CTA runs the
+    // loop; one elected lane issues the tcgen05 instructions)
+    if (rank == 0) {
+      // measurement aid: UMMA shapes / TMEM columns / B offsets of the two UMMAs of a 384-wide k-step (p.dbg_mma)
+      int pn1 = 256, pn2 = 128;
+      uint32_t pcol2 = 256u, pboff2 = 16384u;
+      switch (p.dbg_mma) {
+        case 2: pn2 = 0; break;
+        case 3: pn1 = 0; break;
+        case 4: pn1 = 192; pn2 = 192; pcol2 = 192u; pboff2 = 12288u; break;
+        case 5: pn1 = 0; pcol2 = 0u; break;
+        case 6: pn1 = 128; pn2 = 0; break;
+        case 7: pn1 = 0; pboff2 = 0u; break;
+        case 8: pn1 = 0; pn2 = 256; pcol2 = 0u; pboff2 = 0u; break;
+        case 9: pn1 = 128; pn2 = 128; pcol2 = 128u; pboff2 = 8192u; break;
+        case 10: pcol2 = 0u; break;
+        case 11: pn1 = 0; pn2 = 64; break;
+        case 12: pn1 = 0; pn2 = 256; pcol2 = 256u; pboff2 = 0u; break;
+        default: break;
+      }
+      const uint32_t idesc = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG,
+                                         BN == 384 ? (uint32_t)(pn1 ? pn1 : 256) : BN, (uint32_t)p.a_mn, (uint32_t)p.b_mn);
+      const uint32_t idesc2 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, (uint32_t)(pn2 ? pn2 : 128),
+                                          (uint32_t)p.a_mn, (uint32_t)p.b_mn);  // second UMMA of a 384-wide tile
       const uint32_t idesc3 = make_idesc2(p.a_f16 ? 0u : 1u, p.b_f16 ? 0u : 1u, BM * CG, 16, (uint32_t)p.a_mn, 1u);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kadv = p.a_mn ? (UMMA_K * 128u) : (UMMA_K * 2u);
@@ -333,15 +366,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sb = sa + S::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
             const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
-            if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BN == 384 && pn1 == 0) {
+            } else if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (BN == 384) {
-              const uint64_t db2 = make_smem_desc_sw128(sb + 16384u + k * b_kadv, b_lbo, 1024u);
-              umma_bf16_cg2(tmem_d + 256u, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (BN == 384 && pn2 != 0) {
+              const uint64_t db2 = make_smem_desc_sw128(sb + pboff2 + k * b_kadv, b_lbo, 1024u);
+              umma_bf16_cg2(tmem_d + pcol2, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
               if (want_rs)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
                 umma_bf16_cg2(tmem_d + 384u, da, make_smem_desc_sw128(smem_u32(ones_tile), 8192u, 1024u), idesc3,
                               (kb > kb0 || k > 0) ? 1u : 0u);
@@ -349,9 +384,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
           if (CG == 2) umma_commit_cg2(&empty_bar[stage], MC ? 0xF : 0x3); else umma_commit(&empty_bar[stage]);
-          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == kb1 - 1) {
+            if (CG == 2) umma_commit_cg2(&tfull_bar[as], (uint16_t)(0x3u << (2 * pq))); else umma_commit(&tfull_bar[as]);
+          }
+          }
+          __syncwarp();
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) umma_commit_cg2(&tfull_bar[as], (uint16_t)(0x3u << (2 * pq))); else umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -894,6 +933,13 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
   p.has_c2 = a->C2 != nullptr;
   p.has_c3 = a->C3 != nullptr;
   p.dbg_skip_epilogue = (a->dtype_flags >> 8) & 15;  // bit0: skip everything, bit1: skip the bulk stores
+  p.dbg_stages = 0;
+  p.dbg_mma = (p.dbg_skip_epilogue & 1) ? ((a->dtype_flags >> 16) & 15) : 0;
+  if ((p.dbg_skip_epilogue & 1) && ((a->dtype_flags >> 12) & 15)) {
+    const int want = (a->dtype_flags >> 12) & 15;
+    const int room = (S::STAGES * S::STAGE_BYTES + S::EPI_BYTES) / S::STAGE_BYTES;
+    p.dbg_stages = want < 2 ? 2 : (want > room ? room : (want > MAX_STAGES ? MAX_STAGES : want));
+  }
   p.bias_gstride = a->bias_gstride;
   p.bias = (const float*)a->bias;
   p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_mean = a->ln_mean; p.ln_rstd = a->ln_rstd;

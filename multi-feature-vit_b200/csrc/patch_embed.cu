@@ -60,7 +60,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmImg0, const __grid_cons
   uint64_t* tfull_bar = b_empty + PE_RING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   int item = blockIdx.x;                                 // (group, image, band of PH patch rows)
   const int t = item % p.tiles_per_img; item /= p.tiles_per_img;
   const int b = item % p.B;
@@ -91,25 +91,31 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmImg0, const __grid_cons
   griddep_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp in uniform control flow, one elected lane issues (see elect_one() in common.cuh)
       griddep_wait();
       const CUtensorMap* tmImg = g ? &tmImg1 : &tmImg0;
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb & 1;
         const uint32_t par = (uint32_t)((kb >> 1) & 1);
         mbar_wait(&raw_empty[s], par ^ 1);
-        mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(p.gw * p.PH * 256));
-        // pixels (j 0..15, rows 4*(kb%4) .. +3 of the patch, every patch column, PH patch rows, channel kb/4 of image b)
-        tma_load_5d(s_raw + s * PE_RAW_BYTES, tmImg, &raw_full[s], 0, (kb & 3) * 4, 0, ph0, b * 3 + (kb >> 2));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(p.gw * p.PH * 256));
+          // pixels (j 0..15, rows 4*(kb%4) .. +3 of the patch, every patch column, PH patch rows, channel kb/4 of image b)
+          tma_load_5d(s_raw + s * PE_RAW_BYTES, tmImg, &raw_full[s], 0, (kb & 3) * 4, 0, ph0, b * 3 + (kb >> 2));
+        }
+        __syncwarp();
         mbar_wait(&b_empty[s], par ^ 1);
-        mbar_arrive_expect_tx(&b_full[s], (uint32_t)PE_B_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[s], (uint32_t)PE_B_BYTES);
 #pragma unroll
-        for (int j = 0; j < 6; ++j)
-          tma_load_3d(s_b + s * PE_B_BYTES + j * 8192, &tmW, &b_full[s], kb * 64, j * 64, g);
+          for (int j = 0; j < 6; ++j)
+            tma_load_3d(s_b + s * PE_B_BYTES + j * 8192, &tmW, &b_full[s], kb * 64, j * 64, g);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t fmt = p.f16 ? 0u : 1u;
       const uint32_t idesc = make_idesc2(fmt, fmt, 128, 256, 0, 0);
       const uint32_t idesc2 = make_idesc2(fmt, fmt, 128, 128, 0, 0);
@@ -121,19 +127,22 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmImg0, const __grid_cons
         tc_fence_after();
         const uint32_t sa = smem_u32(s_a + s * PE_A_BYTES);
         const uint32_t sb = smem_u32(s_b + s * PE_B_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0u, 1024u);
-          const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0u, 1024u);
-          const uint64_t db2 = make_smem_desc_sw128(sb + 32768u + k * 32, 0u, 1024u);
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, da, db, idesc, acc);
-          umma_bf16(tmem_base + 256u, da, db2, idesc2, acc);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0u, 1024u);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0u, 1024u);
+            const uint64_t db2 = make_smem_desc_sw128(sb + 32768u + k * 32, 0u, 1024u);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base, da, db, idesc, acc);
+            umma_bf16(tmem_base + 256u, da, db2, idesc2, acc);
+          }
+          umma_commit(&a_empty[s]);
+          umma_commit(&b_empty[s]);
+          if (kb == KB - 1) umma_commit(tfull_bar);
         }
-        umma_commit(&a_empty[s]);
-        umma_commit(&b_empty[s]);
+        __syncwarp();
       }
-      umma_commit(tfull_bar);
     }
   } else {
     // ------------------------------------------------------------------ converter + epilogue warps
