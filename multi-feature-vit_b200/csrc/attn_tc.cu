@@ -397,7 +397,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         __syncwarp();
       };
-      auto issue_sdp = [&](int n) { issue_s(n); issue_dp(n); };
+      // S and dP of a step alternate k-step by k-step: consecutive tcgen05.mma on the SAME accumulator columns leave a
+      // bubble of ~45 clk between them (tests/gpu_ring_probe3.py), two accumulators taken in turn hide it
+      auto issue_sdp = [&](int n) {
+        const int j = n / n_t, i = n % n_t;
+        const uint32_t idesc = make_idesc2(1u, 1u, 128, (uint32_t)r16(rows_of(j)), 0, 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem_base + FB_S_COL, make_smem_desc_sw128(aQ + i * 16384 + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aK + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+            umma_bf16(tmem_base + FB_DP_COL, make_smem_desc_sw128(adO + i * 16384 + k * 32, 0u, 1024u),
+                      make_smem_desc_sw128(aV + j * 16384 + k * 32, 0u, 1024u), idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_sdp);
+        }
+        __syncwarp();
+      };
       // the first S = Q K^T starts as soon as Q and K are in shared memory (and converted, in fp16 mode) - it does not
       // wait for V, dO or the delta prologue of the compute warps
       mbar_wait(&bar_ld[0], 0);
@@ -426,19 +442,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const int kq = r16(rows_of(i)) / 16;  // reduction over the q rows of tile i
         const int kk = r16(rows_of(j)) / 16;  // reduction over the keys of block j
         if (elect_one()) {
-          for (int k = 0; k < kq; ++k) {
-            const uint64_t da_p = make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u);
-            const uint64_t da_s = make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u);
-            const uint64_t db_do = make_smem_desc_sw128(adO + i * 16384 + k * 2048, 8192u, 1024u);
-            const uint64_t db_q = make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192u, 1024u);
-            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(tmem_base + FB_DV_COL, da_p, db_do, idesc_t, acc);
-            umma_bf16(tmem_base + FB_DK_COL, da_s, db_q, idesc_t, acc);
-          }
-          for (int k = 0; k < kk; ++k) {
-            const uint64_t da = make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u);
-            const uint64_t db = make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192u, 1024u);
-            umma_bf16(tmem_base + FB_DQ_COL + (uint32_t)(i * 64), da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+          // dV, dK and dQ k-steps in turn (three accumulators: no back-to-back UMMAs on the same columns)
+          const int kmax = kq > kk ? kq : kk;
+          for (int k = 0; k < kmax; ++k) {
+            if (k < kq) {
+              const uint64_t da_p = make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u);
+              const uint64_t da_s = make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u);
+              const uint64_t db_do = make_smem_desc_sw128(adO + i * 16384 + k * 2048, 8192u, 1024u);
+              const uint64_t db_q = make_smem_desc_sw128(aQ + i * 16384 + k * 2048, 8192u, 1024u);
+              const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(tmem_base + FB_DV_COL, da_p, db_do, idesc_t, acc);
+              umma_bf16(tmem_base + FB_DK_COL, da_s, db_q, idesc_t, acc);
+            }
+            if (k < kk) {
+              const uint64_t da = make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u);
+              const uint64_t db = make_smem_desc_sw128(aK + j * 16384 + k * 2048, 8192u, 1024u);
+              umma_bf16(tmem_base + FB_DQ_COL + (uint32_t)(i * 64), da, db, idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(bar_mma);
         }
@@ -762,15 +782,14 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       };
       auto issue_sdp = [&](int i) {
         const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
-        if (elect_one()) {
+        if (elect_one()) {  // S and dP k-steps in turn: no back-to-back UMMAs on the same accumulator columns
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k) {
             umma_bf16(tmem_base + FM_S_COL, make_smem_desc_sw128(q + k * 32, 0u, 1024u),
                       make_smem_desc_sw128(aK + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
             umma_bf16(tmem_base + FM_DP_COL, make_smem_desc_sw128(d + k * 32, 0u, 1024u),
                       make_smem_desc_sw128(aV + k * 32, 0u, 1024u), idesc_s, k > 0 ? 1u : 0u);
+          }
           umma_commit(bar_sdp);
         }
         __syncwarp();
@@ -791,16 +810,19 @@ attn_bwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const uint32_t q = aQ + (i & 1) * 16384, d = adO + (i & 1) * 16384;
         const int kq = r16(rows_of(i)) / 16;
         if (elect_one()) {
-          for (int k = 0; k < kq; ++k) {
-            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(tmem_base + FM_DV_COL, make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u),
-                      make_smem_desc_sw128(d + k * 2048, 8192u, 1024u), idesc_t, acc);
-            umma_bf16(tmem_base + FM_DK_COL, make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u),
-                      make_smem_desc_sw128(q + k * 2048, 8192u, 1024u), idesc_t, acc);
+          const int kk = nk / 16, kmax = kq > kk ? kq : kk;
+          for (int k = 0; k < kmax; ++k) {  // dV, dK and dQ k-steps in turn
+            if (k < kq) {
+              const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(tmem_base + FM_DV_COL, make_smem_desc_sw128(aP + k * 2048, 16384u, 1024u),
+                        make_smem_desc_sw128(d + k * 2048, 8192u, 1024u), idesc_t, acc);
+              umma_bf16(tmem_base + FM_DK_COL, make_smem_desc_sw128(adS + k * 2048, 16384u, 1024u),
+                        make_smem_desc_sw128(q + k * 2048, 8192u, 1024u), idesc_t, acc);
+            }
+            if (k < kk)
+              umma_bf16(tmem_base + FM_DQ_COL, make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u),
+                        make_smem_desc_sw128(aK + k * 2048, 8192u, 1024u), idesc_q, k > 0 ? 1u : 0u);
           }
-          for (int k = 0; k < nk / 16; ++k)
-            umma_bf16(tmem_base + FM_DQ_COL, make_smem_desc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 0u, 1024u),
-                      make_smem_desc_sw128(aK + k * 2048, 8192u, 1024u), idesc_q, k > 0 ? 1u : 0u);
           umma_commit(&bar_qfree[i & 1]);  // the slot's Q / dO tiles are no longer needed
           umma_commit(bar_mma);
         }

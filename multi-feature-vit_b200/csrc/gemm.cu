@@ -42,6 +42,8 @@ struct GemmParams {
   int dbg_skip_epilogue;  // measurement aid (dtype_flags bits 8..9): see launch_gemm
   int dbg_mma;            // measurement aid (dtype_flags bits 16..19, epilogue skipped): 1 = no TMA loads (MMAs on stale smem),
                           // 2 / 3 = + only the N=256 / only the N=128 UMMA of a 384-wide tile, 4 = + two N=192 UMMAs
+  unsigned long long* dbg_prof;  // measurement aid (dtype_flags bit 20; the buffer rides in row_sum): per epilogue warp,
+                          // clock64 sums of 8 phases - [CTA][16 warps][8], see PROF_MARK
   int dbg_stages;         // measurement aid (dtype_flags bits 12..15, only with the epilogue skipped): operand ring depth;
                           // stages past S::STAGES lie over the unused epilogue rings
   int rows_cta;           // rows of the output tile each CTA owns: 128, or 96 (K-major A only; see launch_gemm_epi)
@@ -78,7 +80,7 @@ struct GemmParams {
 // 384-column accumulator - for the N = 384 GEMMs (proj, fc2, every dgrad, qkv/fc1 wgrad) the A operand is then read from
 // L2 exactly once instead of three times.  These kernels are L2->SM bandwidth bound (about 10 TB/s on the chip, measured:
 // the mainloop-only time of every shape tracks its tile traffic), so tile traffic is what sets their speed.
-template <int BN, int CG, int NBUF>
+template <int BN, int CG, int NBUF, int EPI>
 struct GemmSmem {
   static_assert(BN != 384 || CG == 2, "384-wide tiles need a CTA pair");
   static constexpr int A_BYTES = BM * BK * 2;
@@ -86,15 +88,19 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;  // TMEM accumulators: double-buffered when two fit in 512 columns
   static constexpr int BAR_BYTES = 512;
-  static constexpr int ONES_BYTES = (BN == 384) ? 2048 : 0;  // [16 k][64 n] tile of 1.0 for the row-sum UMMA
-  static constexpr int LN_BYTES = (BN == 384) ? NUM_EPI_WARPS * 32 * 8 : 0;  // (mean, M2) of each warp's share of a row
+  static constexpr int ONES_BYTES = (BN == 384 && EPI == MFV_EPI_F32) ? 2048 : 0;  // [16 k][64 n] tile of 1.0 for the row-sum UMMA
+  static constexpr int LN_BYTES = (EPI == MFV_EPI_RESID_LN) ? NUM_EPI_WARPS * 32 * 8 : 0;  // (mean, M2) of each warp's share of a row
+  // bias (and LayerNorm gamma, beta) of the tile's 384 columns, staged once per tile: with 227 KB of the SM's 228 KB
+  // configured as shared memory there is no L1 left, and every __ldg of these vectors in the epilogue was an L2 round
+  // trip (~700 clk per piece: tests/gpu_epi_prof.py)
+  static constexpr int PAR_BYTES = (BN != 384) ? 0 : (EPI == MFV_EPI_RESID_LN) ? 3 * 384 * 4 : (EPI == MFV_EPI_RESID_F32) ? 384 * 4 : 0;
   static constexpr int EPI_BYTES = NUM_EPI_WARPS * NBUF * EPI_BUF;
   // operand stages: what is left of the 227 KB after the epilogue rings (3 slots: 6/5/4/4/3/2 stages for 16/24/32/32/
   // 40/48 KB stages, 4 slots: one fewer from 32 KB up), at most 6
-  static constexpr int AVAIL = 232448 - 1024 - BAR_BYTES - ONES_BYTES - LN_BYTES - EPI_BYTES;
+  static constexpr int AVAIL = 232448 - 1024 - BAR_BYTES - ONES_BYTES - LN_BYTES - PAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES > 6) ? 6 : AVAIL / STAGE_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a double-buffered mainloop");
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + LN_BYTES + 1024;  // +1024: alignment
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + ONES_BYTES + LN_BYTES + PAR_BYTES + 1024;  // +1024: alignment
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -185,7 +191,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC3, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
   constexpr int EPI_NBUF = epi_nbuf(EPI);
-  using S = GemmSmem<BN, CG, EPI_NBUF>;
+  using S = GemmSmem<BN, CG, EPI_NBUF, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_base = smem + S::STAGES * S::STAGE_BYTES;
@@ -195,7 +201,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint8_t* ones_tile = bar_base + S::BAR_BYTES;  // BN == 384 only
-  float2* ln_part = reinterpret_cast<float2*>(ones_tile + S::ONES_BYTES);  // BN == 384 only: [16 warps][32 lanes]
+  float2* ln_part = reinterpret_cast<float2*>(ones_tile + S::ONES_BYTES);  // MFV_EPI_RESID_LN only: [16 warps][32 lanes]
+  [[maybe_unused]] float* par = reinterpret_cast<float*>(ones_tile + S::ONES_BYTES + S::LN_BYTES);  // bias | gamma | beta
   uint64_t* aux_bar = tempty_bar + 2;  // [NUM_EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + AUX_BARS);
 
@@ -229,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     if (CG == 2) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
   }
-  if (BN == 384 && warp == 2 && (p.row_sum || p.row_sum1)) {  // bf16 1.0 everywhere: the swizzle is irrelevant for a constant tile
+  if (S::ONES_BYTES > 0 && warp == 2 && (p.row_sum || p.row_sum1)) {  // bf16 1.0 everywhere: the swizzle is irrelevant for a constant tile
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       reinterpret_cast<uint4*>(ones_tile)[lane + 32 * i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -353,7 +360,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (; cur.next(p, fr); ++it) {
         const TileInfo ti = decode_tile(p, fr.t);
         const int split = ti.split;
-        const bool want_rs = (ti.prob ? p.row_sum1 : p.row_sum) != nullptr;
+        const bool want_rs = S::ONES_BYTES > 0 && (ti.prob ? p.row_sum1 : p.row_sum) != nullptr;
         const int kb0 = fr.kb0 >= 0 ? fr.kb0 : split * p.kb_per_split;
         const int kb1 = fr.kb0 >= 0 ? fr.kb1 : min(kb0 + p.kb_per_split, p.kb_total);
         const int as = it % NACC;
@@ -406,6 +413,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
+    // phase clocks (measurement aid): 0 accumulator wait, 1 TMEM read, 2 slot / aux wait, 3 convert + staging stores,
+    // 4 fence + bulk store issue, 5 epilogue math, 6 LayerNorm row barrier, 7 final drain
+    unsigned long long* const prof = p.dbg_prof;
+    long long prof_t = 0;
+    unsigned long long prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_MARK(slot)                              \
+  if (prof) {                                        \
+    const long long now_ = clock64();                \
+    prof_c[slot] += (unsigned long long)(now_ - prof_t); \
+    prof_t = now_;                                   \
+  }
     uint8_t* ring = epi_base + ew * (EPI_NBUF * EPI_BUF);
     uint32_t use = 0;  // ring uses so far
     uint64_t* abar = aux_bar + 2 * ew;
@@ -419,30 +437,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto slot_ptr = [&](uint32_t u) { return ring + (u % EPI_NBUF) * EPI_BUF; };
     // make the next slot writable: the bulk store that used it EPI_NBUF uses ago has finished reading it
     auto acquire_slot = [&]() {
-      if (lane == 0) bulk_wait_read_n(EPI_NBUF - 1);
+      PROF_MARK(5)
+      if (elect_one()) bulk_wait_read_n(EPI_NBUF - 1);
       __syncwarp();
+      PROF_MARK(2)
     };
     auto publish = [&](const CUtensorMap* map, const uint8_t* src, int c0, int r0, int gg, bool reduce) {
+      PROF_MARK(3)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {  // the elected lane is the same one every time: bulk groups are per thread
         if (!(p.dbg_skip_epilogue & 2)) {
           if (reduce) tma_reduce_add_3d(map, src, c0, r0, gg); else tma_store_3d(map, src, c0, r0, gg);
         }
         bulk_commit();
       }
       ++use;
+      PROF_MARK(4)
     };
     auto release_accumulator = [&](int as) {  // all tcgen05.ld of this warp have completed (wait::ld is warp-wide)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if (CG == 2) mbar_arrive_cluster_relaxed(&tempty_bar[as], 2 * pq); else mbar_arrive_relaxed(&tempty_bar[as]);
       }
     };
     auto pack16 = [&](float a, float b) { return p.out_f16 ? pack_f16(a, b) : pack_bf16(a, b); };
     griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
+    if (prof) prof_t = clock64();
     int it = 0;
+    [[maybe_unused]] int par_g = -1;  // group whose bias / gamma / beta the parameter block holds
+    constexpr bool bias_by_shfl = (S::PAR_BYTES == 0) && (PW == 32) && (npieces <= 8);
     FragCursor cur;
     cur.init(p, cta_id, num_ctas, total_tiles);
     Frag fr;
@@ -475,19 +500,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int upc = (epi == MFV_EPI_DGELU && p.has_c2) ? 2 : 1;
       const int aux_ahead = (upc == 1 || EPI_NBUF >= 4) ? 2 : 1;
       const uint32_t use0 = use;
-      auto issue_aux = [&](int i, int pending_ok) {  // lane 0 only
+      auto issue_aux = [&](int i, int pending_ok) {  // the elected lane only
         bulk_wait_read_n(pending_ok);
         mbar_arrive_expect_tx(&abar[i & 1], EPI_BUF);
         tma_load_3d(slot_ptr(use0 + (uint32_t)(i * upc)), &tmAux, &abar[i & 1], ncol0 + (h + 4 * i) * PW, row0, g);
       };
       if constexpr (has_aux) {
-        if (lane == 0 && fr.role != 1)
-          for (int j = 0; j < aux_ahead && j < n_my; ++j) issue_aux(j, (int)EPI_NBUF - 1 - j * upc);
+        if (fr.role != 1) {
+          if (elect_one())
+            for (int j = 0; j < aux_ahead && j < n_my; ++j) issue_aux(j, (int)EPI_NBUF - 1 - j * upc);
+          __syncwarp();
+        }
       }
-      // pull this warp's bias lines into L1 while the MMAs of the tile are still running
-      if (bias && lane < n_my && fr.role != 1) prefetch_l1(bias + ncol0 + (h + 4 * lane) * PW);
+      // Bias (gamma, beta) of this tile, fetched while its MMAs are still running.  384-wide tiles: the whole vectors
+      // into the shared parameter block (all 16 warps; re-staged only when the group changes).  Narrower tiles with
+      // 32-column pieces: lane L keeps bias[piece column L] of the warp's (at most two) pieces in a register and the
+      // piece loop broadcasts it by shuffle.  Either way no epilogue thread waits on L2 for them.
+      [[maybe_unused]] float breg0 = 0.f, breg1 = 0.f;
+      if constexpr (S::PAR_BYTES > 0) {
+        if (bias && fr.role != 1 && g != par_g) {
+          if (par_g >= 0) named_bar_sync(5u, 32u * NUM_EPI_WARPS);  // every warp has finished with the previous group's values
+          for (int idx = ew * 32 + lane; idx < 384; idx += 32 * NUM_EPI_WARPS) {
+            par[idx] = __ldg(bias + idx);
+            if constexpr (EPI == MFV_EPI_RESID_LN) {
+              par[384 + idx] = __ldg(p.ln_gamma + (long long)g * p.bias_gstride + idx);
+              par[768 + idx] = __ldg(p.ln_beta + (long long)g * p.bias_gstride + idx);
+            }
+          }
+          named_bar_sync(5u, 32u * NUM_EPI_WARPS);
+          par_g = g;
+        }
+      } else if constexpr (bias_by_shfl) {
+        if (bias && fr.role != 1) {
+          if (n_my > 0) breg0 = __ldg(bias + ncol0 + h * PW + lane);
+          if (n_my > 1) breg1 = __ldg(bias + ncol0 + (h + 4) * PW + lane);
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      PROF_MARK(0)
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       if (fr.role == 1) {
         // ---- stream-K tail: this pair's partial sums of a tile the previous pair finishes.  Dump, raise the counter.
@@ -588,6 +639,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         }
+        PROF_MARK(1)
         if (sk_part) {  // stream-K head: + the partial sums of the pairs that hold the rest of this tile
           for (int j = 0; j < ((p.dbg_skip_epilogue & 4) ? 0 : fr.contrib); ++j) {
             const float* wp = sk_part + (size_t)j * (CG * NUM_EPI_WARPS * SK_WARP_FLOATS) + i * 32 * PW;
@@ -602,22 +654,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (epi != MFV_EPI_RESID_LN && i == n_my - 1)
           release_accumulator(as);  // last TMEM read of the tile: the MMA warp may reuse the buffer
         if (bias) {
-          const float* bp = bias + n0;
+          if constexpr (S::PAR_BYTES > 0) {
+            const float* bp = par + c * PW;  // the same address in every lane: one broadcast wavefront per load
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            if (k < PW) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + k));
+            for (int k = 0; k < PW; k += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bp + k);
               f[k] += b4.x; f[k + 1] += b4.y; f[k + 2] += b4.z; f[k + 3] += b4.w;
+            }
+          } else if constexpr (bias_by_shfl) {
+            const float bsel = (i == 0) ? breg0 : breg1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] += __shfl_sync(0xffffffffu, bsel, k);
+          } else {
+            const float* bp = bias + n0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              if (k < PW) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + k));
+                f[k] += b4.x; f[k + 1] += b4.y; f[k + 2] += b4.z; f[k + 3] += b4.w;
+              }
             }
           }
         }
         uint8_t* st0 = slot_ptr(use);
+        PROF_MARK(5)
         if constexpr (has_aux) {
           mbar_wait(&abar[i & 1], (aux_phase >> (i & 1)) & 1u);
           aux_phase ^= 1u << (i & 1);
         } else {
           acquire_slot();
         }
+        PROF_MARK(2)
         if constexpr (epi == MFV_EPI_BF16) {
           {
 #pragma unroll
@@ -665,7 +732,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *pp = make_float4(f[4 * j] + rr.x, f[4 * j + 1] + rr.y, f[4 * j + 2] + rr.z, f[4 * j + 3] + rr.w);
             }
             publish(&tmC, st0, n0, row0, g, false);
-            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
+            if (i + aux_ahead < n_my) {
+              if (elect_one()) issue_aux(i + aux_ahead, 1);
+              __syncwarp();
+            }
           }
         } else if constexpr (epi == MFV_EPI_RESID_LN) {
           {  // pass 1 of the fused LayerNorm: x = acc + bias + residual -> C (fp32) as above, x kept in TMEM over the
@@ -680,7 +750,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *pp = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             }
             publish(&tmC, st0, n0, row0, g, false);
-            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
+            if (i + aux_ahead < n_my) {
+              if (elect_one()) issue_aux(i + aux_ahead, 1);
+              __syncwarp();
+            }
             {
               uint32_t yb[16];
 #pragma unroll
@@ -735,7 +808,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               publish(&tmC2, st1, n0, row0, g, false);
             }
             // the slot piece i + aux_ahead lands in was last read by a store that is at least the second-newest group
-            if (lane == 0 && i + aux_ahead < n_my) issue_aux(i + aux_ahead, 1);
+            if (i + aux_ahead < n_my) {
+              if (elect_one()) issue_aux(i + aux_ahead, 1);
+              __syncwarp();
+            }
           }
         } else {
           {  // MFV_EPI_F32 (also serves MFV_EPI_ATOMIC_F32: p.epi selects the reduce-add store): raw fp32 tile
@@ -752,8 +828,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_st_wait();
         ln_part[ew * 32 + lane] = make_float2(ln_m, ln_s);
         tc_fence_before();
+        PROF_MARK(5)
         named_bar_sync(1u + (uint32_t)q, 128u);  // the four epilogue warps of TMEM lane quarter q: ew = (ew & 3) + 4 h
         tc_fence_after();
+        PROF_MARK(6)
         float mean = 0.f, m2 = 0.f;
         float2 part[4];
 #pragma unroll
@@ -770,22 +848,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           p.ln_mean[(long long)g * p.M + row0 + lane] = mean;
           p.ln_rstd[(long long)g * p.M + row0 + lane] = rstd;
         }
-                const float* gam = p.ln_gamma + (long long)g * p.bias_gstride + ncol0;
-        const float* bet = p.ln_beta + (long long)g * p.bias_gstride + ncol0;
+        const float* gam = par + 384;  // staged at the start of the tile (BN == N == 384: ncol0 == 0)
+        const float* bet = par + 768;
         // ---- pass 2: x back out of TMEM, normalised, to C2 (and C3)
         if (!p.ln_out_f32) {
 #pragma unroll 1
           for (int j = 0; j < 3; ++j) {  // 32-column pieces h, h + 4, h + 8 of the 12
             const int c2 = h + 4 * j;
             uint32_t v[32];
+            PROF_MARK(5)
             tmem_ld32(trow + (uint32_t)(c2 * 32), v);
             tmem_ld_wait();
+            PROF_MARK(1)
             if (j == 2) release_accumulator(as);
             float o[32];
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c2 * 32 + k));
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bet + c2 * 32 + k));
+              const float4 g4 = *reinterpret_cast<const float4*>(gam + c2 * 32 + k);
+              const float4 b4 = *reinterpret_cast<const float4*>(bet + c2 * 32 + k);
               o[k] = fmaf((__uint_as_float(v[k]) - mean) * rstd, g4.x, b4.x);
               o[k + 1] = fmaf((__uint_as_float(v[k + 1]) - mean) * rstd, g4.y, b4.y);
               o[k + 2] = fmaf((__uint_as_float(v[k + 2]) - mean) * rstd, g4.z, b4.z);
@@ -822,8 +902,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             acquire_slot();
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + k));
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + k));
+              const float4 g4 = *reinterpret_cast<const float4*>(gam + c * 16 + k);
+              const float4 b4 = *reinterpret_cast<const float4*>(bet + c * 16 + k);
               *reinterpret_cast<float4*>(s2 + stage_off(lane, k >> 2)) =
                   make_float4(fmaf((__uint_as_float(v[k]) - mean) * rstd, g4.x, b4.x),
                               fmaf((__uint_as_float(v[k + 1]) - mean) * rstd, g4.y, b4.y),
@@ -835,7 +915,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (lane == 0) bulk_wait0();  // all global writes of this warp are complete before the CTA exits
+    PROF_MARK(5)
+    if (elect_one()) bulk_wait0();  // all global writes of this warp are complete before the CTA exits
+    __syncwarp();
+    PROF_MARK(7)
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) prof[((size_t)blockIdx.x * NUM_EPI_WARPS + ew) * 8 + k] = prof_c[k];
+    }
+#undef PROF_MARK
   }
 
   tc_fence_before();
@@ -893,7 +981,7 @@ static int encode_tile_map(CUtensorMap* map, const void* base, int elem_bytes, i
 
 template <int BN, int CG, int EPI>
 static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
-  using S = GemmSmem<BN, CG, epi_nbuf(EPI)>;
+  using S = GemmSmem<BN, CG, epi_nbuf(EPI), EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -950,7 +1038,10 @@ static int launch_gemm_epi(const mfv_gemm_args* a, cudaStream_t stream) {
     if (a->ln_out_f32 && a->C3) return MFV_ERR_ARG;
   }
   p.row_sum = nullptr;
-  if (a->row_sum) {
+  p.dbg_prof = nullptr;
+  if (((a->dtype_flags >> 20) & 1) && a->row_sum && a->epilogue != MFV_EPI_ATOMIC_F32) {
+    p.dbg_prof = reinterpret_cast<unsigned long long*>(a->row_sum);
+  } else if (a->row_sum) {
     if (BN != 384 || a->epilogue != MFV_EPI_ATOMIC_F32 || a->N % 384 != 0) return MFV_ERR_ARG;
     p.row_sum = a->row_sum;
   }
@@ -1094,7 +1185,7 @@ static int launch_gemm(const mfv_gemm_args* a, cudaStream_t stream) {
 // split count, groups and operand formats; problem 1's operand / output maps ride in the tmC2 / tmC3 / tmAux slots.
 static int launch_wgrad_pair(const mfv_gemm_args* a, const mfv_gemm_args* b, cudaStream_t stream) {
   constexpr int BN = 384, CG = 2;
-  using S = GemmSmem<BN, CG, epi_nbuf(MFV_EPI_F32)>;
+  using S = GemmSmem<BN, CG, epi_nbuf(MFV_EPI_F32), MFV_EPI_F32>;
   static bool attr_set = false;
   if (!attr_set) {
     MFV_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG, MFV_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -18,7 +18,7 @@ def timeit(fn, reps=20):
         a.record(); g.replay(); b.record(); torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / reps)
     return best * 1e3
-for N, bn, modes in ((384, 384, (0, 1, 2, 3)),):
+for N, bn, modes in ((384, 384, tuple(range(13))),):
     for K in (1536, 3072):
         for tiles in (2,):
             M = tiles // 2 * 256
