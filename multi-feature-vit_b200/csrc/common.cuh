@@ -429,6 +429,28 @@ __device__ __forceinline__ void gelu_erf2(float& a, float& b) {
   const f32x2 x = pack2(a, b);
   unpack2(mul2(x, normal_cdf_fast2(x, mul2(x, x))), a, b);
 }
+// Forward GELU of a pair with ONE MUFU per pair: Phi(x) = 1/2 + 1/2 tanh(x H(x^2)) (the logistic polynomial above, halved:
+// the same H as gelu_tanh_both2) with the tanh taken on both elements at once by tanh.approx.f16x2.  The GELU epilogue of
+// the fc1 GEMM is bound by the XU pipe in its math phase (4 warps per scheduler x 64 MUFU x 8 clk per 32-column piece:
+// tests/gpu_epi_prof.py); this form issues a quarter of the MUFUs.  Error budget against the exact GELU: the f16 argument
+// (|dPhi| <= 5.5e-5) and the f16 tanh (half an ulp below 1: |dPhi| <= 1.2e-4), i.e. |dg| <= 1.7e-4 |x| - below half an ulp
+// of the fp16 value the result is stored as (2.4e-4 |g| .. 4.9e-4 |g|) wherever |g| > |x| / 2, i.e. for every x > 0.
+__device__ __forceinline__ void gelu_tanh_h2(float& a, float& b) {
+  const f32x2 x = pack2(a, b);
+  const f32x2 x2 = mul2(x, x);
+  f32x2 hh = fma2(splat2(1.1190779787284555e-06f), x2, splat2(-3.058092624996789e-05f));
+  hh = fma2(hh, x2, splat2(-0.00012486183550208807f));
+  hh = fma2(hh, x2, splat2(0.03646879270672798f));
+  hh = fma2(hh, x2, splat2(0.7978281378746033f));
+  float z0, z1;
+  unpack2(mul2(hh, x), z0, z1);
+  uint32_t zh, th;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(zh) : "f"(z1), "f"(z0));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(zh));
+  const float2 t = unpack_f16(th);
+  unpack2(mul2(x, fma2(splat2(0.5f), pack2(t.x, t.y), splat2(0.5f))), a, b);
+}
+
 // gelu and gelu' of a pair
 __device__ __forceinline__ void gelu_erf_both2(float xa, float xb, f32x2& g, f32x2& dg) {
   const f32x2 x = pack2(xa, xb);

@@ -29,6 +29,7 @@ constexpr int EPI_BUF = 2048;                 // one staging slot: 32 rows x 64 
 // the pre-GELU tiles of BOTH pieces of a tile are requested at tile start - with three, the second one waited for the
 // previous tile's last store and its L2 latency was exposed, 12 % of the stall samples in profiles/r01_summary.md)
 constexpr int epi_nbuf(int epi) { return epi == MFV_EPI_DGELU ? 4 : 3; }
+constexpr bool GELU_H2 = false;               // forward GELU through tanh.approx.f16x2 (one MUFU per pair), see common.cuh
 constexpr int MAX_STAGES = 6;                 // barrier slots reserved per operand ring
 constexpr int AUX_BARS = 2 * NUM_EPI_WARPS;   // aux (residual / pre-GELU) TMA loads: 2 in flight per epilogue warp
 
@@ -703,7 +704,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
             publish(&tmC, st0, n0, row0, g, false);
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) gelu_erf2(f[k], f[k + 1]);
+            for (int k = 0; k < 32; k += 2) {
+              if (GELU_H2) gelu_tanh_h2(f[k], f[k + 1]); else gelu_erf2(f[k], f[k + 1]);
+            }
             uint8_t* st1 = slot_ptr(use);
             acquire_slot();
 #pragma unroll
