@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "mfvit_internal.h"
 
+#include <stdlib.h>
+
 namespace mfv {
 
 constexpr int FA_THREADS = 160;  // warps 0..3: softmax + epilogue (TMEM lane quarter = warp), warp 4: TMA + MMA issue
@@ -306,7 +308,7 @@ template <bool QKV_F16>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmG, const __nv_bfloat16* __restrict__ o,
-                   const float* __restrict__ lse, int S, int H, int NK, float scale) {
+                   const float* __restrict__ lse, int S, int H, int NK, float scale, unsigned long long* prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int TILE = NK * 128;           // [NK][64] bf16, 128B-swizzled (multiple of 2 KB)
@@ -468,6 +470,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   } else {
     // ------------------------------------------------------------------------------------------ compute warps
     griddep_wait();
+    // phase clocks (measurement aid, MFVIT_ATTN_PROF): 0 prologue (loads, conversion, delta), 1 wait for S / dP,
+    // 2 TMEM read + P / dS math, 3 wait for the previous step's MMAs, 4 P / dS tiles to smem, 5 dK / dV read-out,
+    // 6 dQ read-out and drain
+    long long prof_t = prof ? clock64() : 0;
+    unsigned long long prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define FB_MARK(slot)                                    \
+  if (prof) {                                            \
+    const long long now_ = clock64();                    \
+    prof_c[slot] += (unsigned long long)(now_ - prof_t); \
+    prof_t = now_;                                       \
+  }
     const int tid = threadIdx.x;  // 0..511
     const int q = warp & 3;       // TMEM lane quarter
     const int cseg = warp >> 2;   // 32-column segment
@@ -553,6 +566,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
+    FB_MARK(0)
     for (int n = 0; n < n_steps; ++n) {
       const int j = n / n_t, i = n % n_t;
       const int qrows = rows_of(i), nk = r16(rows_of(j));
@@ -560,6 +574,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const int r = q * 32 + lane;
       mbar_wait(bar_sdp, (uint32_t)(n & 1));
       tc_fence_after();
+      FB_MARK(1)
       uint32_t pk[16], dk[16];
       if (active) {
         const float l2 = sLse[i * 128 + r], dl = sDelta[i * 128 + r];
@@ -586,7 +601,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sdp_free);
+      FB_MARK(2)
       if (n > 0) mbar_wait(bar_mma, (uint32_t)((n - 1) & 1));  // the previous step's MMAs have finished reading P / dS
+      FB_MARK(3)
       if (active) {
         const uint32_t off = (uint32_t)((cseg >> 1) * 16384 + r * 128);
 #pragma unroll
@@ -599,6 +616,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_pds);
+      FB_MARK(4)
       if (i == n_t - 1) {  // dK_j, dV_j are complete once this step's MMAs retire
         mbar_wait(bar_mma, (uint32_t)(n & 1));
         tc_fence_after();
@@ -615,6 +633,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_free);
         if (rows_ok) stage_store(f, cseg < 2 ? 1 : 2, cseg & 1, j * 128 + q * 32);
+        FB_MARK(5)
       }
     }
     {  // dQ: tile = cseg >> 1 (lanes = its queries), columns (cseg & 1) * 32
@@ -631,6 +650,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+    FB_MARK(6)
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(prof + warp * 8 + k, prof_c[k]);
+      if (warp == 0) atomicAdd(prof + FB_CWARPS * 8, 1ULL);
+    }
+#undef FB_MARK
   }
   tc_fence_before();
   __syncthreads();
@@ -1673,20 +1700,23 @@ int attn_bwd_tc(const void* qkv, int qkv_is_f16, const void* o, const void* d_o,
   cfg.attrs = attr;
   cfg.numAttrs = na;
   const __nv_bfloat16* op = reinterpret_cast<const __nv_bfloat16*>(o);
+  // measurement aid: MFVIT_ATTN_PROF = device address (decimal) of 16 x 8 + 1 uint64 counters (tests/gpu_attn_prof.py)
+  unsigned long long* prof = nullptr;
+  if (const char* e = getenv("MFVIT_ATTN_PROF")) prof = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 10));
   if (qkv_is_f16) {
     static bool set = false;
     if (!set) {
       MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set = true;
     }
-    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<true>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale));
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<true>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale, prof));
   } else {
     static bool set = false;
     if (!set) {
       MFV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set = true;
     }
-    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<false>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale));
+    MFV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel<false>, tmQKV, tmDO, tmG, op, lse, (int)S, (int)H, NK, scale, prof));
   }
   MFV_LAUNCH_CHECK();
   return MFV_OK;

@@ -278,7 +278,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          if (p.dbg_mma) {
+          if (p.dbg_mma && p.dbg_mma < 13) {
             if (rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
             __syncwarp();
             if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -286,15 +286,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (elect_one()) {
           // the leader's barrier collects the bytes of both CTAs' loads
+          // measurement aid: dbg_mma 13 = B loads only, 14 = A loads only (which operand's delivery costs what)
+          const bool ld_a = p.dbg_mma != 13, ld_b = p.dbg_mma != 14;
           if (rank == 0)
-            mbar_arrive_expect_tx(&full_bar[stage], (S::STAGE_BYTES - S::A_BYTES + p.rows_cta * BK * 2) * CG);
-          if (!p.a_mn) {
+            mbar_arrive_expect_tx(&full_bar[stage], ((ld_b ? S::STAGE_BYTES - S::A_BYTES : 0) + (ld_a ? p.rows_cta * BK * 2 : 0)) * CG);
+          if (!ld_a) {
+          } else if (!p.a_mn) {
             load(sa, mapA, &full_bar[stage], kb * BK, m0, g);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, mapA, &full_bar[stage], m0 + j * 64, kb * BK, g);
           }
-          if (BN == 384) {
+          if (!ld_b) {
+          } else if (BN == 384) {
             // pair tile = UMMA N=256 (each CTA supplies rows [rank*128, +128) of it) + UMMA N=128 (rows 256 + rank*64)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {

@@ -27,3 +27,11 @@ for tag, N, K, sp in (("qkv ", 1152, 384, 6), ("proj", 384, 384, 12), ("fc1 ", 1
         return ops.gemm(dy, x, dw, M=N, N=K, K=M, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=M * K, c_gstride=N * K,
                         a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, splits=sp, dtype_flags=fl)
     print("%s splits %d: full %.1f  nostore %.1f  noepi %.1f us" % (tag, sp, timeit(lambda: run(0)), timeit(lambda: run(512)), timeit(lambda: run(256))), flush=True)
+# mainloop only, with and without the TMA loads (stale shared memory): what bounds the MN-major mainloop
+for tag, N, K, sp in (("qkv ", 1152, 384, 6), ("fc1 ", 1536, 384, 6), ("fc2 ", 384, 1536, 3)):
+    dy = torch.randn(G, M, N, device=dev).bfloat16(); x = torch.randn(G, M, K, device=dev).bfloat16()
+    dw = torch.zeros(G, N, K, device=dev)
+    def run(fl):
+        return ops.gemm(dy, x, dw, M=N, N=K, K=M, G=G, lda=N, ldb=K, ldc=K, a_gstride=M * N, b_gstride=M * K, c_gstride=N * K,
+                        a_mn=True, b_mn=True, epilogue=EPI_ATOMIC_F32, splits=sp, dtype_flags=fl)
+    print("%s splits %d mainloop only: with loads %.1f  without %.1f us" % (tag, sp, timeit(lambda: run(256)), timeit(lambda: run(256 | (1 << 16)))), flush=True)
