@@ -78,12 +78,15 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Started BEFORE the warm-up steps: the first nvidia-smi answer on a fresh box can take longer than the whole
+        timed region (20 steps are ~90 ms), which left the record without a single sample."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -91,32 +94,58 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_ready(self, timeout=15.0):
+        """Block until the sampler has delivered its first row (or the timeout passes)."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t_end is None:
+            self.t_end = time.time()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+        def digest(rows):
+            sm, smax, reasons = [], None, set()
+            for _, r in rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    smax = float(f[1])
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, smax, reasons
+
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for r in self.rows if lo <= r[0] <= self.t_end + 0.02]
+        sm, smax, reasons = digest(inside)
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+               "samples": len(sm), "window": "the device-resident and end-to-end timed regions"}
+        if not sm:  # nothing landed inside the window: say so and give what the whole run saw
+            sm, smax, reasons = digest(self.rows)
+            out.update({"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                        "samples": 0, "samples_whole_run": len(sm)})
+        return out
 
 
 def measured_peaks():
@@ -415,6 +444,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # nvidia-smi loop: up and answering before the timed regions begin
+    if rank == 0:
+        sampler.start()
     # ---- warm-up (allocations, cudaFuncSetAttribute, NCCL channels)
     for i in range(args.warmup):
         trainer.step(*dev_batches[i % nb])
@@ -427,9 +459,9 @@ def main():
         barrier()
 
     # ---- timed: device-resident inputs
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.wait_ready()
+        sampler.begin()
     launches0 = lib.mfv_launch_count() + trainer.graph_replays * trainer.graph_launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -476,6 +508,8 @@ def main():
     e_end.record()
     barrier()
     e2e_ms = e_start.elapsed_time(e_end)
+    if rank == 0:
+        sampler.end()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed: the same loop fed by the paired uint8 input pipeline (mfvit.data): pinned uint8

@@ -32,7 +32,7 @@ def classify(launches):
         if "fusion_fwd_kernel" in n or "fus2_ln0_kernel" in n:  # single-kernel / batched fusion forward
             seen_fusion = True
         if "gemm_bf16_kernel" in n:
-            m = re.search(r"gemm_bf16_kernel<\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+)>", n)
+            m = re.search(r"gemm_bf16_kernel<\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+),\s*(?:\(int\))?(\d+)(?:,\s*(?:\(int\))?\d+)?>", n)
             epi = int(m.group(3)) if m else -1
             l["kernel"] = "gemm<%s,%s,epi%s>" % (m.group(1), m.group(2), m.group(3)) if m else "gemm"
             l["cls"] = "gemm_fwd" if not seen_fusion else ("gemm_wgrad" if epi == 4 else "gemm_dgrad")
