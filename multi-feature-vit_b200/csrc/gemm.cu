@@ -75,12 +75,13 @@ struct GemmParams {
 };
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (cta_group::2) computes 256 x BN; each CTA stages its own
-// 128 rows of A and HALF of the B tile, so the L2->SMEM ingest per MMA cycle is halved (128x128 tiles need 128 B/clk/SM,
-// about twice what an SM can ingest - measured 52 % of the tensor peak; the 256 x 256 pair needs 64 B/clk/SM).
+// 128 rows of A and HALF of the B tile, so the operand bytes per UMMA cycle are halved (128 x 128 single-CTA tiles: measured
+// 52 % of the tensor peak).
 // BN = 384 (pairs only): the 256 x 384 output tile of a CTA pair is two UMMAs per k-step (N = 256 and N = 128) into one
 // 384-column accumulator - for the N = 384 GEMMs (proj, fc2, every dgrad, qkv/fc1 wgrad) the A operand is then read from
-// L2 exactly once instead of three times.  These kernels are L2->SM bandwidth bound (about 10 TB/s on the chip, measured:
-// the mainloop-only time of every shape tracks its tile traffic), so tile traffic is what sets their speed.
+// L2 exactly once instead of three times.  With the UMMAs issued from uniform control flow (see elect_one() in common.cuh)
+// the mainloops are UMMA-bound: 820 clk per k-block for the 256 x 384 tile (768 at the peak), 550 for 256 x 256 (512), with
+// or without the operand loads, K- or MN-major, 2 to 6 stages (tests/gpu_ring_probe*.py).
 template <int BN, int CG, int NBUF, int EPI>
 struct GemmSmem {
   static_assert(BN != 384 || CG == 2, "384-wide tiles need a CTA pair");
@@ -1265,7 +1266,7 @@ extern "C" int mfv_gemm(const mfv_gemm_args* a, void* stream) {
     return MFV_ERR_ARG;
   if (a->epilogue == MFV_EPI_GELU && !a->C2) return MFV_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // Tile selection (0 = auto).  These GEMMs are L2->SM bandwidth bound, so the widest tile that fits wins: CTA pairs
+  // Tile selection (0 = auto).  The widest tile that fits wins (fewest operand re-reads, fewest epilogue pieces): CTA pairs
   // (256 rows) whenever M allows, 384 columns when N is exactly 384 (A read once), else 256 columns for N >= 512.
   int bn = a->block_n;
   int cg = a->cta_group;

@@ -121,7 +121,7 @@ int streamk_mask() {
 }
 // B-operand multicast between two CTA pairs in the 384-wide GEMMs (gemm.cu, MC kernels): MFVIT_GEMM_MC=1.  Off by
 // default: it takes 13 % off the L2 traffic of an fc2-shaped GEMM (152 -> 132 MB, ncu lts__t_bytes) and nothing off its
-// duration (25.9 us cold either way; step 4.71 vs 4.74 ms) - what bounds these mainloops is per SM, not L2 bytes.
+// duration (25.9 us cold either way; step 4.71 vs 4.74 ms) - these mainloops are UMMA-bound, not bound by L2 bytes.
 static int g_opt_gemm_mc = -1;
 bool gemm_multicast_enabled() {
   if (g_opt_gemm_mc < 0) g_opt_gemm_mc = env_flag("MFVIT_GEMM_MC", 0, '1');
