@@ -212,8 +212,17 @@ class MFViTCATrainer:
             # it is all-reduced (NCCL, asynchronously) while the next segment computes; then - or at once on one GPU -
             # the optimizer steps that slice on its own stream.
             d = lay.depth
-            nseg = max(1, int(os.environ.get("MFVIT_DP_SEGMENTS", "3")))
-            cuts = sorted({(d * k) // nseg for k in range(nseg + 1)}, reverse=True)
+            # Cut points (block indices, descending): three equal segments by default; MFVIT_DP_SEGMENTS=n asks for n,
+            # MFVIT_DP_CUTS="6,2" sets them explicitly.  Shrinking the last segment (the one whose all-reduce nothing
+            # hides) was measured at 2 GPUs and is within the run-to-run spread: 8.49 (thirds) / 8.53 (6,2) / 8.45 (6,1) /
+            # 8.54 (5,1) / 8.50 ms (7,3,1) - what stays exposed (~0.3 ms) is not that segment's bytes.
+            env_cuts, env_nseg = os.environ.get("MFVIT_DP_CUTS", ""), os.environ.get("MFVIT_DP_SEGMENTS", "")
+            if env_cuts:
+                inner = {min(max(int(c), 0), d) for c in env_cuts.split(",") if c.strip()}
+            else:
+                nseg = max(1, int(env_nseg)) if env_nseg else 3
+                inner = {(d * k) // nseg for k in range(nseg + 1)}
+            cuts = sorted(inner | {0, d}, reverse=True)
             segments = [(cuts[i] - 1, cuts[i + 1]) for i in range(len(cuts) - 1)]
             main = torch.cuda.current_stream()
             if prezero:
