@@ -383,6 +383,22 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
   auto res16 = [&](int c) -> const void* { return dx32 ? nullptr : p->dx16[c]; };
   // final norm
   // each LN backward also emits colsum(dx) = bias gradient of the Linear feeding that residual add (fc2 / proj)
+  // The bf16 patch matrix the conv weight-gradient GEMM reads (the im2col-free forward never wrote one) depends on the
+  // input images only: it is built on the weight-gradient lane at the START of the backward, not in front of that GEMM
+  // at its end, where it sat on the chain the optimizer waits for (2 x 9 us at 32 pairs).  Every later launch on `sw`
+  // and the joins in front of the tail order it before the GEMM.
+  const bool patch_rebuild = !p->stop_grad_conv1 && patch_tma_enabled() && C == 384 && p->img / 16 <= 128;
+  if ((flags & MFV_BWD_HEAD) && patch_rebuild && ss) {
+    RC(fork(1));
+    const long long rows_pe0 = p->B * p->np;
+    for (int g = 0; g < G; ++g) {
+      if (!p->images[g]) return MFV_ERR_ARG;
+      RCP(PROF_PATCHIFY, mfv_patchify(p->images[g],
+                                      reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(v.patches_b())) + (long long)g * rows_pe0 * 768,
+                                      0, nullptr, p->B, p->img, sw));
+    }
+    RC(side_done(1));
+  }
   if (flags & MFV_BWD_HEAD)
     RCP(PROF_LN_BWD, mfv_layernorm_bwd(nullptr, p->dtokens, nullptr, nullptr, v.x(last), v.mean(last), v.rstd(last), v.w32(p->off_norm_w),
                          dx32 ? p->dx[cur] : nullptr, p->dx16[cur], v.gr(p->off_norm_w), v.gr(p->off_norm_b),
@@ -433,9 +449,8 @@ extern "C" int mfv_vit_backward_range(const mfv_vit_plan* p, void* stream, int b
   RCP(PROF_EMBED_BWD, mfv_embed_finish_bwd(p->dx[cur], p->dacc, p->stop_grad_conv1 ? nullptr : v.gr(p->off_pe_b), v.gr(p->off_cls), G,
                           p->B, p->np, C, p->P, st));
   if (!p->stop_grad_conv1) {
-    if (patch_tma_enabled() && C == 384 && p->img / 16 <= 128) {
-      // the forward never wrote a patch matrix: build the bf16 one the weight-gradient GEMM reads, here, off the
-      // critical path of the step (nothing later in the backward depends on it)
+    if (patch_rebuild && !ss) {
+      // no side stream (MFVIT_SIDE_STREAM=0): the patch matrix is built here, in front of its only reader
       for (int g = 0; g < G; ++g) {
         if (!p->images[g]) return MFV_ERR_ARG;
         RCP(PROF_PATCHIFY, mfv_patchify(p->images[g],

@@ -44,6 +44,7 @@ class FlatParams:
 
 
 class MFViTCATrainer:
+    prezero = False     # set from MFVIT_PREZERO in __init__ (class default for objects built without it)
     local_only = False  # True: never all-reduce (bench.py's same-work single-GPU reference inside a data-parallel run)
 
     def __init__(self, fusion, vit_cxr, vit_enh, lr=1e-3, momentum=0.9, weight_decay=0.0, process_group=None,
@@ -88,6 +89,11 @@ class MFViTCATrainer:
         # the step at the end - what the overlap hides (0.17 ms of HBM-bound work) is given back by the three extra
         # joins of the weight-gradient side stream at the segment boundaries - so it stays off by default.
         self.overlap_optimizer = os.environ.get("MFVIT_OVERLAP_OPT", "0") == "1"
+        # MFVIT_PREZERO=1 (opt-in): the zero-fill of the gradient buffer the split-K weight gradients add into (173 MB,
+        # 29 us of HBM writes) runs on a second stream beside the forward instead of in front of the backward.  Measured
+        # at 32 pairs: 4.55 ms per step with it, 4.53 without - the forward's epilogues feel the extra HBM writes more
+        # than the backward feels the fill - so it stays off.
+        self.prezero = os.environ.get("MFVIT_PREZERO", "0") == "1"
         self._opt_stream = None
         self._engine_stepped = False
         self._pending = []
@@ -166,7 +172,7 @@ class MFViTCATrainer:
         lay = eng.layout
         target = target.long()  # MAIN_CA:859 (a no-op for int64 labels)
         enc_grads = eng.any_requires_grad()  # frozen backbones (MAIN_CA:298-305 without --semi-supervised): no backward
-        prezero = reduce_async and enc_grads and self.overlap_optimizer
+        prezero = enc_grads and (self.prezero or (reduce_async and self.overlap_optimizer))
         if prezero:  # the 173 MB zero-fill of the gradient buffer runs beside the forward instead of in front of the backward
             if self._opt_stream is None:
                 self._opt_stream = torch.cuda.Stream(device=device)
