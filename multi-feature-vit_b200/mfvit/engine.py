@@ -111,7 +111,9 @@ class _Workspace:
         self.patches_bf = e(G * B * lay.np * 768, bf) if dual else None
         self.xn_bf = e(nxn * G * M * C_, bf) if dual else None
         self.attn_o_bf = e(nblk * G * M * C_, bf) if dual else None
-        self.gact_bf = e(G * M * Hd, bf) if dual else None  # one slot: recomputed per block in the backward
+        # one slot (recomputed per block by the fc2-dgrad epilogue), or one per block with MFVIT_GELU_TWIN=1 (stored by fc1)
+        twin = os.environ.get("MFVIT_GELU_TWIN", "0") == "1"
+        self.gact_bf = e((nblk if twin else 1) * G * M * Hd, bf) if dual else None
         self.bwd = None
 
     def ensure_bwd(self, lay, device):
