@@ -82,7 +82,10 @@ typedef struct {
   int32_t epilogue;
   int32_t splits;  /* split-K factor (only with MFV_EPI_ATOMIC_F32) */
   int32_t block_n; /* 0 = auto, else 64/128/256 */
-  int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere) */
+  int32_t dtype_flags; /* bit0: A is fp16, bit1: B is fp16, bit2: 16-bit outputs are fp16 (default bf16 everywhere).
+                          Bits 8..20 are measurement aids (tests/gpu_*probe*.py, gpu_epi_prof.py) and must be 0 in a real
+                          call: 8 accumulators released unread, 9 bulk stores skipped, 10..11 stream-K probes, 12..15 operand
+                          ring depth, 16..19 UMMA / operand-load probes, 20 per-warp phase clocks into row_sum */
   int32_t cta_group;   /* 0 = auto, 1 = 128-row tiles, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) */
   int32_t rows_per_cta; /* 384-wide pair tiles with K-major A only: 0 = default (128), or 96 = 192-row pair tiles
                          * (more, smaller tiles: fills the SMs better for M ~ 6-12 k; opt-in, see gemm.cu)           */
@@ -309,7 +312,8 @@ typedef struct {
   int32_t fwd_f16;
   int32_t reserved;
   void* patches_bf; void* xn_bf; void* attn_o_bf; /* same slot layout as patches / xn / attn_o */
-  void* gact_bf; /* bf16 [G][M][hidden], ONE slot: recomputed per block by the fc2-dgrad epilogue in the backward */
+  void* gact_bf; /* bf16 [G][M][hidden], ONE slot: recomputed per block by the fc2-dgrad epilogue in the backward
+                    (MFVIT_GELU_TWIN=1: [depth] slots, written by the fc1 epilogue of the forward instead) */
   /* backward only */
   const float* dtokens;   /* f32 [G][M][C] */
   float* dx[2];           /* f32 [G][M][C] ping-pong */

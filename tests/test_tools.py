@@ -40,3 +40,32 @@ def test_ncu_class_summary_of_the_round_2_step(tmp_path):
     assert cls["gemm_wgrad"]["launches_per_step"] == 49
     assert cls["ln_fwd"]["launches_per_step"] == 1 and cls["ln_bwd"]["launches_per_step"] == 25
     assert "patch_embed_kernel" in r.stdout and "fus2_stream_fwd_kernel" in r.stdout
+
+
+def test_clock_sampler_counts_only_rows_inside_the_timed_window():
+    """bench.py's nvidia-smi sampler is started before the warm-up and reports the rows that arrived between begin() and
+    end() (the timed regions); with none inside it says so and falls back to the whole run."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+
+    class _Proc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    row = lambda mhz, cap: "%d, 1965, 700.0, Not Active, Not Active, Not Active, %s" % (mhz, cap)
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.rows = [(10.0, row(1200, "Not Active")), (20.0, row(1965, "Not Active")), (21.0, row(1950, "Active")),
+              (22.0, row(1965, "Not Active")), (30.0, row(900, "Not Active"))]
+    s.t_begin, s.t_end = 19.5, 22.5
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    s2.proc = _Proc()
+    s2.rows = [(10.0, row(1200, "Not Active"))]
+    s2.t_begin, s2.t_end = 19.5, 22.5
+    out2 = s2.stop()
+    assert out2["samples"] == 0 and out2["samples_whole_run"] == 1 and out2["sm_mhz"] == 1200.0
