@@ -44,7 +44,7 @@ struct GemmParams {
   int dbg_mma;            // measurement aid (dtype_flags bits 16..19, epilogue skipped): 1 = no TMA loads (MMAs on stale smem),
                           // 2 / 3 = + only the N=256 / only the N=128 UMMA of a 384-wide tile, 4 = + two N=192 UMMAs
   unsigned long long* dbg_prof;  // measurement aid (dtype_flags bit 20; the buffer rides in row_sum): per epilogue warp,
-                          // clock64 sums of 8 phases - [CTA][16 warps][8], see PROF_MARK
+                          // clock64 sums of 8 phases - [CTA][16 epilogue warps + the UMMA issuer][8], see PROF_MARK
   int dbg_stages;         // measurement aid (dtype_flags bits 12..15, only with the epilogue skipped): operand ring depth;
                           // stages past S::STAGES lie over the unused epilogue rings
   int rows_cta;           // rows of the output tile each CTA owns: 128, or 96 (K-major A only; see launch_gemm_epi)
@@ -360,10 +360,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      // measurement aid (dtype_flags bit 20): slot 16 of the CTA's phase clocks = the issuer: [0] waiting for a free
+      // accumulator, [1] in the k-loop (waits for operands + issue), [2] tiles
+      unsigned long long mprof[3] = {0, 0, 0};
       FragCursor cur;
       cur.init(p, cta_id, num_ctas, total_tiles);
       Frag fr;
       for (; cur.next(p, fr); ++it) {
+        const long long mt0 = p.dbg_prof ? clock64() : 0;
         const TileInfo ti = decode_tile(p, fr.t);
         const int split = ti.split;
         const bool want_rs = S::ONES_BYTES > 0 && (ti.prob ? p.row_sum1 : p.row_sum) != nullptr;
@@ -373,6 +377,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t aphase = (it / NACC) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
+        const long long mt1 = p.dbg_prof ? clock64() : 0;
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -404,6 +409,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
+        if (p.dbg_prof) {
+          const long long mt2 = clock64();
+          mprof[0] += (unsigned long long)(mt1 - mt0); mprof[1] += (unsigned long long)(mt2 - mt1); mprof[2] += 1;
+        }
+      }
+      if (p.dbg_prof && lane == 0) {
+        for (int k = 0; k < 3; ++k) p.dbg_prof[((size_t)blockIdx.x * (NUM_EPI_WARPS + 1) + NUM_EPI_WARPS) * 8 + k] = mprof[k];
       }
     }
   } else {
@@ -929,7 +941,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     PROF_MARK(7)
     if (prof && lane == 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) prof[((size_t)blockIdx.x * NUM_EPI_WARPS + ew) * 8 + k] = prof_c[k];
+      for (int k = 0; k < 8; ++k) prof[((size_t)blockIdx.x * (NUM_EPI_WARPS + 1) + ew) * 8 + k] = prof_c[k];
     }
 #undef PROF_MARK
   }

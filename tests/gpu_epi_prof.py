@@ -12,19 +12,24 @@ PH = ["acc wait", "tmem ld", "slot/aux wait", "convert+sts", "fence+store", "mat
 def h(*s): return (torch.randn(*s, device=dev) * 0.3).half()
 def bf(*s): return (torch.randn(*s, device=dev) * 0.3).bfloat16()
 def f32(*s): return torch.randn(*s, device=dev)
-prof = torch.zeros(148 * 16 * 8, device=dev, dtype=torch.int64)
+prof = torch.zeros(148 * 17 * 8, device=dev, dtype=torch.int64)
 def report(name, fn):
     for _ in range(3): fn(0)
     prof.zero_(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); fn(1 << 20); b.record(); torch.cuda.synchronize()
-    p = prof.view(148, 16, 8).double()
+    pall = prof.view(148, 17, 8).double()
+    p = pall[:, :16]
+    mm = pall[:, 16]
+    mu = mm[:, 2] > 0
+    issuer = ("  || issuer per tile: wait for accumulator %.0f, k-loop %.0f clk (%.1f tiles per pair)"
+              % (float(mm[mu, 0].sum() / mm[mu, 2].sum()), float(mm[mu, 1].sum() / mm[mu, 2].sum()), float(mm[mu, 2].mean()))) if mu.any() else ""
     used = p.sum(2) > 0
     n = int(used.sum())
     mean = (p * used[..., None]).sum((0, 1)) / max(n, 1)
     tot = p.sum(2)
     print("%-18s %6.1f us | warps %4d | total/warp mean %7.0f max %7.0f clk | " % (name, a.elapsed_time(b) * 1e3, n, float(tot.sum() / max(n, 1)), float(tot.max()))
-          + "  ".join("%s %.0f" % (PH[k], float(mean[k])) for k in range(8)), flush=True)
+          + "  ".join("%s %.0f" % (PH[k], float(mean[k])) for k in range(8)) + issuer, flush=True)
 x, w, b = h(2, M, 384), h(2, 1536, 384), f32(2, 1536)
 u, g16 = torch.empty(2, M, 1536, device=dev, dtype=torch.bfloat16), torch.empty(2, M, 1536, device=dev, dtype=torch.float16)
 def gemm_kw(**kw): return kw
