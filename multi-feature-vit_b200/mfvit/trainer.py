@@ -182,18 +182,16 @@ class MFViTCATrainer:
         tok, lease = eng.forward([img_cxr, img_enh], save=enc_grads)
         key = (B, device)
         if key not in self._bufs:
-            self._bufs[key] = (torch.empty_like(tok),
-                               torch.empty(2, B, self.NC, device=device, dtype=torch.float32),
-                               ops.fusion_scratch(tok, B, lay.S, lay.C, self.heads),
-                               torch.empty(B, self.NC, device=device, dtype=torch.float32))
-        dtok, d_x, scratch, d_fused = self._bufs[key]
+            # the loss sums the three heads (MAIN_CA:861), so all three logit gradients are the same [B, NC] tensor: one
+            # buffer, d_fused = its first slice, d_x = the other two, filled by ONE broadcast copy per step
+            dl3 = torch.empty(3, B, self.NC, device=device, dtype=torch.float32)
+            self._bufs[key] = (torch.empty_like(tok), dl3[1:3], ops.fusion_scratch(tok, B, lay.S, lay.C, self.heads), dl3[0], dl3)
+        dtok, d_x, scratch, d_fused, dl3 = self._bufs[key]
         ops.fusion_bwd_join(device)  # the previous step's deferred weight-gradient contraction still reads `scratch`
         fused, x = ops.fusion_fwd(tok, self._pstruct, B, lay.S, lay.C, self.heads, self.NC, saved=scratch)
         loss, dlogits = ops.ce_small(fused, x[0], x[1], target)
         ops.fill_(self._small.grad, 0.0)
-        d_fused.copy_(dlogits)
-        d_x[0].copy_(dlogits)
-        d_x[1].copy_(dlogits)
+        dl3.copy_(dlogits.unsqueeze(0).expand_as(dl3))
         # only dtok is needed by the encoder backward: the fusion's own parameter gradients are contracted on the
         # library's side stream meanwhile and joined below (all buffers they read are owned by the trainer)
         ops.fusion_bwd(tok, self._pstruct, self._gstruct, d_fused, d_x, B, lay.S, lay.C, self.heads, self.NC, dtok=dtok,

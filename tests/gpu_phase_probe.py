@@ -30,12 +30,12 @@ def phase(upto):
     if upto == 1:
         lease.release()
         return
-    dtok, d_x, scratch, d_fused = tr._bufs[(B, dev)]
+    dtok, d_x, scratch, d_fused, dl3 = tr._bufs[(B, dev)]
     ops.fusion_bwd_join(dev)
     fused, x = ops.fusion_fwd(tok, tr._pstruct, B, lay.S, lay.C, tr.heads, tr.NC, saved=scratch)
     loss, dlogits = ops.ce_small(fused, x[0], x[1], t)
     ops.fill_(tr._small.grad, 0.0)
-    d_fused.copy_(dlogits); d_x[0].copy_(dlogits); d_x[1].copy_(dlogits)
+    dl3.copy_(dlogits.unsqueeze(0).expand_as(dl3))
     ops.fusion_bwd(tok, tr._pstruct, tr._gstruct, d_fused, d_x, B, lay.S, lay.C, tr.heads, tr.NC, dtok=dtok, scratch=scratch, defer=True)
     if upto == 2:
         ops.fusion_bwd_join(dev)
