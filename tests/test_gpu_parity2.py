@@ -353,3 +353,39 @@ def test_moco_under_syncbn_and_ddp_world_size_1():
     print(out)
     assert out["ok"], out
     assert out["queue_ptr"] == (16 + 5 * 32) % 65536
+
+
+_OPTION_PROBE = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import e2e_common as E
+(_, _, _), (o_f, o_c, o_e) = E.build_mfvit_pair(seed=23)
+img_c, img_e, tgt = E.synthetic_pair(5, 224, device="cuda")
+out, loss, _ = E.mfvit_step(o_f, o_c, o_e, img_c, img_e, tgt)
+grads = torch.cat([p.grad.detach().float().flatten() for m in (o_f, o_c, o_e) for p in m.parameters() if p.grad is not None])
+torch.save({"loss": loss.detach().cpu(), "out": out.detach().cpu(), "grads": grads.cpu()}, sys.argv[1])
+"""
+
+
+def test_options_that_move_work_between_kernels_leave_the_result_alone(tmp_path):
+    """MFVIT_GELU_TWIN=1 (the bf16 gelu(u) of the fc2 weight gradient stored by fc1 instead of recomputed by the fc2 dgrad
+    epilogue) and MFVIT_FUSE_LN=0 (standalone LayerNorm launches) are read once per process: each runs in its own
+    interpreter and must reproduce the default's loss, logits and gradients (to the rounding of a different but equivalent
+    evaluation order: the recomputed GELU uses the tanh form, the stored one the logistic form)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = {}
+    for tag, env in (("default", {}), ("twin", {"MFVIT_GELU_TWIN": "1"}), ("noln", {"MFVIT_FUSE_LN": "0"})):
+        out = os.path.join(str(tmp_path), tag + ".pt")
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", _OPTION_PROBE % here, out], env=e, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = torch.load(out)
+    base = res["default"]
+    for tag in ("twin", "noln"):
+        got = res[tag]
+        assert (got["out"] - base["out"]).abs().max().item() <= 1e-3, tag
+        assert abs(got["loss"].item() - base["loss"].item()) <= 1e-3, tag
+        cos = F.cosine_similarity(got["grads"].double(), base["grads"].double(), dim=0).item()
+        assert cos >= 0.9999, (tag, cos)
