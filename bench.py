@@ -499,11 +499,11 @@ def main():
     prefetch(0)
     for i in range(e_steps):
         s = i % 2
-        if i + 1 < e_steps:
-            prefetch(i + 1)
         torch.cuda.current_stream().wait_event(ready[s])
         loss_e = trainer.step(*slots[s])
         consumed[s].record()
+        if i + 1 < e_steps:  # enqueued AFTER this step's launch: the host work of the copies runs under the step
+            prefetch(i + 1)
         loss_host = float(loss_e)  # device -> host read of the step's result (synchronises, as MAIN_CA:884 does)
     e_end.record()
     barrier()
