@@ -310,10 +310,10 @@ typedef struct {
    * logits within 2e-3 of the fp32 reference); the backward stays bf16 and reads the *_bf copies written alongside
    * (only when save_for_backward).  fwd_f16 = 0: everything bf16, the *_bf pointers are unused.                        */
   int32_t fwd_f16;
-  int32_t reserved;
+  int32_t gact_bf_per_block; /* 1: gact_bf holds one slot per block, written by the fc1 epilogue of the forward; 0: one slot,
+                                recomputed per block by the fc2-dgrad epilogue of the backward (was a reserved field) */
   void* patches_bf; void* xn_bf; void* attn_o_bf; /* same slot layout as patches / xn / attn_o */
-  void* gact_bf; /* bf16 [G][M][hidden], ONE slot: recomputed per block by the fc2-dgrad epilogue in the backward
-                    (MFVIT_GELU_TWIN=1: [depth] slots, written by the fc1 epilogue of the forward instead) */
+  void* gact_bf; /* bf16 gelu(u) for the fc2 weight gradient: [G][M][hidden] x (gact_bf_per_block ? depth : 1) slots */
   /* backward only */
   const float* dtokens;   /* f32 [G][M][C] */
   float* dx[2];           /* f32 [G][M][C] ping-pong */

@@ -13,7 +13,6 @@ int num_sms();
 bool pdl_enabled();
 bool fuse_ln_enabled();  // MFVIT_FUSE_LN=0: standalone LayerNorm launches instead of the fused proj / fc2 epilogue
 bool dx32_stream_enabled();  // MFVIT_DX32=1: fp32 residual-gradient stream through the LayerNorm backward (default: bf16)
-bool gelu_twin_enabled();  // MFVIT_GELU_TWIN=1: bf16 gelu(u) stored by the fc1 epilogue (one slot per block) instead of recomputed by fc2 dgrad
 bool patch_tma_enabled();  // MFVIT_PATCH_TMA=0: patchify -> GEMM -> embed_finish instead of the im2col-free TMA kernel
 bool gemm_multicast_enabled();  // MFVIT_GEMM_MC (default 0): B multicast between two pairs in the 384-wide GEMMs
 int streamk_mask();           // MFVIT_STREAMK bit mask (runtime.cu)

@@ -101,14 +101,6 @@ bool patch_tma_enabled() {
   if (g_opt_patch_tma < 0) g_opt_patch_tma = env_flag("MFVIT_PATCH_TMA", 1, '0');
   return g_opt_patch_tma == 1;
 }
-// MFVIT_GELU_TWIN=1 (fp16-forward mode): the fc1 epilogue also stores the bf16 copy of gelu(u) the fc2 weight gradient reads
-// (one slot per block in gact_bf - the host side sizes the buffer from the same variable), and the fc2-dgrad epilogue no
-// longer recomputes it.  See vit.cu.
-static int g_opt_gelu_twin = -1;
-bool gelu_twin_enabled() {
-  if (g_opt_gelu_twin < 0) g_opt_gelu_twin = env_flag("MFVIT_GELU_TWIN", 0, '1');
-  return g_opt_gelu_twin == 1;
-}
 bool pdl_enabled() {
   if (g_opt_pdl < 0) g_opt_pdl = env_flag("MFVIT_PDL", 1, '0');
   return g_opt_pdl == 1;

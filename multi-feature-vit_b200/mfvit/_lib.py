@@ -57,7 +57,7 @@ class VitPlan(C.Structure):
                               "r_ln2_w", "r_ln2_b", "r_fc1_w", "r_fc1_b", "r_fc2_w", "r_fc2_b"]]
         + [("images", c_vp * 2)]
         + [(n, c_vp) for n in ["patches", "acc", "x", "xn", "stats", "qkv", "attn_o", "lse", "u", "gact", "tokens"]]
-        + [("save_for_backward", i32), ("stop_grad_conv1", i32), ("fwd_f16", i32), ("reserved", i32)]
+        + [("save_for_backward", i32), ("stop_grad_conv1", i32), ("fwd_f16", i32), ("gact_bf_per_block", i32)]
         + [(n, c_vp) for n in ["patches_bf", "xn_bf", "attn_o_bf", "gact_bf"]]
         + [("dtokens", c_vp), ("dx", c_vp * 2), ("dx16", c_vp * 2)]
         + [(n, c_vp) for n in ["dhid", "dxn", "d_o", "dqkv", "delta", "dacc", "attn_ws"]]

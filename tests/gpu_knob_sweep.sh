@@ -12,4 +12,4 @@ run "MFVIT_WGRAD_PAIR=1"
 run "MFVIT_ROWS96=0"
 run "MFVIT_ROWS96=2"
 run "MFVIT_PREZERO=1"
-run "MFVIT_GELU_TWIN=1"
+run "MFVIT_GELU_TWIN=0"

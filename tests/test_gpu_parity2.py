@@ -368,14 +368,14 @@ torch.save({"loss": loss.detach().cpu(), "out": out.detach().cpu(), "grads": gra
 
 
 def test_options_that_move_work_between_kernels_leave_the_result_alone(tmp_path):
-    """MFVIT_GELU_TWIN=1 (the bf16 gelu(u) of the fc2 weight gradient stored by fc1 instead of recomputed by the fc2 dgrad
-    epilogue) and MFVIT_FUSE_LN=0 (standalone LayerNorm launches) are read once per process: each runs in its own
+    """MFVIT_GELU_TWIN=0 (the bf16 gelu(u) of the fc2 weight gradient recomputed by the fc2 dgrad epilogue instead of stored
+    by fc1) and MFVIT_FUSE_LN=0 (standalone LayerNorm launches) are read once per process: each runs in its own
     interpreter and must reproduce the default's loss, logits and gradients (to the rounding of a different but equivalent
     evaluation order: the recomputed GELU uses the tanh form, the stored one the logistic form)."""
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     res = {}
-    for tag, env in (("default", {}), ("twin", {"MFVIT_GELU_TWIN": "1"}), ("noln", {"MFVIT_FUSE_LN": "0"})):
+    for tag, env in (("default", {}), ("twin", {"MFVIT_GELU_TWIN": "0"}), ("noln", {"MFVIT_FUSE_LN": "0"})):
         out = os.path.join(str(tmp_path), tag + ".pt")
         e = dict(os.environ)
         e.update(env)
