@@ -286,42 +286,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             continue;
           }
           if (elect_one()) {
-          // the leader's barrier collects the bytes of both CTAs' loads
-          // measurement aid: dbg_mma 13 = B loads only, 14 = A loads only (which operand's delivery costs what)
-          const bool ld_a = p.dbg_mma != 13, ld_b = p.dbg_mma != 14;
-          if (rank == 0)
-            mbar_arrive_expect_tx(&full_bar[stage], ((ld_b ? S::STAGE_BYTES - S::A_BYTES : 0) + (ld_a ? p.rows_cta * BK * 2 : 0)) * CG);
-          if (!ld_a) {
-          } else if (!p.a_mn) {
-            load(sa, mapA, &full_bar[stage], kb * BK, m0, g);
-          } else {
+            // the leader's barrier collects the bytes of both CTAs' loads
+            // measurement aid: dbg_mma 13 = B loads only, 14 = A loads only (which operand's delivery costs what)
+            const bool ld_a = p.dbg_mma != 13, ld_b = p.dbg_mma != 14;
+            if (rank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], ((ld_b ? S::STAGE_BYTES - S::A_BYTES : 0) + (ld_a ? p.rows_cta * BK * 2 : 0)) * CG);
+            if (!ld_a) {
+            } else if (!p.a_mn) {
+              load(sa, mapA, &full_bar[stage], kb * BK, m0, g);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, mapA, &full_bar[stage], m0 + j * 64, kb * BK, g);
-          }
-          if (!ld_b) {
-          } else if (BN == 384) {
-            // pair tile = UMMA N=256 (each CTA supplies rows [rank*128, +128) of it) + UMMA N=128 (rows 256 + rank*64)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int nn = n_tile * BN + (j < 2 ? (int)rank * 128 + j * 64 : 256 + (int)rank * 64);
-              if constexpr (MC) {
-                // pair 0 fetches boxes 0 and 1, pair 1 box 2; every box goes to this CTA and to the CTA of the same
-                // pair rank in the other pair (cluster ranks rank and rank + 2)
-                if ((j < 2) != (pq == 0)) continue;
-                const uint16_t mask = (uint16_t)(0x5u << rank);
-                if (!p.b_mn) tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g, mask);
-                else tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g, mask);
-              } else {
-                if (!p.b_mn) load(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g);
-                else load(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g);
-              }
+              for (int j = 0; j < BM / 64; ++j) load(sa + j * 8192, mapA, &full_bar[stage], m0 + j * 64, kb * BK, g);
             }
-          } else if (!p.b_mn) {
-            load(sb, mapB, &full_bar[stage], kb * BK, n0, g);
-          } else {
+            if (!ld_b) {
+            } else if (BN == 384) {
+              // pair tile = UMMA N=256 (each CTA supplies rows [rank*128, +128) of it) + UMMA N=128 (rows 256 + rank*64)
 #pragma unroll
-            for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, mapB, &full_bar[stage], n0 + j * 64, kb * BK, g);
-          }
+              for (int j = 0; j < 3; ++j) {
+                const int nn = n_tile * BN + (j < 2 ? (int)rank * 128 + j * 64 : 256 + (int)rank * 64);
+                if constexpr (MC) {
+                  // pair 0 fetches boxes 0 and 1, pair 1 box 2; every box goes to this CTA and to the CTA of the same
+                  // pair rank in the other pair (cluster ranks rank and rank + 2)
+                  if ((j < 2) != (pq == 0)) continue;
+                  const uint16_t mask = (uint16_t)(0x5u << rank);
+                  if (!p.b_mn) tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g, mask);
+                  else tma_load_3d_cg2_mc(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g, mask);
+                } else {
+                  if (!p.b_mn) load(sb + j * 8192, mapB, &full_bar[stage], kb * BK, nn, g);
+                  else load(sb + j * 8192, mapB, &full_bar[stage], nn, kb * BK, g);
+                }
+              }
+            } else if (!p.b_mn) {
+              load(sb, mapB, &full_bar[stage], kb * BK, n0, g);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / CG / 64; ++j) load(sb + j * 8192, mapB, &full_bar[stage], n0 + j * 64, kb * BK, g);
+            }
           }
           __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -386,25 +386,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sb = sa + S::A_BYTES;
           if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
-            const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
-            if (BN == 384 && pn1 == 0) {
-            } else if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (BN == 384 && pn2 != 0) {
-              const uint64_t db2 = make_smem_desc_sw128(sb + pboff2 + k * b_kadv, b_lbo, 1024u);
-              umma_bf16_cg2(tmem_d + pcol2, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
-              if (want_rs)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
-                umma_bf16_cg2(tmem_d + 384u, da, make_smem_desc_sw128(smem_u32(ones_tile), 8192u, 1024u), idesc3,
-                              (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc_sw128(sa + k * a_kadv, a_lbo, 1024u);
+              const uint64_t db = make_smem_desc_sw128(sb + k * b_kadv, b_lbo, 1024u);
+              if (BN == 384 && pn1 == 0) {
+              } else if (CG == 2) umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (BN == 384 && pn2 != 0) {
+                const uint64_t db2 = make_smem_desc_sw128(sb + pboff2 + k * b_kadv, b_lbo, 1024u);
+                umma_bf16_cg2(tmem_d + pcol2, da, db2, idesc2, (kb > kb0 || k > 0) ? 1u : 0u);
+                if (want_rs)  // columns 384..399 += A . ones: every column is the row sum of A over this k-step
+                  umma_bf16_cg2(tmem_d + 384u, da, make_smem_desc_sw128(smem_u32(ones_tile), 8192u, 1024u), idesc3,
+                                (kb > kb0 || k > 0) ? 1u : 0u);
+              }
             }
-          }
-          // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
-          if (CG == 2) umma_commit_cg2(&empty_bar[stage], MC ? 0xF : 0x3); else umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) {
-            if (CG == 2) umma_commit_cg2(&tfull_bar[as], (uint16_t)(0x3u << (2 * pq))); else umma_commit(&tfull_bar[as]);
-          }
+            // frees the smem stage in BOTH CTAs (their producers wait on their own empty barrier)
+            if (CG == 2) umma_commit_cg2(&empty_bar[stage], MC ? 0xF : 0x3); else umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) {
+              if (CG == 2) umma_commit_cg2(&tfull_bar[as], (uint16_t)(0x3u << (2 * pq))); else umma_commit(&tfull_bar[as]);
+            }
           }
           __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
