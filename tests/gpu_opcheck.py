@@ -360,10 +360,15 @@ def t_ln():
 
 
 # ------------------------------------------------------------------------------------------------------------ attention
-def t_attn(NB, S, H, D, f16=False):
+def t_attn(NB, S, H, D, f16=False, amp=1.0, check_bwd=True):
+    """amp > 1 widens the score range (q and k scaled): block maxima then differ by more than the forward's lazy-rescaling
+    threshold (2^8), so the path that waits for the previous P.V and rescales O is exercised too.  (The fp16-mode backward
+    recomputes the scores from bf16-rounded q / k: with scores this wide that alone moves the gradients by 4-5 %, so the
+    wide fp16 case checks the forward only.)"""
     def f():
         torch.manual_seed(4)
         qkv = torch.randn(NB, S, 3, H, D, device=dev)
+        qkv[:, :, :2] *= amp
         qkv = qkv.half() if f16 else bf(qkv)
         if f16:
             o16, lse, o = ops.attn_fwd(qkv, H, f16=True, bf16_copy=True)
@@ -373,9 +378,11 @@ def t_attn(NB, S, H, D, f16=False):
         q, k, v = [qkv[:, :, i].float().permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3)]
         s = (q @ k.transpose(-1, -2)) * D ** -0.5
         ref = (s.softmax(-1) @ v)
-        tag = "NB%d S%d H%d D%d%s" % (NB, S, H, D, " f16" if f16 else "")
+        tag = "NB%d S%d H%d D%d%s%s" % (NB, S, H, D, " f16" if f16 else "", " amp%g" % amp if amp != 1.0 else "")
         report("attn fwd o " + tag, o.permute(0, 2, 1, 3), ref, 2e-2, rel=True)
         report("attn fwd lse " + tag, lse, torch.logsumexp(s, -1), 1e-3)
+        if not check_bwd:
+            return
         do = bf(torch.randn(NB, S, H, D, device=dev))
         ref.backward(do.float().permute(0, 2, 1, 3))
         dqkv = ops.attn_bwd(qkv, o, do, lse)
@@ -622,6 +629,9 @@ def main():
     run("attn 128/64", t_attn(70, 128, 3, 64), flt)
     run("attn 129/64 f16", t_attn(70, 129, 3, 64, True), flt)
     run("attn 17/64", t_attn(200, 17, 2, 64), flt)
+    run("attn 197/64 f16 wide scores", t_attn(8, 197, 6, 64, True, amp=3.0, check_bwd=False), flt)
+    run("attn 197/64 wide scores", t_attn(8, 197, 6, 64, False, amp=3.0), flt)
+    run("attn 577/64 wide scores", t_attn(2, 577, 6, 64, False, amp=3.0), flt)
     run("fusion", t_fusion, flt)
     run("ema", t_ema, flt)
     run("infonce", t_infonce, flt)
