@@ -130,7 +130,10 @@ def test_gradients_are_linear_in_upstream():
 
     g1, g3 = grads(1.0), grads(3.0)
     for n in g1:
-        assert E.cos(g3[n], g1[n]) > 0.9999, n  # not bit-linear: bf16 rounding of scaled gradients, red.add order
+        # not bit-linear: 3 is not a power of two, so the bf16 residual-gradient stream (24 roundings along the depth, ~1 %
+        # relative noise on the earliest tensors) rounds differently in the two runs.  Measured worst tensor: cls_token
+        # 0.999911, the same on every repetition (tests/gpu_linearity_margin.py); the bar leaves that noise a margin
+        assert E.cos(g3[n], g1[n]) > 0.9998, n
         ratio = (g3[n].norm() / g1[n].norm().clamp_min(1e-20)).item()
         assert abs(ratio - 3.0) < 0.05, (n, ratio)
 
