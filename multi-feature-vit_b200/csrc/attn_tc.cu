@@ -1053,8 +1053,11 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* ring_free = bars + 1 + FL_RING;  // [FL_RING]
   uint64_t* bar_s = bars + 1 + 2 * FL_RING;  // [2] S buffer complete
   uint64_t* bar_p = bar_s + 2;               // P written / O rescaled (4 warp arrivals)
-  uint64_t* bar_o = bar_p + 1;               // P.V of the block complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+  // P.V of block kb complete: bar_o[kb & 1].  TWO barriers, because a softmax warp does not wait for every block's P.V
+  // (lazy rescaling below) and a parity wait cannot tell phase k from phase k + 2: with one barrier per block parity the
+  // phase a warp asks for is always the barrier's current or last one.
+  uint64_t* bar_o = bar_p + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 2);
 
   const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int bh = blockIdx.x, mt = blockIdx.y;
@@ -1066,7 +1069,7 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmO);
       mbar_init(bar_q, 1);
       for (int i = 0; i < FL_RING; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_free[i], 1); }
-      mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
+      mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1); mbar_init(bar_p, 4); mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -1132,7 +1135,7 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             umma_f16_ts(tmem_base + FL_O_COL, tmem_base + (uint32_t)((kb & 1) * 64 + k * 8),
                         make_smem_desc_sw128(va + k * 2048, 8192u, 1024u), idesc_o, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&ring_free[kb % FL_RING]);  // K (used by S) and V of this block are spent
-          umma_commit(bar_o);
+          umma_commit(&bar_o[kb & 1]);
         }
         __syncwarp();
         if (kb + 2 < n_kb) issue_s(kb + 2);     // reuses S buffer kb & 1: ordered behind the P.V just issued
@@ -1162,9 +1165,15 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int k = 0; k < 32; ++k)
           if (32 + k < keys) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(v1[k]));
       }
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      // Lazy reference maximum: m_run (the value the exponents are taken against) moves only when this block's maximum
+      // exceeds it by more than 8 in the log2 domain, so P stays <= 2^8 (exact enough in fp16 / bf16, fp32 accumulation)
+      // and O - whose rescaling needs the previous P.V to have RETIRED - is touched, and that MMA waited for, only then.
+      // The row sum l and the lse use the same reference, so the result is the same softmax.
+      const float m_cand = fmaxf(m_run, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      const bool move = (m_cand - m_run) * scale_log2 > 8.0f;  // always on the first block (m_run = -inf)
+      const float m_new = move ? m_cand : m_run;
       const float mc = m_new * scale_log2;
-      const float alpha = fast_exp2(m_run * scale_log2 - mc);  // 0 on the first block (m_run = -inf)
+      const float alpha = move ? fast_exp2(m_run * scale_log2 - mc) : 1.0f;  // 0 on the first block
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
@@ -1196,11 +1205,11 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_st16(sbuf, lo);
         if (nk > 32) tmem_st16(sbuf + 16u, hi);
       }
-      if (kb > 0) {
-        // O so far belongs to the old maximum: wait for the previous P.V, rescale rows whose maximum moved
-        mbar_wait(bar_o, (uint32_t)((kb - 1) & 1));
+      if (kb > 0 && __any_sync(0xffffffffu, move)) {
+        // O so far belongs to the old reference: wait for the previous P.V, rescale the rows whose reference moved
+        mbar_wait(&bar_o[(kb - 1) & 1], (uint32_t)(((kb - 1) >> 1) & 1));
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha < 1.0f)) {
+        {
           uint32_t o0[32], o1[32];
           tmem_ld32(trow + FL_O_COL, o0);
           tmem_ld32(trow + FL_O_COL + 32u, o1);
@@ -1228,7 +1237,7 @@ attn_fwd_tc_mb_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int row = mt * 128 + warp * 32 + lane;
     if (row < S) lse[(long long)bh * S + row] = (m_run * scale_log2 + log2f(l_run)) * FA_LN2;
     const float inv = 1.f / l_run;
-    mbar_wait(bar_o, (uint32_t)((n_kb - 1) & 1));
+    mbar_wait(&bar_o[(n_kb - 1) & 1], (uint32_t)(((n_kb - 1) >> 1) & 1));
     tc_fence_after();
     float o[64];
     {
